@@ -216,10 +216,22 @@ int32_t nhd_restore(nhd_handle* h);
 int32_t nhd_solve_batch(nhd_handle* h, int32_t n_pods, const nhd_pod* pods,
                         const double* now, nhd_binding* out);
 
-/* Same, but pods/now/out are DEVICE pointers already resident in HBM
- * (pods must be followed by nothing; out receives n_pods records). */
-int32_t nhd_solve_batch_dev(nhd_handle* h, int32_t n_pods, const nhd_pod* pods_dev,
-                            const double* now_dev, nhd_binding* out_dev);
+/*
+ * The three phases of nhd_solve_batch, separately callable so that a caller (or a
+ * benchmark) can keep a batch resident in HBM:
+ *   nhd_stage_batch    validate, de-duplicate descriptors into pod types, host -> device
+ *   nhd_solve_staged   launch the kernels on the staged batch (asynchronous)
+ *   nhd_fetch_bindings wait, device -> host
+ * nhd_sync only waits (bindings stay on the device).
+ */
+int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod* pods, const double* now);
+int32_t nhd_solve_staged(nhd_handle* h);
+int32_t nhd_fetch_bindings(nhd_handle* h, nhd_binding* out);
+int32_t nhd_sync(nhd_handle* h);
+
+/* Debug / tests: run only the snapshot predicate kernel on the staged batch, so that
+ * nhd_read_filter returns the bitmaps before the sweep edits them. */
+int32_t nhd_run_filter_only(nhd_handle* h);
 
 int32_t nhd_last_timing(const nhd_handle* h, nhd_timing* out);
 

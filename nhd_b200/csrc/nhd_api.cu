@@ -1,0 +1,622 @@
+/*
+ * nhd_api.cu — the C-ABI of include/nhd_b200.h on top of the sm_100a kernels.
+ *
+ * Host side of the drop-in boundary: owns the device mirror of the cluster (tiled node
+ * records in HBM), de-duplicates the pod descriptors of a batch into pod types, launches
+ * the snapshot predicate kernel and the select+assign sweep, and (when the node set is
+ * sharded over several GPUs) merges the per-rank feasibility bitmaps with one NCCL
+ * all-reduce.  There is no CPU fallback: every entry point that computes fails with
+ * NHD_ERR_CUDA when no device is usable.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nhd_b200.h"
+#include "nhd_kernels.cuh"
+
+using namespace nhd;
+
+/* ------------------------------------------------------------------ NCCL, resolved at run time */
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_;
+typedef int ncclResult_t_;
+enum { NCCL_UINT64 = 5, NCCL_SUM = 0 };      /* ncclUint64, ncclSum (nccl.h, stable since 2.0) */
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t_ (*GetUniqueId)(ncclUniqueId_*) = nullptr;
+    ncclResult_t_ (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_, int) = nullptr;
+    ncclResult_t_ (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t_ (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t_) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        /* reuse the copy already mapped into the process (e.g. PyTorch's) before opening the system one */
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+    }
+};
+static NcclApi g_nccl;
+
+/* ------------------------------------------------------------------ handle */
+
+struct nhd_handle {
+    nhd_params params;
+    double cap[NHD_MAX_SPEED_CLASSES];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+    ncclComm_t comm = nullptr;
+
+    /* cluster mirror */
+    int n_nodes = 0, n_super = 0, words = 0, max_numa = 1;
+    uint8_t* d_nodes = nullptr;
+    uint8_t* d_snapshot = nullptr;
+    size_t nodes_bytes = 0;
+    bool loaded = false, have_snapshot = false;
+
+    /* staging for records (AoS) */
+    void* d_stage = nullptr;  size_t d_stage_cap = 0;
+    void* h_stage = nullptr;  size_t h_stage_cap = 0;
+    int32_t* d_idx = nullptr; size_t d_idx_cap = 0;
+
+    /* batch */
+    int n_pods = 0, n_types = 0;
+    bool staged = false, solved = false;
+    PodType* d_types = nullptr;     size_t types_cap = 0;
+    int32_t* d_pod_type = nullptr;  double* d_now = nullptr;  nhd_binding* d_out = nullptr;  size_t pods_cap = 0;
+    uint8_t* h_batch = nullptr;     size_t h_batch_cap = 0;     /* pinned: types | pod_type | now */
+    nhd_binding* h_out = nullptr;   size_t h_out_cap = 0;       /* pinned */
+    uint64_t* d_bitmaps = nullptr;  size_t bitmaps_cap = 0;
+    int32_t* d_cursors = nullptr;   size_t cursors_cap = 0;
+    int32_t* d_busy_list = nullptr;
+    uint64_t* d_memo = nullptr;
+    double now0 = 0.0;
+    std::vector<int32_t> pod_type_host;
+
+    nhd_timing timing;
+    std::string err;
+};
+
+static int32_t fail(nhd_handle* h, int32_t code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, NHD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename T>
+static cudaError_t grow_dev(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)256);
+    cudaError_t e = cudaMalloc((void**)&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+template <typename T>
+static cudaError_t grow_pinned(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)256);
+    cudaError_t e = cudaMallocHost((void**)&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+/* ------------------------------------------------------------------ validation */
+
+extern "C" int32_t nhd_validate_node(const nhd_node_rec* r)
+{
+    if (!r) return NHD_ERR_INVALID;
+    const int K = r->n_numa;
+    if (K < 1 || K > NHD_MAX_NUMA) return NHD_ERR_UNSUPPORTED;
+    const int phys = r->phys_cores;
+    const bool smt = r->flags & NHD_NODE_SMT;
+    if (phys < 1 || phys % K != 0) return NHD_ERR_UNSUPPORTED;
+    if ((smt ? 2 * phys : phys) > NHD_MAX_LCORES) return NHD_ERR_UNSUPPORTED;
+    if (r->n_gpus > NHD_MAX_GPUS || r->n_nics > NHD_MAX_NICS) return NHD_ERR_UNSUPPORTED;
+    uint32_t gseen = 0, nseen = 0;
+    for (int k = 0; k < NHD_MAX_NUMA; k++) {
+        if (k >= K && (r->gpu_numa_mask[k] || r->nic_numa_mask[k])) return NHD_ERR_INVALID;
+        if ((gseen & r->gpu_numa_mask[k]) || (nseen & r->nic_numa_mask[k])) return NHD_ERR_INVALID;
+        gseen |= r->gpu_numa_mask[k];
+        nseen |= r->nic_numa_mask[k];
+    }
+    const uint32_t gall = r->n_gpus ? ((1u << r->n_gpus) - 1) : 0;
+    const uint32_t nall = r->n_nics == 32 ? 0xFFFFFFFFu : ((1u << r->n_nics) - 1);
+    if (gseen != gall || nseen != nall) return NHD_ERR_INVALID;
+    if ((r->gpu_used & ~gall) || (r->nic_inuse & ~nall)) return NHD_ERR_INVALID;
+    if (!std::isfinite(r->busy_time)) return NHD_ERR_INVALID;
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_validate_pod(const nhd_pod* p)
+{
+    if (!p) return NHD_ERR_INVALID;
+    if (p->n_groups < 1) return NHD_ERR_INVALID;             /* zero groups crashes the reference (Matcher.py:346) */
+    if (p->n_groups > NHD_MAX_GROUPS) return NHD_ERR_UNSUPPORTED;
+    int cores = p->n_misc, gpus = 0;
+    for (int g = 0; g < p->n_groups; g++) {
+        const nhd_pod_group& pg = p->groups[g];
+        if (pg.n_gpus > NHD_MAX_GROUP_GPUS) return NHD_ERR_UNSUPPORTED;
+        cores += pg.n_proc + pg.n_helpers;
+        for (int j = 0; j < pg.n_gpus; j++) cores += pg.gpu_feeders[j];
+        gpus += pg.n_gpus;
+        if (!(pg.rx_gbps >= 0.0) || !(pg.tx_gbps >= 0.0) || !std::isfinite(pg.rx_gbps) || !std::isfinite(pg.tx_gbps))
+            return NHD_ERR_INVALID;
+    }
+    if (cores > NHD_MAX_POD_CORES || gpus > NHD_MAX_POD_GPUS) return NHD_ERR_UNSUPPORTED;
+    return NHD_OK;
+}
+
+/* numa^(groups+1) enumeration limits of the mapping stage */
+static bool tuple_limits_ok(int K, int G)
+{
+    long nq = 1, np = 1;
+    for (int i = 0; i < G + 1; i++) nq *= K;
+    for (int i = 0; i < G; i++) np *= K;
+    return nq <= NHD_MAX_TUPLES && np <= 64;
+}
+
+/* ------------------------------------------------------------------ lifecycle */
+
+extern "C" void nhd_default_params(nhd_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->nic_bw_avail_percent = 0.9;       /* Node.py:18 */
+    p->min_busy_secs = 30.0;             /* Node.py:107 */
+    p->enable_sharing = 0;               /* Node.py:20 */
+    p->world_size = 1;
+}
+
+extern "C" int32_t nhd_nccl_unique_id(uint8_t out[128])
+{
+    if (!out) return NHD_ERR_INVALID;
+    if (!g_nccl.load()) return NHD_ERR_NCCL;
+    ncclUniqueId_ id;
+    if (g_nccl.GetUniqueId(&id) != 0) return NHD_ERR_NCCL;
+    memcpy(out, id.internal, 128);
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_destroy(nhd_handle* h)
+{
+    if (!h) return NHD_OK;
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaSetDevice(h->params.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
+    cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_batch) cudaFreeHost(h->h_batch);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
+{
+    if (!p || !out) return NHD_ERR_INVALID;
+    *out = nullptr;
+    if (p->enable_sharing) return NHD_ERR_UNSUPPORTED;        /* the reference ships with sharing off (Node.py:20) */
+    if (p->n_speed_classes < 0 || p->n_speed_classes > NHD_MAX_SPEED_CLASSES) return NHD_ERR_INVALID;
+    if (p->world_size < 1 || p->rank < 0 || p->rank >= p->world_size) return NHD_ERR_INVALID;
+    nhd_handle* h = new nhd_handle();
+    h->params = *p;
+    memset(&h->timing, 0, sizeof(h->timing));
+    for (int i = 0; i < NHD_MAX_SPEED_CLASSES; i++)
+        h->cap[i] = p->speed_gbps[i] * p->nic_bw_avail_percent;   /* n.speed*NIC_BW_AVAIL_PERCENT, Node.py:292 */
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || p->device < 0 || p->device >= ndev) {
+        delete h;
+        return NHD_ERR_CUDA;                                    /* no CPU fallback */
+    }
+    *out = h;
+    CK(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p->device));
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    CK(cudaMalloc((void**)&h->d_memo, (size_t)MEMO_SLOTS * 16));
+    CK(cudaMemsetAsync(h->d_memo, 0, (size_t)MEMO_SLOTS * 16, h->stream));
+    CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            FILTER_STAGES * SUPER_BYTES + TYPES_SMEM_MAX * (int)sizeof(PodType)));
+    if (p->world_size > 1) {
+        if (!g_nccl.load()) return fail(h, NHD_ERR_NCCL, "libnccl.so.2 not loadable");
+        ncclUniqueId_ id;
+        memcpy(id.internal, p->nccl_unique_id, 128);
+        ncclResult_t_ r = g_nccl.CommInitRank(&h->comm, p->world_size, id, p->rank);
+        if (r != 0) return fail(h, NHD_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return NHD_OK;
+}
+
+extern "C" const char* nhd_last_error(const nhd_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+/* ------------------------------------------------------------------ cluster mirror */
+
+static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx)
+{
+    const size_t bytes = (size_t)n * sizeof(nhd_node_rec);
+    CK(grow_dev(h->d_stage, h->d_stage_cap, bytes));
+    CK(grow_pinned(h->h_stage, h->h_stage_cap, bytes));
+    memcpy(h->h_stage, recs, bytes);
+    CK(cudaMemcpyAsync(h->d_stage, h->h_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int32_t* d_idx = nullptr;
+    if (idx) {
+        CK(grow_dev(h->d_idx, h->d_idx_cap, (size_t)n * 4));
+        CK(cudaMemcpyAsync(h->d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+        d_idx = h->d_idx;
+    }
+    const int threads = 256, total = n * REC_CHUNKS;
+    ingest_kernel<<<(total + threads - 1) / threads, threads, 0, h->stream>>>(
+        (const uint4*)h->d_stage, d_idx, n, h->d_nodes);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node_rec* recs)
+{
+    if (!h || n_nodes < 0 || (n_nodes > 0 && !recs)) return NHD_ERR_INVALID;
+    CK(cudaSetDevice(h->params.device));
+    int max_numa = 1;
+    for (int i = 0; i < n_nodes; i++) {
+        int32_t v = nhd_validate_node(&recs[i]);
+        if (v != NHD_OK) return fail(h, v, "node %d: record rejected by nhd_validate_node", i);
+        max_numa = std::max(max_numa, (int)recs[i].n_numa);
+    }
+    h->max_numa = max_numa;
+    const int n_super = std::max(1, (n_nodes + SUPER_NODES - 1) / SUPER_NODES);
+    const size_t bytes = (size_t)n_super * SUPER_BYTES;
+    if (bytes != h->nodes_bytes) {
+        cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_busy_list);
+        h->d_nodes = h->d_snapshot = nullptr; h->d_busy_list = nullptr;
+        h->nodes_bytes = 0;
+        CK(cudaMalloc((void**)&h->d_nodes, bytes));
+        CK(cudaMalloc((void**)&h->d_snapshot, bytes));
+        CK(cudaMalloc((void**)&h->d_busy_list, ((size_t)n_super * SUPER_NODES + 64) * 4));
+        h->nodes_bytes = bytes;
+    }
+    h->n_nodes = n_nodes;
+    h->n_super = n_super;
+    h->words = n_super * SUPER_NODES / 64;
+    CK(cudaMemsetAsync(h->d_nodes, 0, bytes, h->stream));     /* padding nodes: inactive */
+    h->loaded = true;
+    h->have_snapshot = false;
+    h->staged = h->solved = false;
+    if (n_nodes == 0) { CK(cudaStreamSynchronize(h->stream)); return NHD_OK; }
+    return upload_records(h, n_nodes, recs, nullptr);
+}
+
+extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx, const nhd_node_rec* recs)
+{
+    if (!h || n < 0 || (n > 0 && (!idx || !recs))) return NHD_ERR_INVALID;
+    if (!h->loaded) return fail(h, NHD_ERR_STATE, "nhd_update_nodes before nhd_load_nodes");
+    CK(cudaSetDevice(h->params.device));
+    for (int i = 0; i < n; i++) {
+        if (idx[i] < 0 || idx[i] >= h->n_nodes) return fail(h, NHD_ERR_INVALID, "node index %d out of range", idx[i]);
+        int32_t v = nhd_validate_node(&recs[i]);
+        if (v != NHD_OK) return fail(h, v, "update %d: record rejected", i);
+        h->max_numa = std::max(h->max_numa, (int)recs[i].n_numa);
+    }
+    if (n == 0) return NHD_OK;
+    return upload_records(h, n, recs, idx);
+}
+
+extern "C" int32_t nhd_read_nodes(nhd_handle* h, int32_t first, int32_t n, nhd_node_rec* out)
+{
+    if (!h || first < 0 || n < 0 || (n > 0 && !out)) return NHD_ERR_INVALID;
+    if (!h->loaded || first + n > h->n_nodes) return fail(h, NHD_ERR_STATE, "range outside the loaded cluster");
+    if (n == 0) return NHD_OK;
+    CK(cudaSetDevice(h->params.device));
+    const size_t bytes = (size_t)n * sizeof(nhd_node_rec);
+    CK(grow_dev(h->d_stage, h->d_stage_cap, bytes));
+    CK(grow_pinned(h->h_stage, h->h_stage_cap, bytes));
+    const int threads = 256, total = n * REC_CHUNKS;
+    export_kernel<<<(total + threads - 1) / threads, threads, 0, h->stream>>>(h->d_nodes, first, n, (uint4*)h->d_stage);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_stage, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_stage, bytes);
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_snapshot(nhd_handle* h)
+{
+    if (!h || !h->loaded) return NHD_ERR_STATE;
+    CK(cudaSetDevice(h->params.device));
+    CK(cudaMemcpyAsync(h->d_snapshot, h->d_nodes, h->nodes_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_snapshot = true;
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_restore(nhd_handle* h)
+{
+    if (!h || !h->loaded || !h->have_snapshot) return NHD_ERR_STATE;
+    CK(cudaSetDevice(h->params.device));
+    CK(cudaMemcpyAsync(h->d_nodes, h->d_snapshot, h->nodes_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return NHD_OK;
+}
+
+/* ------------------------------------------------------------------ batch: stage / solve / fetch */
+
+extern "C" int32_t nhd_sync(nhd_handle* h);
+
+struct PodKey {
+    nhd_pod p;
+    bool operator==(const PodKey& o) const { return memcmp(&p, &o.p, sizeof(nhd_pod)) == 0; }
+};
+struct PodKeyHash {
+    size_t operator()(const PodKey& k) const
+    {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k.p);
+        uint64_t h = 0x9E3779B97F4A7C15ULL;
+        for (size_t i = 0; i < sizeof(nhd_pod) / 8; i++) { h ^= w[i]; h *= 0xff51afd7ed558ccdULL; h ^= h >> 29; }
+        return (size_t)h;
+    }
+};
+
+/* normalise a descriptor so that equal requests compare equal bytewise */
+static nhd_pod canonical_pod(const nhd_pod& in)
+{
+    nhd_pod p;
+    memset(&p, 0, sizeof(p));
+    p.n_groups = in.n_groups; p.map_type = in.map_type; p.n_misc = in.n_misc;
+    p.flags = in.flags & NHD_POD_MISC_SMT;
+    p.hugepages_gb = in.hugepages_gb; p.group_mask = in.group_mask;
+    for (int g = 0; g < in.n_groups && g < NHD_MAX_GROUPS; g++) {
+        nhd_pod_group& o = p.groups[g];
+        const nhd_pod_group& i = in.groups[g];
+        o.n_gpus = i.n_gpus; o.n_proc = i.n_proc; o.n_helpers = i.n_helpers;
+        o.flags = i.flags & (NHD_GRP_PROC_SMT | NHD_GRP_HELPER_SMT | NHD_GRP_HAS_NIC_CORES);
+        for (int j = 0; j < i.n_gpus && j < NHD_MAX_GROUP_GPUS; j++) o.gpu_feeders[j] = i.gpu_feeders[j];
+        o.rx_gbps = i.rx_gbps + 0.0; o.tx_gbps = i.tx_gbps + 0.0;     /* -0.0 -> +0.0 */
+    }
+    return p;
+}
+
+extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod* pods, const double* now)
+{
+    if (!h || n_pods < 0 || (n_pods > 0 && (!pods || !now))) return NHD_ERR_INVALID;
+    if (!h->loaded) return fail(h, NHD_ERR_STATE, "nhd_stage_batch before nhd_load_nodes");
+    CK(cudaSetDevice(h->params.device));
+    h->staged = h->solved = false;
+
+    /* pod types = distinct descriptors (the reference re-derives everything per pod) */
+    std::unordered_map<PodKey, int32_t, PodKeyHash> index;
+    index.reserve(64);
+    std::vector<PodType> types;
+    h->pod_type_host.resize(n_pods);
+    for (int i = 0; i < n_pods; i++) {
+        int32_t v = nhd_validate_pod(&pods[i]);
+        if (v != NHD_OK) return fail(h, v, "pod %d: descriptor rejected by nhd_validate_pod", i);
+        if (!std::isfinite(now[i])) return fail(h, NHD_ERR_INVALID, "pod %d: non-finite clock", i);
+        if (!tuple_limits_ok(h->max_numa, pods[i].n_groups))
+            return fail(h, NHD_ERR_UNSUPPORTED, "pod %d: %d groups on %d-NUMA nodes exceeds the tuple limits", i,
+                        (int)pods[i].n_groups, h->max_numa);
+        PodKey k{canonical_pod(pods[i])};
+        auto it = index.find(k);
+        if (it == index.end()) {
+            PodType t;
+            memset(&t, 0, sizeof(t));
+            make_pod_type(k.p, t);
+            it = index.emplace(k, (int32_t)types.size()).first;
+            types.push_back(t);
+        }
+        h->pod_type_host[i] = it->second;
+    }
+    const int T = (int)types.size();
+    const size_t types_bytes = (size_t)T * sizeof(PodType);
+    const size_t off_pt = (types_bytes + 15) & ~(size_t)15;
+    const size_t off_now = (off_pt + (size_t)n_pods * 4 + 15) & ~(size_t)15;
+    const size_t total = off_now + (size_t)n_pods * 8;
+    CK(grow_pinned(h->h_batch, h->h_batch_cap, total));
+    if (T) memcpy(h->h_batch, types.data(), types_bytes);
+    if (n_pods) {
+        memcpy(h->h_batch + off_pt, h->pod_type_host.data(), (size_t)n_pods * 4);
+        memcpy(h->h_batch + off_now, now, (size_t)n_pods * 8);
+    }
+    CK(grow_dev(h->d_types, h->types_cap, types_bytes));
+    if ((size_t)n_pods > h->pods_cap) {
+        cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
+        h->d_pod_type = nullptr; h->d_now = nullptr; h->d_out = nullptr; h->pods_cap = 0;
+        CK(cudaMalloc((void**)&h->d_pod_type, (size_t)n_pods * 4));
+        CK(cudaMalloc((void**)&h->d_now, (size_t)n_pods * 8));
+        CK(cudaMalloc((void**)&h->d_out, (size_t)n_pods * sizeof(nhd_binding)));
+        h->pods_cap = n_pods;
+    }
+    CK(grow_dev(h->d_bitmaps, h->bitmaps_cap, (size_t)(T + 2) * h->words * 8));
+    CK(grow_dev(h->d_cursors, h->cursors_cap, (size_t)std::max(T, 1) * 2 * 4));
+    if (T) CK(cudaMemcpyAsync(h->d_types, h->h_batch, types_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (n_pods) {
+        CK(cudaMemcpyAsync(h->d_pod_type, h->h_batch + off_pt, (size_t)n_pods * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_now, h->h_batch + off_now, (size_t)n_pods * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->n_pods = n_pods;
+    h->n_types = T;
+    h->now0 = n_pods ? now[0] : 0.0;
+    h->staged = true;
+    return NHD_OK;
+}
+
+static int32_t solve_staged(nhd_handle* h, bool filter_only);
+extern "C" int32_t nhd_solve_staged(nhd_handle* h) { return solve_staged(h, false); }
+extern "C" int32_t nhd_run_filter_only(nhd_handle* h)
+{
+    int32_t r = solve_staged(h, true);
+    if (r != NHD_OK) return r;
+    return nhd_sync(h);
+}
+
+static int32_t solve_staged(nhd_handle* h, bool filter_only)
+{
+    if (!h) return NHD_ERR_INVALID;
+    if (!h->staged) return fail(h, NHD_ERR_STATE, "nhd_solve_staged without a staged batch");
+    CK(cudaSetDevice(h->params.device));
+    const int T = h->n_types, W = h->words;
+    int launches = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+
+    /* 1. snapshot predicate kernel over this rank's node shard */
+    const int ws = h->params.world_size, rk = h->params.rank;
+    const int super_lo = (int)((long)h->n_super * rk / ws), super_hi = (int)((long)h->n_super * (rk + 1) / ws);
+    const size_t bm_bytes = (size_t)(T + 2) * W * 8;
+    if (ws > 1) CK(cudaMemsetAsync(h->d_bitmaps, 0, bm_bytes, h->stream));
+    if (super_hi > super_lo && h->n_pods > 0) {
+        FilterArgs fa;
+        fa.nodes = h->d_nodes; fa.types = h->d_types; fa.n_types = T; fa.n_nodes = h->n_nodes;
+        fa.super_lo = super_lo; fa.super_hi = super_hi; fa.words = W; fa.bitmaps = h->d_bitmaps;
+        fa.now0 = h->now0; fa.min_busy = h->params.min_busy_secs;
+        memcpy(fa.cap, h->cap, sizeof(fa.cap));
+        const int grid = std::min(super_hi - super_lo, h->sm_count * 2);
+        const size_t smem = FILTER_STAGES * SUPER_BYTES + (T <= TYPES_SMEM_MAX ? (size_t)T * sizeof(PodType) : 0);
+        filter_kernel<<<grid, FILTER_THREADS, smem, h->stream>>>(fa);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+
+    /* 2. one collective per batch: every rank contributes its disjoint slice of the bitmaps */
+    if (ws > 1 && h->n_pods > 0) {
+        ncclResult_t_ r = g_nccl.AllReduce(h->d_bitmaps, h->d_bitmaps, bm_bytes / 8, NCCL_UINT64, NCCL_SUM, h->comm, h->stream);
+        if (r != 0) return fail(h, NHD_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        launches++;
+    }
+    CK(cudaEventRecord(h->ev[2], h->stream));
+
+    /* 3. sequential select + assign sweep (replicated on every rank) */
+    if (h->n_pods > 0 && !filter_only) {
+        SweepArgs sa;
+        sa.nodes = h->d_nodes; sa.types = h->d_types; sa.pod_type = h->d_pod_type; sa.now = h->d_now; sa.out = h->d_out;
+        sa.n_pods = h->n_pods; sa.n_types = T; sa.n_nodes = h->n_nodes; sa.words = W;
+        sa.bitmaps = h->d_bitmaps; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list; sa.memo = h->d_memo;
+        sa.min_busy = h->params.min_busy_secs;
+        memcpy(sa.cap, h->cap, sizeof(sa.cap));
+        sweep_kernel<<<1, 32, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    h->timing.n_launches = launches;
+    h->timing.n_types = T;
+    h->solved = true;
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_fetch_bindings(nhd_handle* h, nhd_binding* out)
+{
+    if (!h) return NHD_ERR_INVALID;
+    if (!h->solved) return fail(h, NHD_ERR_STATE, "nhd_fetch_bindings without a solved batch");
+    CK(cudaSetDevice(h->params.device));
+    const size_t bytes = (size_t)h->n_pods * sizeof(nhd_binding);
+    if (bytes) {
+        if (!out) return NHD_ERR_INVALID;
+        CK(grow_pinned(h->h_out, h->h_out_cap, bytes));
+        CK(cudaMemcpyAsync(h->h_out, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (bytes) memcpy(out, h->h_out, bytes);
+    cudaEventElapsedTime(&h->timing.filter_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->timing.exchange_ms, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->timing.sweep_ms, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[3]);
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_sync(nhd_handle* h)
+{
+    if (!h) return NHD_ERR_INVALID;
+    CK(cudaSetDevice(h->params.device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->solved) {
+        cudaEventElapsedTime(&h->timing.filter_ms, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&h->timing.exchange_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&h->timing.sweep_ms, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[3]);
+    }
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_solve_batch(nhd_handle* h, int32_t n_pods, const nhd_pod* pods, const double* now, nhd_binding* out)
+{
+    int32_t r = nhd_stage_batch(h, n_pods, pods, now);
+    if (r != NHD_OK) return r;
+    r = nhd_solve_staged(h);
+    if (r != NHD_OK) return r;
+    return nhd_fetch_bindings(h, out);
+}
+
+extern "C" int32_t nhd_last_timing(const nhd_handle* h, nhd_timing* out)
+{
+    if (!h || !out) return NHD_ERR_INVALID;
+    *out = h->timing;
+    return NHD_OK;
+}
+
+extern "C" int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* words_per_type, uint64_t* words,
+                                   int64_t capacity_words, int32_t* pod_type, int32_t n_pods)
+{
+    if (!h || !h->solved) return NHD_ERR_STATE;
+    CK(cudaSetDevice(h->params.device));
+    if (n_types) *n_types = h->n_types;
+    if (words_per_type) *words_per_type = h->words;
+    const int64_t need = (int64_t)(h->n_types + 2) * h->words;
+    if (words) {
+        if (capacity_words < need) return NHD_ERR_INVALID;
+        CK(cudaMemcpyAsync(words, h->d_bitmaps, (size_t)need * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (pod_type) {
+        if (n_pods < h->n_pods) return NHD_ERR_INVALID;
+        memcpy(pod_type, h->pod_type_host.data(), (size_t)h->n_pods * 4);
+    }
+    return NHD_OK;
+}

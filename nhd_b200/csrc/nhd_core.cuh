@@ -1,0 +1,768 @@
+/*
+ * nhd_core.cuh — per-(pod type, node) placement arithmetic of the B200 solver.
+ *
+ * Everything here is scalar, branch-light bitmask code over the packed
+ * nhd_node_rec (include/nhd_b200.h).  The CUDA kernels (nhd_kernels.cu) call
+ * these functions from the snapshot predicate kernel (one thread per node) and
+ * from the sequential select+assign sweep.  The functions are
+ * __host__ __device__ only so that tests/emu can compile the very same logic
+ * with g++ and diff it against the oracle without a GPU; the shipped library
+ * never runs them on the host.
+ *
+ * What each block replaces in the reference (file:line under /root/reference):
+ *   free_cores / free_gpus / nic tables   nhd/Node.py:250-296, 456-462
+ *   gpu_ok / cpu_ok / nic_first_fit       nhd/Matcher.py:95-276 (+ PCI pruning :295-335)
+ *   choose_mapping (+ the set emulator)   nhd/Matcher.py:337-389, 423-452
+ *   cpu_batch                             nhd/Node.py:502-519
+ *   assign_pod                            nhd/Node.py:663-841, nhd/NHDScheduler.py:289,302-304
+ */
+#pragma once
+
+#include <stdint.h>
+#include "../../include/nhd_b200.h"
+
+#if defined(__CUDACC__)
+#define NHD_HD __host__ __device__ __forceinline__
+#define NHD_HDN __host__ __device__ __noinline__
+#else
+#define NHD_HD inline
+#define NHD_HDN
+#endif
+
+namespace nhd {
+
+/* ---------------------------------------------------------------- bit helpers */
+NHD_HD int popc32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+NHD_HD int popc64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+NHD_HD int ctz32(uint32_t x)      /* x != 0 */
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+NHD_HD int ctz64(uint64_t x)      /* x != 0 */
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+/* index of the n-th (0-based) set bit of x, -1 if fewer */
+NHD_HD int nth_bit32(uint32_t x, int n)
+{
+#ifdef __CUDA_ARCH__
+    unsigned r = __fns(x, 0, n + 1);
+    return r == 0xFFFFFFFFu ? -1 : (int)r;
+#else
+    for (; n > 0 && x; n--) x &= x - 1;
+    return x ? __builtin_ctz(x) : -1;
+#endif
+}
+
+/* 256-bit core mask (logical core c = bit c) */
+struct M256 { uint64_t w[4]; };
+
+NHD_HD M256 m_zero() { M256 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; return r; }
+NHD_HD M256 m_and(const M256& a, const M256& b) { M256 r; for (int i = 0; i < 4; i++) r.w[i] = a.w[i] & b.w[i]; return r; }
+NHD_HD M256 m_or(const M256& a, const M256& b) { M256 r; for (int i = 0; i < 4; i++) r.w[i] = a.w[i] | b.w[i]; return r; }
+NHD_HD M256 m_andnot(const M256& a, const M256& b) { M256 r; for (int i = 0; i < 4; i++) r.w[i] = a.w[i] & ~b.w[i]; return r; }
+NHD_HD int  m_popc(const M256& a) { return popc64(a.w[0]) + popc64(a.w[1]) + popc64(a.w[2]) + popc64(a.w[3]); }
+NHD_HD bool m_test(const M256& a, int c) { return (a.w[c >> 6] >> (c & 63)) & 1; }
+NHD_HD void m_set(M256& a, int c) { a.w[c >> 6] |= 1ULL << (c & 63); }
+NHD_HD void m_clr(M256& a, int c) { a.w[c >> 6] &= ~(1ULL << (c & 63)); }
+/* bits [lo, hi) */
+NHD_HD M256 m_range(int lo, int hi)
+{
+    M256 r;
+    for (int i = 0; i < 4; i++) {
+        int a = lo - 64 * i, b = hi - 64 * i;
+        a = a < 0 ? 0 : a;
+        b = b > 64 ? 64 : b;
+        uint64_t m = 0;
+        if (b > a) m = (b - a == 64) ? ~0ULL : (((1ULL << (b - a)) - 1) << a);
+        r.w[i] = m;
+    }
+    return r;
+}
+NHD_HD M256 m_shr(const M256& a, int s)   /* 0 <= s < 256 */
+{
+    M256 r;
+    int ws = s >> 6, bs = s & 63;
+    for (int i = 0; i < 4; i++) {
+        uint64_t lo = (i + ws < 4) ? a.w[i + ws] : 0;
+        uint64_t hi = (i + ws + 1 < 4) ? a.w[i + ws + 1] : 0;
+        r.w[i] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+    }
+    return r;
+}
+NHD_HD M256 m_shl(const M256& a, int s)   /* 0 <= s < 256 */
+{
+    M256 r;
+    int ws = s >> 6, bs = s & 63;
+    for (int i = 3; i >= 0; i--) {
+        uint64_t hi = (i - ws >= 0) ? a.w[i - ws] : 0;
+        uint64_t lo = (i - ws - 1 >= 0) ? a.w[i - ws - 1] : 0;
+        r.w[i] = bs ? ((hi << bs) | (lo >> (64 - bs))) : hi;
+    }
+    return r;
+}
+
+/* ---------------------------------------------------------------- pod type */
+
+/* Device-side pod type: the wire descriptor plus the request vectors of
+ * CfgTopology.GetTotal{Gpus,Cpus,NICs}Requested (CfgTopology.py:199-232) and the
+ * per-group physical-core demand of Matcher.py:179-201, all precomputed once per
+ * distinct descriptor by the host. */
+struct PodType {
+    nhd_pod pod;
+    uint8_t G;
+    uint8_t needs_gpu;                 /* sum(req_gpus) > 0 (Matcher.py:107) == any group has GPUs (:406-410) */
+    uint8_t pci;                       /* map_type == PCI */
+    uint8_t valid_map;                 /* map_type in {NUMA, PCI} (Matcher.py:45) */
+    uint8_t tot[NHD_MAX_GROUPS];       /* len(proc_cores) + sum(len(gpu.cpu_cores)) */
+    uint8_t cl_smt[NHD_MAX_GROUPS + 1];    /* physical cores needed on an SMT node, [G] = misc */
+    uint8_t cl_nosmt[NHD_MAX_GROUPS + 1];  /* ... on a non-SMT node */
+    uint8_t total_gpus;
+    uint8_t pad_[5];
+};
+
+NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
+{
+    t.pod = p;
+    t.G = p.n_groups;
+    t.pci = p.map_type == NHD_MAP_PCI;
+    t.valid_map = (p.map_type == NHD_MAP_NUMA || p.map_type == NHD_MAP_PCI);
+    int gpus = 0;
+    for (int g = 0; g < NHD_MAX_GROUPS + 1; g++) t.cl_smt[g] = t.cl_nosmt[g] = 0;
+    for (int g = 0; g < NHD_MAX_GROUPS; g++) t.tot[g] = 0;
+    for (int g = 0; g < p.n_groups && g < NHD_MAX_GROUPS; g++) {
+        const nhd_pod_group& pg = p.groups[g];
+        int tot = pg.n_proc;
+        for (int j = 0; j < pg.n_gpus && j < NHD_MAX_GROUP_GPUS; j++) tot += pg.gpu_feeders[j];
+        gpus += pg.n_gpus;
+        t.tot[g] = (uint8_t)tot;
+        int a = (pg.flags & NHD_GRP_PROC_SMT) ? (tot + 1) / 2 : tot;                    /* Matcher.py:182-185 */
+        int b = (pg.flags & NHD_GRP_HELPER_SMT) ? (pg.n_helpers + 1) / 2 : pg.n_helpers; /* :187-190 */
+        t.cl_smt[g] = (uint8_t)(a + b);
+        t.cl_nosmt[g] = (uint8_t)(tot + pg.n_helpers);                                    /* :194 */
+    }
+    /* Matcher.py:197-201: on SMT nodes the misc cores are always halved (the SMT flag
+     * tested there is an Enum member, hence always true). */
+    if (p.n_groups <= NHD_MAX_GROUPS) {
+        t.cl_smt[p.n_groups] = (uint8_t)((p.n_misc + 1) / 2);
+        t.cl_nosmt[p.n_groups] = p.n_misc;
+    }
+    t.total_gpus = (uint8_t)gpus;
+    t.needs_gpu = gpus > 0;
+    for (int i = 0; i < 5; i++) t.pad_[i] = 0;
+}
+
+/* ---------------------------------------------------------------- node queries */
+
+NHD_HD M256 rec_used(const nhd_node_rec& r) { M256 m; for (int i = 0; i < 4; i++) m.w[i] = r.used[i]; return m; }
+NHD_HD bool rec_smt(const nhd_node_rec& r) { return (r.flags & NHD_NODE_SMT) != 0; }
+
+/* physical cores c < phys whose hyperthreads are all unused (Node.py:257-262) */
+NHD_HD M256 eligible_phys(const nhd_node_rec& r)
+{
+    M256 u = rec_used(r);
+    M256 e = m_andnot(m_range(0, r.phys_cores), u);
+    if (rec_smt(r)) e = m_andnot(e, m_shr(u, r.phys_cores));
+    return e;
+}
+
+/* Node.GetFreeCpuCores (Node.py:250-264) */
+NHD_HD void free_cores(const nhd_node_rec& r, int* fc)
+{
+    M256 e = eligible_phys(r);
+    int per = r.phys_cores / r.n_numa;
+    for (int k = 0; k < r.n_numa; k++) fc[k] = m_popc(m_and(e, m_range(k * per, (k + 1) * per)));
+}
+
+/* Node.GetFreeNumaGPUs (Node.py:456-462) */
+NHD_HD void free_gpus(const nhd_node_rec& r, int* fg)
+{
+    uint32_t fr = ~(uint32_t)r.gpu_used & ((1u << r.n_gpus) - 1);
+    for (int k = 0; k < r.n_numa; k++) fg[k] = popc32(fr & r.gpu_numa_mask[k]);
+}
+
+NHD_HD int gpu_switch(const nhd_node_rec& r, int i) { return (int)((r.gpu_sw >> (4 * i)) & 0xF); }
+NHD_HD int nic_switch(const nhd_node_rec& r, int i) { return (int)((r.nic_sw[i >> 4] >> (4 * (i & 15))) & 0xF); }
+NHD_HD int nic_speed_class(const nhd_node_rec& r, int i) { return (int)((r.nic_speed[i >> 4] >> (4 * (i & 15))) & 0xF); }
+
+/* Node.GetFreeGPUPCICount (Node.py:266-273): free GPUs per local switch id, packed 4 bits each
+ * (a node has at most 16 GPUs, but a count of 16 would not fit: saturate at 15, which is
+ * still >= NHD_MAX_GROUPS, the largest value it is ever compared with). */
+NHD_HD uint64_t free_gpus_per_switch(const nhd_node_rec& r)
+{
+    uint64_t cnt = 0;
+    uint32_t fr = ~(uint32_t)r.gpu_used & ((1u << r.n_gpus) - 1);
+    while (fr) {
+        int i = ctz32(fr);
+        fr &= fr - 1;
+        int s = gpu_switch(r, i);
+        if (((cnt >> (4 * s)) & 0xF) < 15) cnt += 1ULL << (4 * s);
+    }
+    return cnt;
+}
+
+/* Node.GetFreeNumaNicResources (Node.py:283-296), sharing disabled: a NIC offers
+ * speed * NIC_BW_AVAIL_PERCENT in each direction, or nothing once a pod uses it. */
+NHD_HD double nic_free_bw(const nhd_node_rec& r, int li, const double* cap)
+{
+    return ((r.nic_inuse >> li) & 1) ? 0.0 : cap[nic_speed_class(r, li)];
+}
+
+/* Node.IsBusy (Node.py:847-850) */
+NHD_HD bool node_busy(const nhd_node_rec& r, double now, double min_busy)
+{
+    return (now - r.busy_time) < min_busy;
+}
+
+/* Pod-independent gates: InitialNodeFilter (NHDScheduler.py:241-243) and
+ * FilterPodResources (Matcher.py:73,78). */
+NHD_HD bool node_gates(const nhd_node_rec& r, const PodType& t)
+{
+    if (!(r.flags & NHD_NODE_ACTIVE)) return false;
+    if ((r.group_mask & t.pod.group_mask) == 0) return false;
+    if (r.flags & NHD_NODE_MAINTENANCE) return false;
+    if (t.pod.hugepages_gb > r.free_hugepages_gb) return false;
+    return true;
+}
+
+/* ---------------------------------------------------------------- NUMA tuples */
+
+/* tuple #idx of itertools.product(range(K), repeat=L): first element most significant */
+NHD_HD void tuple_digits(int idx, int K, int L, uint8_t* p)
+{
+    for (int i = L - 1; i >= 0; i--) { p[i] = (uint8_t)(idx % K); idx /= K; }
+}
+NHD_HD int ipow(int K, int L) { int r = 1; for (int i = 0; i < L; i++) r *= K; return r; }
+
+/* GPU stage predicate for one tuple (Matcher.py:121-129) */
+NHD_HD bool gpu_ok(const PodType& t, const uint8_t* p, int K, const int* fg)
+{
+    int ttl[NHD_MAX_NUMA] = {0, 0, 0, 0};
+    for (int g = 0; g < t.G; g++) ttl[p[g]] += t.pod.groups[g].n_gpus;
+    for (int k = 0; k < K; k++) if (ttl[k] > fg[k]) return false;
+    return true;
+}
+
+/* CPU stage predicate for one (G+1)-tuple (Matcher.py:204-212); m = NUMA node of the misc cores */
+NHD_HD bool cpu_ok(const PodType& t, const uint8_t* p, int m, int K, const int* fc, bool smt)
+{
+    const uint8_t* cl = smt ? t.cl_smt : t.cl_nosmt;
+    int ttl[NHD_MAX_NUMA] = {0, 0, 0, 0};
+    for (int g = 0; g < t.G; g++) ttl[p[g]] += cl[g];
+    ttl[m] += cl[t.G];
+    for (int k = 0; k < K; k++) if (ttl[k] > fc[k]) return false;
+    return true;
+}
+
+/*
+ * NIC stage for one NUMA tuple p: the FIRST entry of filts['nic'] whose NUMA part is p,
+ * after the PCI-switch pruning when map_type == PCI.
+ *
+ * The reference enumerates, for this p, every joint choice of per-NUMA NIC indices
+ * (NUMA 0's combination most significant, inside a NUMA node the first group most
+ * significant; Matcher.py:245-258), keeps the choices where no NIC goes negative after
+ * subtracting the groups' (rx, tx) in group order (:261-268), and in PCI mode drops
+ * choices that put more groups on a PCIe switch than it has free GPUs (:312-322).
+ * Both constraints only tighten as groups are added (speeds are >= 0), so a
+ * depth-first search in that same significance order with pruning returns exactly the
+ * first surviving entry.  Returns false when no entry survives.
+ */
+NHD_HD bool nic_first_fit(const nhd_node_rec& r, const PodType& t, const uint8_t* p, int K,
+                          const double* cap, uint64_t gsw, uint8_t* out_idx, uint8_t* out_li)
+{
+    const int G = t.G;
+    int ord[NHD_MAX_GROUPS];
+    int n = 0;
+    for (int k = 0; k < K; k++)
+        for (int g = 0; g < G; g++)
+            if (p[g] == k) {
+                if (r.nic_numa_mask[k] == 0) return false;      /* product(range(0), ...) is empty (:247) */
+                ord[n++] = g;
+            }
+    int choice[NHD_MAX_GROUPS], li[NHD_MAX_GROUPS];
+    double rrx[NHD_MAX_GROUPS], rtx[NHD_MAX_GROUPS];
+    int d = 0;
+    choice[0] = 0;
+    for (;;) {
+        const int g = ord[d];
+        const uint32_t nm = r.nic_numa_mask[p[g]];
+        const int l = nth_bit32(nm, choice[d]);
+        if (l < 0) {                                           /* exhausted this level: backtrack */
+            if (d == 0) return false;
+            d--;
+            choice[d]++;
+            continue;
+        }
+        double rx = nic_free_bw(r, l, cap), tx = rx;
+        for (int e = d - 1; e >= 0; e--)
+            if (li[e] == l) { rx = rrx[e]; tx = rtx[e]; break; }
+        rx -= t.pod.groups[g].rx_gbps;                          /* fp64, group order (:262-263) */
+        tx -= t.pod.groups[g].tx_gbps;
+        bool ok = !(rx < 0) && !(tx < 0);
+        if (ok && t.pci) {
+            const int s = nic_switch(r, l);
+            int cnt = 1;
+            for (int e = 0; e < d; e++) cnt += (nic_switch(r, li[e]) == s);
+            ok = cnt <= (int)((gsw >> (4 * s)) & 0xF);
+        }
+        if (!ok) { choice[d]++; continue; }
+        li[d] = l; rrx[d] = rx; rtx[d] = tx;
+        if (d == G - 1) break;
+        d++;
+        choice[d] = 0;
+    }
+    for (int e = 0; e < G; e++) {
+        out_idx[ord[e]] = (uint8_t)choice[e];
+        out_li[ord[e]] = (uint8_t)li[e];
+    }
+    return true;
+}
+
+/*
+ * Snapshot predicate: would node r be in filts[1] after IntersectResources for pod
+ * type t, ignoring the time-dependent busy window?  True iff some NUMA tuple p passes
+ * the GPU stage, has a CPU tuple (p, m) and a surviving NIC entry — i.e. the three-way
+ * set intersection of Matcher.py:349 is non-empty.
+ */
+NHD_HD bool node_feasible(const nhd_node_rec& r, const PodType& t, const double* cap)
+{
+    if (!t.valid_map) return false;
+    if (!node_gates(r, t)) return false;
+    const int K = r.n_numa, G = t.G;
+    int fg[NHD_MAX_NUMA], fc[NHD_MAX_NUMA];
+    free_gpus(r, fg);
+    free_cores(r, fc);
+    /* cheap necessary conditions before enumerating tuples */
+    {
+        int sg = 0, sc = 0, need = 0;
+        const uint8_t* cl = rec_smt(r) ? t.cl_smt : t.cl_nosmt;
+        for (int k = 0; k < K; k++) { sg += fg[k]; sc += fc[k]; }
+        for (int g = 0; g <= G; g++) need += cl[g];
+        if (t.total_gpus > sg || need > sc) return false;
+    }
+    const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+    const bool smt = rec_smt(r);
+    const int np = ipow(K, G);
+    uint8_t p[NHD_MAX_GROUPS], idx[NHD_MAX_GROUPS], li[NHD_MAX_GROUPS];
+    for (int pi = 0; pi < np; pi++) {
+        tuple_digits(pi, K, G, p);
+        if (!gpu_ok(t, p, K, fg)) continue;
+        bool c = false;
+        for (int m = 0; m < K && !c; m++) c = cpu_ok(t, p, m, K, fc, smt);
+        if (!c) continue;
+        if (nic_first_fit(r, t, p, K, cap, gsw, idx, li)) return true;
+    }
+    return false;
+}
+
+/* ---------------------------------------------------------------- CPython set emulation */
+
+/*
+ * The order in which the reference walks its candidate tuples is the iteration order of
+ * CPython sets of int tuples (Matcher.py:129,141,212,220,349,365).  This is the
+ * product's own model of that table (Objects/setobject.c, CPython 3.8-3.12: 8 initial
+ * slots, LINEAR_PROBES 9, perturb shift 5, resize at fill*5 >= mask*3 to the smallest
+ * power of two > 4*used, re-insertion in old slot order) and of the tuple hash
+ * (Objects/tupleobject.c).  Keys are tuple indices of product(range(K), repeat=L).
+ */
+NHD_HD uint64_t py_tuple_hash(int idx, int K, int L)
+{
+    const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P5 = 2870177450012600261ULL;
+    uint8_t d[8];
+    tuple_digits(idx, K, L, d);
+    uint64_t acc = P5;
+    for (int i = 0; i < L; i++) {
+        acc += (uint64_t)d[i] * P2;           /* hash(small int) == the int */
+        acc = (acc << 31) | (acc >> 33);
+        acc *= P1;
+    }
+    acc += (uint64_t)L ^ (P5 ^ 3527539ULL);
+    return acc == ~0ULL ? 1546275796ULL : acc;
+}
+
+template <int SLOTS>
+struct PySet {
+    uint16_t slot[SLOTS];      /* tuple index + 1, 0 = empty */
+    int mask, fill, K, L;
+
+    NHD_HD void init(int K_, int L_)
+    {
+        K = K_; L = L_; mask = 7; fill = 0;
+        for (int i = 0; i < 8; i++) slot[i] = 0;
+    }
+    NHD_HD void insert_clean(uint16_t* tab, int msk, int idx) const
+    {
+        uint64_t h = py_tuple_hash(idx, K, L), perturb = h;
+        uint64_t i = h & (uint64_t)msk;
+        for (;;) {
+            if (!tab[i]) { tab[i] = (uint16_t)(idx + 1); return; }
+            if (i + 9 <= (uint64_t)msk) {
+                for (int j = 1; j <= 9; j++)
+                    if (!tab[i + j]) { tab[i + j] = (uint16_t)(idx + 1); return; }
+            }
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & (uint64_t)msk;
+        }
+    }
+    NHD_HD bool has(int idx) const
+    {
+        uint64_t h = py_tuple_hash(idx, K, L), perturb = h;
+        uint64_t i = h & (uint64_t)mask;
+        for (;;) {
+            int probes = (i + 9 <= (uint64_t)mask) ? 9 : 0;
+            for (int j = 0; j <= probes; j++) {
+                if (!slot[i + j]) return false;
+                if (slot[i + j] == idx + 1) return true;
+            }
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & (uint64_t)mask;
+        }
+    }
+    NHD_HD void add(int idx)
+    {
+        uint64_t h = py_tuple_hash(idx, K, L), perturb = h;
+        uint64_t i = h & (uint64_t)mask;
+        for (;;) {
+            int probes = (i + 9 <= (uint64_t)mask) ? 9 : 0;
+            for (int j = 0; j <= probes; j++) {
+                if (!slot[i + j]) { i += j; goto found_unused; }
+                if (slot[i + j] == idx + 1) return;
+            }
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & (uint64_t)mask;
+        }
+found_unused:
+        slot[i] = (uint16_t)(idx + 1);
+        fill++;
+        if (fill * 5 < mask * 3) return;
+        /* resize: smallest power of two > 4 * used, old entries re-inserted in slot order */
+        int newsize = 8;
+        while (newsize <= fill * 4) newsize <<= 1;
+        uint16_t old[SLOTS / 4 > 8 ? SLOTS / 4 : 8];    /* the old table is at most a quarter of SLOTS */
+        int oldmask = mask;
+        for (int k = 0; k <= oldmask; k++) old[k] = slot[k];
+        for (int k = 0; k < newsize; k++) slot[k] = 0;
+        mask = newsize - 1;
+        for (int k = 0; k <= oldmask; k++)
+            if (old[k]) insert_clean(slot, mask, old[k] - 1);
+    }
+    /* list(s): indices in slot order */
+    NHD_HD int list(uint8_t* out) const
+    {
+        int n = 0;
+        for (int i = 0; i <= mask; i++) if (slot[i]) out[n++] = (uint8_t)(slot[i] - 1);
+        return n;
+    }
+};
+
+/* a & b with CPython's rule: walk the smaller operand (the right one on ties) in slot
+ * order, keep members of the other (setobject.c set_intersection) */
+template <int SA, int SB, int SO>
+NHD_HD void pyset_and(const PySet<SA>& a, const PySet<SB>& b, PySet<SO>& out)
+{
+    out.init(a.K, a.L);
+    if (b.fill > a.fill) {
+        for (int i = 0; i <= a.mask; i++) if (a.slot[i] && b.has(a.slot[i] - 1)) out.add(a.slot[i] - 1);
+    } else {
+        for (int i = 0; i <= b.mask; i++) if (b.slot[i] && a.has(b.slot[i] - 1)) out.add(b.slot[i] - 1);
+    }
+}
+
+/* 256-bit tuple-feasibility mask, bit = tuple index */
+struct TMask { uint64_t w[4]; };
+NHD_HD bool tm_test(const TMask& m, int i) { return (m.w[i >> 6] >> (i & 63)) & 1; }
+NHD_HD void tm_set(TMask& m, int i) { m.w[i >> 6] |= 1ULL << (i & 63); }
+NHD_HD TMask tm_zero() { TMask m; m.w[0] = m.w[1] = m.w[2] = m.w[3] = 0; return m; }
+
+/*
+ * GetNumaGroupIdx on top of IntersectResources for ONE node, given which tuples passed
+ * each stage: maskA over product(range(K), repeat=G) (GPU stage), maskB over
+ * repeat=G+1 (CPU stage), maskC over repeat=G (NUMA tuples that keep at least one NIC
+ * entry).  Reproduces, including CPython set order:
+ *   A_list = list(set of A tuples added in product order)          Matcher.py:113-141
+ *   B_list likewise                                                :175-220
+ *   intersect = list(set(A_list) & set(prefixes of B_list) & set(C numa parts))   :344-349
+ *   gpu list = intersect when something was removed, else A_list   :365-368
+ *   gtuple   = first element with the largest max-min group count  :428-439
+ *   ctuple   = first B_list entry whose prefix is gtuple           :442-444
+ * Returns false when the intersection is empty; else *p_star = index of gtuple,
+ * *m_star = last element of ctuple.
+ */
+NHD_HDN bool choose_mapping(int K, int G, const TMask& maskA, const TMask& maskB, const TMask& maskC,
+                            int* p_star, int* m_star)
+{
+    const int np = ipow(K, G), nq = np * K;
+    PySet<128> sa;  sa.init(K, G);
+    for (int i = 0; i < np; i++) if (tm_test(maskA, i)) sa.add(i);
+    if (sa.fill == 0) return false;
+    PySet<512> sb;  sb.init(K, G + 1);
+    for (int i = 0; i < nq; i++) if (tm_test(maskB, i)) sb.add(i);
+    if (sb.fill == 0) return false;
+    uint8_t a_list[64], b_list[256];
+    const int na = sa.list(a_list), nb = sb.list(b_list);
+
+    PySet<128> sg, sc, sn, t1, isect;
+    sg.init(K, G);
+    for (int i = 0; i < na; i++) sg.add(a_list[i]);
+    sc.init(K, G);
+    for (int i = 0; i < nb; i++) sc.add(b_list[i] / K);          /* x[:-1] */
+    sn.init(K, G);
+    for (int i = 0; i < np; i++) if (tm_test(maskC, i)) sn.add(i); /* first appearance = product order */
+    pyset_and(sg, sc, t1);
+    pyset_and(t1, sn, isect);
+    if (isect.fill == 0) return false;
+
+    uint8_t i_list[64];
+    const int ni = isect.list(i_list);
+    const uint8_t* gl = a_list;
+    int ngl = na;
+    if (ni != na) { gl = i_list; ngl = ni; }                       /* intersect is a subset of A */
+
+    int best = -1, bestv = -1;
+    for (int x = 0; x < ngl; x++) {
+        uint8_t d[NHD_MAX_GROUPS];
+        tuple_digits(gl[x], K, G, d);
+        int mx = 0, mn = 1 << 20;
+        for (int y = 0; y < K; y++) {
+            int c = 0;
+            for (int g = 0; g < G; g++) c += (d[g] == y);
+            mx = c > mx ? c : mx;
+            mn = c < mn ? c : mn;
+        }
+        if (mx - mn > bestv) { bestv = mx - mn; best = x; }        /* strict '>' keeps the first */
+    }
+    *p_star = gl[best];
+    for (int i = 0; i < nb; i++)
+        if (b_list[i] / K == *p_star) { *m_star = b_list[i] % K; return true; }
+    return false;   /* unreachable: p_star is in set(prefixes of B) */
+}
+
+/* list({x[0] for x in nic_list}) for up to NHD_MAX_GROUPS small ints (NHDScheduler.py:302):
+ * an 8-slot table, hash(i) == i, no resize below five distinct keys. */
+NHD_HD int claimed_nic_order(const uint8_t* li, int n, uint8_t* out)
+{
+    int slot[8];
+    for (int i = 0; i < 8; i++) slot[i] = -1;
+    for (int e = 0; e < n; e++) {
+        uint64_t h = li[e], perturb = h, i = h & 7;
+        for (;;) {
+            if (slot[i] < 0) { slot[i] = li[e]; break; }
+            if (slot[i] == li[e]) break;
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & 7;
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < 8; i++) if (slot[i] >= 0) out[m++] = (uint8_t)slot[i];
+    return m;
+}
+
+/* ---------------------------------------------------------------- evaluation of one node */
+
+/*
+ * Full evaluation of (pod type, node) on the node's CURRENT state: decides feasibility
+ * and, when feasible, the mapping GetNumaGroupIdx would return.
+ */
+struct Mapping {
+    uint8_t gpu_numa[NHD_MAX_GROUPS];
+    uint8_t misc_numa;
+    uint8_t nic_idx[NHD_MAX_GROUPS];
+    uint8_t nic_li[NHD_MAX_GROUPS];
+};
+
+/* Stage masks of one node on its current state: which NUMA tuples pass the GPU stage (a),
+ * the CPU stage (b, over G+1 tuples) and keep a NIC entry (c).  False when a stage is empty. */
+NHD_HD bool stage_masks(const nhd_node_rec& r, const PodType& t, const double* cap, uint64_t gsw,
+                        TMask& ma, TMask& mb, TMask& mc)
+{
+    const int K = r.n_numa, G = t.G;
+    int fg[NHD_MAX_NUMA], fc[NHD_MAX_NUMA];
+    free_gpus(r, fg);
+    free_cores(r, fc);
+    const bool smt = rec_smt(r);
+    const int np = ipow(K, G);
+    ma = tm_zero(); mb = tm_zero(); mc = tm_zero();
+    uint8_t p[NHD_MAX_GROUPS], idx[NHD_MAX_GROUPS], li[NHD_MAX_GROUPS];
+    bool anyA = false, anyB = false, anyC = false;
+    for (int pi = 0; pi < np; pi++) {
+        tuple_digits(pi, K, G, p);
+        if (gpu_ok(t, p, K, fg)) { tm_set(ma, pi); anyA = true; }
+        for (int m = 0; m < K; m++)
+            if (cpu_ok(t, p, m, K, fc, smt)) { tm_set(mb, pi * K + m); anyB = true; }
+        if (nic_first_fit(r, t, p, K, cap, gsw, idx, li)) { tm_set(mc, pi); anyC = true; }
+    }
+    return anyA && anyB && anyC;
+}
+
+NHD_HDN bool evaluate_mapping(const nhd_node_rec& r, const PodType& t, const double* cap, Mapping* out)
+{
+    const int K = r.n_numa, G = t.G;
+    const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+    TMask ma, mb, mc;
+    if (!stage_masks(r, t, cap, gsw, ma, mb, mc)) return false;
+    int ps, ms;
+    if (!choose_mapping(K, G, ma, mb, mc, &ps, &ms)) return false;
+    tuple_digits(ps, K, G, out->gpu_numa);
+    out->misc_numa = (uint8_t)ms;
+    nic_first_fit(r, t, out->gpu_numa, K, cap, gsw, out->nic_idx, out->nic_li);
+    return true;
+}
+
+/* ---------------------------------------------------------------- physical assignment */
+
+/*
+ * Node.GetFreeCpuBatch (Node.py:502-519): walk ALL logical ids in ascending order, take
+ * ids on socket `numa` that are unused and (on SMT nodes) whose sibling is unused —
+ * judged against the state at call time, nothing is marked during the walk.  An SMT
+ * request takes [core, sibling] while at least two are still needed.
+ * Returns the number of ids written to out (== num on success).
+ */
+NHD_HD int cpu_batch(const nhd_node_rec& r, int numa, int num, bool smt_req, uint8_t* out)
+{
+    const int phys = r.phys_cores, per = phys / r.n_numa;
+    const bool smt = rec_smt(r);
+    M256 e = m_and(eligible_phys(r), m_range(numa * per, (numa + 1) * per));
+    if (smt) e = m_or(e, m_shl(e, phys));      /* both hyperthreads of a free core are eligible ids */
+    int n = 0;
+    for (int w = 0; w < 4 && num > 0; w++) {
+        uint64_t bits = e.w[w];
+        while (bits && num > 0) {
+            int c = 64 * w + ctz64(bits);
+            bits &= bits - 1;
+            if (smt && smt_req && num >= 2) {
+                out[n++] = (uint8_t)c;
+                out[n++] = (uint8_t)(c < phys ? c + phys : c - phys);
+                num -= 2;
+            } else {
+                out[n++] = (uint8_t)c;
+                num -= 1;
+            }
+        }
+    }
+    return n;
+}
+
+NHD_HD void mark_used(nhd_node_rec& r, int c) { r.used[c >> 6] |= 1ULL << (c & 63); }
+
+/*
+ * Node.SetPhysicalIdsFromMapping (Node.py:663-841) + SetBusy (NHDScheduler.py:289) +
+ * ClaimPodNICResources (NHDScheduler.py:302-304) on the packed record.  r is updated in
+ * place; on failure every core/GPU taken so far is given back (Node.py:825-830) but the
+ * busy stamp stays.  b->status, node-independent fields and the physical ids are filled.
+ */
+NHD_HDN void assign_pod(nhd_node_rec& r, const PodType& t, const Mapping& m, double now, nhd_binding* b)
+{
+    const nhd_node_rec saved = r;
+    const int G = t.G;
+    r.busy_time = now;                                             /* NHDScheduler.py:289 */
+    int nc = 0, ng = 0, n_nic_rec = 0;
+    uint8_t nic_rec[NHD_MAX_GROUPS];
+    uint8_t batch[NHD_MAX_POD_CORES + 2];
+    bool hp_taken = false;
+    bool fail = false;
+
+    for (int g = 0; g < G; g++) {
+        b->gpu_numa[g] = m.gpu_numa[g];
+        b->cpu_numa[g] = m.gpu_numa[g];
+        b->nic_numa[g] = m.gpu_numa[g];
+        b->nic_idx[g] = m.nic_idx[g];
+        b->nic_list_index[g] = m.nic_li[g];
+    }
+    b->cpu_numa[G] = m.misc_numa;
+    b->n_groups = (uint8_t)G;
+
+    for (int g = 0; g < G && !fail; g++) {
+        const nhd_pod_group& pg = t.pod.groups[g];
+        const int numa = m.gpu_numa[g];
+        const int req = t.tot[g];
+        if (cpu_batch(r, numa, req, (pg.flags & NHD_GRP_PROC_SMT) != 0, batch) != req) { fail = true; break; }   /* :685 */
+        int ci = 0;
+        const int nsw = nic_switch(r, m.nic_li[g]);
+        for (int j = 0; j < pg.n_gpus; j++) {                       /* :707-732 */
+            uint32_t fr = ~(uint32_t)r.gpu_used & ((1u << r.n_gpus) - 1);
+            int dev = -1;
+            for (uint32_t f = fr; f; f &= f - 1) {                  /* GetFreePciGpuFromNic :648-655 */
+                int i = ctz32(f);
+                if (gpu_switch(r, i) == nsw) { dev = i; break; }
+            }
+            if (dev < 0) {
+                if (t.pci) { fail = true; break; }                  /* :711-713 */
+                uint32_t f = fr & r.gpu_numa_mask[numa];            /* GetNextGpuFree :495-500 */
+                if (f) dev = ctz32(f);
+            }
+            if (dev < 0) { fail = true; break; }                    /* :718-720 */
+            r.gpu_used |= (uint16_t)(1u << dev);
+            if (ng < NHD_MAX_POD_GPUS) b->gpu_index[ng] = (uint8_t)dev;
+            ng++;
+            for (int k = 0; k < pg.gpu_feeders[j]; k++) {
+                mark_used(r, batch[ci]);
+                if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[ci];
+                nc++; ci++;
+            }
+        }
+        if (fail) break;
+        for (int k = 0; k < pg.n_proc; k++) {                       /* :735-739 */
+            mark_used(r, batch[ci]);
+            if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[ci];
+            nc++; ci++;
+        }
+        if (pg.flags & NHD_GRP_HAS_NIC_CORES) nic_rec[n_nic_rec++] = m.nic_li[g];   /* :742-755 */
+        const int nh = pg.n_helpers;                                /* :773-788 */
+        if (cpu_batch(r, numa, nh, (pg.flags & NHD_GRP_HELPER_SMT) != 0, batch) != nh) { fail = true; break; }
+        for (int k = 0; k < nh; k++) {
+            mark_used(r, batch[k]);
+            if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[k];
+            nc++;
+        }
+    }
+    if (!fail) {
+        if (t.pod.hugepages_gb > 0) { r.free_hugepages_gb -= t.pod.hugepages_gb; hp_taken = true; }   /* :794-796 */
+        const int nm = t.pod.n_misc;                                                  /* :799-811 */
+        if (cpu_batch(r, m.misc_numa, nm, (t.pod.flags & NHD_POD_MISC_SMT) != 0, batch) != nm) fail = true;
+        else
+            for (int k = 0; k < nm; k++) {
+                mark_used(r, batch[k]);
+                if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[k];
+                nc++;
+            }
+    }
+    if (fail) {                                                      /* :825-837 */
+        const double bt = r.busy_time;
+        r = saved;
+        r.busy_time = bt;
+        if (hp_taken) r.free_hugepages_gb -= t.pod.hugepages_gb;   /* the unwind never restores hugepages */
+        b->n_cores = b->n_gpus = b->n_claimed = 0;
+        b->status = n_nic_rec ? NHD_REF_WOULD_CRASH : NHD_ASSIGN_FAILED;
+        return;
+    }
+    b->n_cores = (uint8_t)nc;
+    b->n_gpus = (uint8_t)ng;
+    const int ncl = claimed_nic_order(nic_rec, n_nic_rec, b->claimed_nics);          /* NHDScheduler.py:302 */
+    b->n_claimed = (uint8_t)ncl;
+    for (int i = 0; i < ncl; i++) r.nic_inuse |= 1u << b->claimed_nics[i];          /* Node.py:644-646 */
+    b->status = NHD_PLACED;
+}
+
+} // namespace nhd

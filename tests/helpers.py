@@ -1,0 +1,45 @@
+"""Shared test helpers: run a packed scenario through the oracle / the host-emulated core."""
+import ctypes
+
+import numpy as np
+
+from nhd_b200 import wire
+
+
+def emu_solve(emu, recs, speed_table, pods, now, bw=0.9, min_busy=30.0):
+    recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE).copy()
+    pods = np.ascontiguousarray(pods, dtype=wire.POD_DTYPE)
+    now = np.ascontiguousarray(now, dtype='<f8')
+    speed = np.ascontiguousarray(speed_table, dtype='<f8')
+    out = np.zeros(len(pods), dtype=wire.BINDING_DTYPE)
+    emu.nhd_emu_solve.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rc = emu.nhd_emu_solve(bw, min_busy, speed.ctypes.data, len(recs), recs.ctypes.data, len(pods),
+                           pods.ctypes.data, now.ctypes.data, out.ctypes.data)
+    assert rc == 0, f'emu error {rc}'
+    return out, recs
+
+
+def emu_feasible(emu, recs, speed_table, pod, bw=0.9):
+    recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE)
+    pod = np.ascontiguousarray(pod, dtype=wire.POD_DTYPE).reshape(1)
+    speed = np.ascontiguousarray(speed_table, dtype='<f8')
+    out = np.zeros(len(recs), dtype=np.uint8)
+    emu.nhd_emu_feasible.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+    emu.nhd_emu_feasible(bw, speed.ctypes.data, len(recs), recs.ctypes.data, pod.ctypes.data, out.ctypes.data)
+    return out
+
+
+def binding_bytes_equal(a, b):
+    """Bindings compared on every meaningful byte (pad excluded)."""
+    names = [n for n in a.dtype.names if n != 'pad_']
+    return all(np.array_equal(a[n], b[n]) for n in names)
+
+
+def first_binding_diff(a, b):
+    for i in range(len(a)):
+        for n in a.dtype.names:
+            if n != 'pad_' and not np.array_equal(a[i][n], b[i][n]):
+                return f'pod {i} field {n}: {a[i][n]} != {b[i][n]}'
+    return None

@@ -1,0 +1,38 @@
+"""CPU-only: the product's scalar core (nhd_core.cuh compiled with g++, tests/emu) must agree
+with the oracle bit for bit — bindings and final node records — on randomized clusters."""
+import numpy as np
+import pytest
+
+from tests import helpers, ref_compare, scenarios
+
+
+@pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
+def test_core_matches_oracle_random(oracle_lib, emu, flavor):
+    placed = 0
+    for seed in range(40):
+        scn = scenarios.random_scenario(1000 + seed * 13 + len(flavor), n_nodes=8, n_pods=40, flavor=flavor,
+                                        max_groups=4 if flavor != 'wild' else 3)
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now)
+        eb, erecs = helpers.emu_solve(emu, recs, layout.speed_table(), pods, now)
+        assert helpers.binding_bytes_equal(ob, eb), helpers.first_binding_diff(ob, eb)
+        assert orecs.tobytes() == erecs.tobytes(), ref_compare.diff_records(orecs, erecs)[:3]
+        placed += int((ob['status'] == 0).sum())
+    assert placed > 100
+
+
+def test_snapshot_predicate_matches_oracle_candidates(oracle_lib, emu):
+    """node_feasible (what the CUDA filter kernel evaluates per thread) == membership in
+    filts[1] after IntersectResources, on a partially filled cluster, busy window aside."""
+    checked = 0
+    for seed in range(25):
+        scn = scenarios.random_scenario(77 + seed, n_nodes=12, n_pods=30, flavor='wild' if seed % 2 else 'mixed')
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        _, filled = oracle_lib.solve(recs, layout.speed_table(), pods[:15], now[:15])
+        for pod in pods[15:]:
+            cand = oracle_lib.candidates(filled, layout.speed_table(), pod, now=1e9)   # nobody busy
+            feas = helpers.emu_feasible(emu, filled, layout.speed_table(), pod)
+            if pod['map_type'] in (1, 2):
+                assert np.array_equal(cand, feas), (seed, cand, feas)
+                checked += int(cand.sum())
+    assert checked > 50

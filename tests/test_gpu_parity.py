@@ -1,0 +1,143 @@
+"""GPU parity tests proper: the CUDA solver, called through the C-ABI, must produce the same
+bindings and the same final node records as the oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import workload
+from tests import helpers, ref_compare, scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def solver_mod():
+    from nhd_b200 import solver
+    return solver
+
+
+def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0):
+    s = solver_mod.Solver(speed, min_busy_secs=min_busy)
+    try:
+        s.load_nodes(recs)
+        b = s.solve_batch(pods, now)
+        final = s.read_nodes()
+        return b, final, s.timing()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
+def test_random_scenarios_match_oracle(oracle_lib, solver_mod, flavor):
+    placed = 0
+    for seed in range(25):
+        scn = scenarios.random_scenario(5000 + seed * 17 + len(flavor), n_nodes=10, n_pods=48, flavor=flavor,
+                                        max_groups=4 if flavor != 'wild' else 3)
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now)
+        cb, crecs, _ = _run_cuda(solver_mod, recs, layout.speed_table(), pods, now)
+        assert helpers.binding_bytes_equal(ob, cb), (seed, helpers.first_binding_diff(ob, cb))
+        assert orecs.tobytes() == crecs.tobytes(), (seed, ref_compare.diff_records(orecs, crecs)[:3])
+        placed += int((ob['status'] == 0).sum())
+    assert placed > 100
+
+
+def test_filter_kernel_matches_oracle_candidates(oracle_lib, solver_mod):
+    """F[type][node] from filter_kernel == filts[1] membership after IntersectResources
+    (busy window aside), on partially filled clusters, plus the NOGPU / BUSY bitmaps."""
+    for seed in range(6):
+        scn = scenarios.random_scenario(900 + seed, n_nodes=300 + 37 * seed, n_pods=60, flavor='mixed')
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        _, filled = oracle_lib.solve(recs, layout.speed_table(), pods[:40], now[:40])
+        s = solver_mod.Solver(layout.speed_table())
+        try:
+            s.load_nodes(filled)
+            tail, tnow = pods[40:], np.full(20, 2000.0)
+            s.stage_batch(tail, tnow)
+            feas, nogpu, busy, pt = s.filter_bitmaps()
+        finally:
+            s.close()
+        assert np.array_equal(nogpu, filled['n_gpus'] == 0)
+        assert np.array_equal(busy, (2000.0 - filled['busy_time']) < 30.0)
+        for i, pod in enumerate(tail):
+            cand = oracle_lib.candidates(filled, layout.speed_table(), pod, now=1e9).astype(bool)
+            assert np.array_equal(feas[pt[i]], cand), (seed, i)
+
+
+@pytest.mark.parametrize('config,n_nodes,n_pods', [(1, None, None), (2, None, None), (3, 4096, 384), (5, 4096, 384)])
+def test_baseline_configs_match_oracle(oracle_lib, solver_mod, config, n_nodes, n_pods):
+    recs, speed, pods, now = workload.make_workload(config, n_nodes, n_pods)
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now)
+    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now)
+    assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
+    assert orecs.tobytes() == crecs.tobytes()
+    assert timing['n_launches'] == 2
+
+
+def test_clock_changes_and_busy_window(oracle_lib, solver_mod):
+    """Per-pod clocks that move forwards, stall and jump backwards exercise the busy list."""
+    recs, speed, pods, _ = workload.make_workload(3, n_nodes=512, n_pods=200)
+    rng = np.random.default_rng(3)
+    now = 1000.0 + np.cumsum(rng.choice([0.0, 0.0, 5.0, 12.0, 31.0, -40.0], size=len(pods)))
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now)
+    cb, crecs, _ = _run_cuda(solver_mod, recs, speed, pods, now)
+    assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
+    assert orecs.tobytes() == crecs.tobytes()
+
+
+def test_update_snapshot_restore_and_prefix(oracle_lib, solver_mod):
+    recs, speed, pods, now = workload.make_workload(3, n_nodes=2048, n_pods=256)
+    s = solver_mod.Solver(speed)
+    try:
+        s.load_nodes(recs)
+        s.snapshot()
+        full = s.solve_batch(pods, now)
+        s.restore()
+        again = s.solve_batch(pods, now)
+        assert helpers.binding_bytes_equal(full, again)                 # deterministic replay
+        s.restore()
+        half = s.solve_batch(pods[:128], now[:128])
+        assert helpers.binding_bytes_equal(full[:128], half)           # pod i only sees pods < i
+        rest = s.solve_batch(pods[128:], now[128:])                    # state carried across batches
+        assert helpers.binding_bytes_equal(full[128:], rest)
+        # release: put back the original record of every touched node, then re-solve
+        s.restore()
+        s.solve_batch(pods[:64], now[:64])
+        touched = np.unique(full[:64]['node'][full[:64]['node'] >= 0])
+        s.update_nodes(touched, recs[touched])
+        assert s.read_nodes().tobytes() == recs.tobytes()
+        assert helpers.binding_bytes_equal(s.solve_batch(pods, now), full)
+    finally:
+        s.close()
+
+
+def test_full_size_properties(oracle_lib, solver_mod):
+    """65 536 nodes x 4 096 pods (the metric's configuration): too big for the oracle in
+    full, so (a) the first pods are compared with the oracle at full N, (b) size-independent
+    invariants are checked on everything."""
+    recs, speed, pods, now = workload.make_workload(4)
+    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now)
+    n_check = 12
+    ob, _ = oracle_lib.solve(recs, speed, pods[:n_check], now[:n_check])
+    assert helpers.binding_bytes_equal(ob, cb[:n_check]), helpers.first_binding_diff(ob, cb[:n_check])
+    placed = cb[cb['status'] == 0]
+    assert len(placed) > 3000
+    # every core handed out was free before, and is handed out once
+    used0 = np.unpackbits(recs['used'].view(np.uint8).reshape(len(recs), 32), axis=1, bitorder='little')
+    used1 = np.unpackbits(crecs['used'].view(np.uint8).reshape(len(recs), 32), axis=1, bitorder='little')
+    taken = np.zeros_like(used0)
+    for b in placed:
+        cores = b['cores'][:b['n_cores']]
+        assert len(set(cores.tolist())) == len(cores)
+        assert not used0[b['node'], cores].any()
+        assert not taken[b['node'], cores].any()
+        taken[b['node'], cores] = 1
+    assert np.array_equal(used1, used0 | taken)
+    # GPU pods: one per node per busy window (constant clock), on GPU nodes only
+    gpu_pods = placed[placed['n_gpus'] > 0]
+    assert len(np.unique(gpu_pods['node'])) == len(gpu_pods)
+    assert (recs['n_gpus'][gpu_pods['node']] > 0).all()
+    # untouched nodes are bit-identical
+    untouched = np.ones(len(recs), bool)
+    untouched[placed['node']] = False
+    assert recs[untouched].tobytes() == crecs[untouched].tobytes()
+    assert timing['n_types'] <= 16

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the NHD placement hot path (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1, one rank per GPU)
+
+A *step* is one pass of the hot path over one batch: 4 096 pending pods scheduled, with the
+reference's sequential semantics, on the 65 536-node synthetic cluster of BASELINE config 4
+(workload.py).  Every step starts from the same cluster state.
+
+Own arm (CUDA):
+  value   decisions/s with the batch and the cluster resident in HBM; the timed region is the
+          solver's kernels (snapshot filter [+ NCCL all-reduce] + sweep), timed with CUDA events
+          on the stream they are launched on; L2 is flushed between steps.
+  e2e     the same metric through the C-ABI with HOST buffers: per step, upload of the cluster
+          records and of the pod batch from host memory, the kernels, and the download of the
+          bindings (wall clock around nhd_load_nodes + nhd_solve_batch).
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+Reference arm (--impl reference): the reference's algorithm on the host CPU — the C restatement
+under oracle/ (the reference itself is Python and cannot travel to the GPU box), one thread, on
+a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workload  # noqa: E402
+
+CONFIG = 4
+METRIC = 'placement decisions/sec (64k nodes x 4k pods)'
+UNIT = 'decisions/s'
+S_BYTES_PER_NODE = 64          # algorithmic bytes per node per decision (configs 2-4)
+FIXED_BYTES_PER_DECISION = 256
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(',')]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_reference_arm(args, rank):
+    """CPU arm: the oracle port of the reference path, single thread, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    ob.build()
+    recs, speed, pods, now = workload.make_workload(CONFIG)
+    N = len(recs)
+    # size one step at roughly budget/(steps+warmup) seconds: ~1.7 us per (pod, node) evaluation
+    budget = 60.0
+    per_step = budget / max(1, args.steps + args.warmup)
+    est_pod_s = N * 1.7e-6
+    n_sample = int(max(2, min(len(pods), per_step / est_pod_s)))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ob.solve(recs, speed, pods[:n_sample], now[:n_sample])
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    value = n_sample * len(times) / sum(times)
+    sample = f'first {n_sample} pods of the 4096-pod stream on all {N} nodes, per step'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u64', 'data': 'synthetic',
+            'config': {'workload': f'BASELINE config {CONFIG}: 65536 nodes x 4096 pods', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'host_cores_available': os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='nhd_b200', choices=['nhd_b200', 'reference'])
+    ap.add_argument('--cpu-sample-pods', type=int, default=128)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nhd_b200 import wire
+    from nhd_b200.solver import Solver, nccl_unique_id
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 solver has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    else:
+        nccl_id = None
+
+    recs, speed, pods, now = workload.make_workload(CONFIG)
+    N, P = len(recs), len(pods)
+    solver = Solver(speed, device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id)
+    solver.load_nodes(recs)
+    solver.snapshot()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- value: batch + cluster resident in HBM, kernels only -----------------
+    solver.stage_batch(pods, now)
+    phase = {'filter_ms': [], 'exchange_ms': [], 'sweep_ms': [], 'total_ms': []}
+    sampler = ClockSampler(local_rank)
+    launches = 0
+    barrier()
+    t_wall0 = None
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            barrier()
+            if rank == 0:
+                sampler.start()
+            t_wall0 = time.perf_counter()
+        solver.restore()
+        solver.sync()
+        flush.zero_()                      # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        solver.solve_staged()
+        solver.sync()
+        t = solver.timing()
+        if it >= args.warmup:
+            for k in phase:
+                phase[k].append(t[k])
+            launches += t['n_launches']
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    bindings = solver.fetch_bindings()
+    n_types = t['n_types']
+
+    step_ms = float(np.sum(phase['total_ms']))
+    if world > 1:
+        tt = torch.tensor([step_ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms = float(tt.item())
+    value = P * args.steps / (step_ms / 1e3)
+
+    # ---------------- e2e: host buffers in, host buffers out --------------------------------
+    pin_recs = recs.copy()
+    out = np.zeros(P, dtype=wire.BINDING_DTYPE)
+    e2e_t = []
+    for it in range(args.warmup + min(args.steps, 10)):
+        barrier()
+        t0 = time.perf_counter()
+        solver.load_nodes(pin_recs)                       # H2D: cluster records
+        out = solver.solve_batch(pods, now)               # H2D: pod batch; D2H: bindings
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if it >= args.warmup:
+            e2e_t.append(dt)
+    e2e_value = P * len(e2e_t) / sum(e2e_t)
+    same = all(np.array_equal(out[n], bindings[n]) for n in out.dtype.names if n != 'pad_')
+    h2d = N * wire.NODE_DTYPE.itemsize + n_types * 168 + P * 12
+    d2h = P * wire.BINDING_DTYPE.itemsize
+
+    if rank != 0:
+        solver.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (the sweep) ---------------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = P * (N * S_BYTES_PER_NODE + FIXED_BYTES_PER_DECISION)
+    sweep_ms = float(np.mean(phase['sweep_ms']))
+    filter_ms = float(np.mean(phase['filter_ms']))
+    dominant = 'sweep_kernel' if sweep_ms >= filter_ms else 'filter_kernel'
+    dom_ms = max(sweep_ms, filter_ms)
+    achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f).get(dominant)
+    except Exception:
+        pass
+
+    # ---------------- CPU baseline on this box's host cores (bounded sample) ------------------
+    cpu = None
+    if world == 1:
+        from oracle import binding as ob
+        ob.build()
+        ns = args.cpu_sample_pods
+        t0 = time.perf_counter()
+        cb, _ = ob.solve(recs, speed, pods[:ns], now[:ns])
+        dt = time.perf_counter() - t0
+        names = [n for n in cb.dtype.names if n != 'pad_']
+        parity = all(np.array_equal(cb[n], bindings[:ns][n]) for n in names)
+        cpu = {'value': ns / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+               'sample': f'first {ns} pods of the same stream on all {N} nodes ({dt:.1f} s); '
+                         f'bindings identical to the GPU run: {parity}',
+               'host_cores_available': os.cpu_count()}
+
+    placed = int((bindings['status'] == 0).sum())
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': step_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'u64', 'data': 'synthetic',
+        'config': {'workload': f'BASELINE config {CONFIG}: {N} nodes x {P} pods, 16 pod types (50% GPU/PCI), '
+                               f'30% nodes pre-occupied, constant clock',
+                   'parallelism': f'node-sharded filter x{world} + one NCCL all-reduce + replicated sweep' if world > 1
+                   else 'single GPU',
+                   'l2': 'flushed between steps (256 MiB memset)', 'pods_placed': placed, 'pod_types': n_types},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': 1e3 * sum(e2e_t) / len(e2e_t), 'steps': len(e2e_t),
+                'includes': 'cluster records H2D + ingest, pod batch H2D, kernels, bindings D2H',
+                'bindings_equal_resident_run': bool(same)},
+        'gpu_launches': int(launches),
+        'kernel_ms': {'filter': filter_ms, 'exchange': float(np.mean(phase['exchange_ms'])), 'sweep': sweep_ms,
+                      'wall_per_step_incl_restore_and_flush': 1e3 * wall_s / args.steps},
+        'roofline': {'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': int(alg_bytes),
+                     'note': 'algorithmic = reference-equivalent bytes (every eligible node record read once per '
+                             'decision, SURVEY 8d); the sweep itself is latency-bound and L2-resident'},
+        'clocks': clocks,
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -43,6 +43,7 @@ def run_reference(scn):
         outcomes.append(o)
     final = packing.pack_nodes([nodes[n] for n in names], layout)
     ref.node.Node.MIN_BUSY_SECS = 30.0
+    run_reference.last_final_state = {n: scenarios.node_state(nodes[n]) for n in names}
     return outcomes, initial, final, layout, names
 
 

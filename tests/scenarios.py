@@ -38,13 +38,15 @@ def _ranges(ids):
 
 def make_node(name, sockets=2, phys_cores=32, smt=True, reserved_per_socket=2, gpus=(), nics=(),
               sriov_pfs=(), groups=None, hp_alloc=64, hp_free=None, active=True, maintenance=False,
-              isol=True, vlan=100, res_hugepages=None):
+              isol=True, vlan=100, res_hugepages=None, isolcpus=None):
     """gpus: [(device_id, numa, pciesw)], nics: [(ifname, mbps, numa, pciesw)] in label order."""
     labels = {NFD + 'nfd-extras-cpu.numSockets': str(sockets),
               NFD + 'nfd-extras-cpu.num_cores': str(phys_cores)}
     if smt:
         labels[NFD + 'cpu-hardware_multithreading'] = 'true'
-    if isol:
+    if isolcpus is not None:
+        labels[NFD + 'nfd-extras-cpu.isolcpus'] = isolcpus
+    elif isol:
         per = phys_cores // sockets
         iso = []
         for s in range(sockets):

@@ -240,6 +240,10 @@ int32_t nhd_last_timing(const nhd_handle* h, nhd_timing* out);
 int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* words_per_type,
                         uint64_t* words, int64_t capacity_words, int32_t* pod_type, int32_t n_pods);
 
+/* Debug: 64 words of per-phase cycle accumulators / counters of the last sweep; only non-zero
+ * in libraries built with -DNHD_PROFILE. */
+int32_t nhd_debug_counters(nhd_handle* h, uint64_t* out64);
+
 #ifdef __cplusplus
 }
 #endif

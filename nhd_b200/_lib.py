@@ -6,13 +6,14 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnhd_b200.so')
+LIB_PATH = os.path.join(_HERE, os.environ.get('NHD_B200_LIB', 'libnhd_b200.so'))
 
 # every symbol include/nhd_b200.h declares
 EXPORTS = ('nhd_default_params', 'nhd_nccl_unique_id', 'nhd_create', 'nhd_destroy', 'nhd_last_error',
            'nhd_validate_node', 'nhd_validate_pod', 'nhd_load_nodes', 'nhd_update_nodes', 'nhd_read_nodes',
            'nhd_snapshot', 'nhd_restore', 'nhd_solve_batch', 'nhd_stage_batch', 'nhd_solve_staged',
-           'nhd_fetch_bindings', 'nhd_sync', 'nhd_run_filter_only', 'nhd_last_timing', 'nhd_read_filter')
+           'nhd_fetch_bindings', 'nhd_sync', 'nhd_run_filter_only', 'nhd_last_timing', 'nhd_read_filter',
+           'nhd_debug_counters')
 
 
 class Params(ctypes.Structure):
@@ -61,6 +62,7 @@ def load():
         'nhd_run_filter_only': (i32, [vp]),
         'nhd_last_timing': (i32, [vp, ctypes.POINTER(Timing)]),
         'nhd_read_filter': (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), vp, i64, vp, i32]),
+        'nhd_debug_counters': (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

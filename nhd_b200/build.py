@@ -29,13 +29,19 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, profile=False):
+    if profile:
+        return _compile(os.path.join(HERE, 'libnhd_b200_prof.so'), verbose, ['-DNHD_PROFILE'])
     if not force and not is_stale():
         return LIB
+    return _compile(LIB, verbose, [])
+
+
+def _compile(LIB, verbose, extra):
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
            '--fmad=false',                      # fp64 NIC arithmetic must stay subtract-then-compare (no contraction)
            '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v' if verbose else '-O3',
-           '-o', LIB] + SOURCES + ['-ldl']
+           '-o', LIB] + extra + SOURCES + ['-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -45,5 +51,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    build(force=True, verbose='-v' in sys.argv)
-    print(LIB)
+    print(build(force=True, verbose='-v' in sys.argv, profile='--profile' in sys.argv))

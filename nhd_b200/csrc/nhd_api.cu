@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -65,6 +66,7 @@ struct nhd_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
+    int smem_optin = 48 * 1024;
     ncclComm_t comm = nullptr;
 
     /* cluster mirror */
@@ -89,8 +91,16 @@ struct nhd_handle {
     uint64_t* d_bitmaps = nullptr;  size_t bitmaps_cap = 0;
     int32_t* d_cursors = nullptr;   size_t cursors_cap = 0;
     int32_t* d_busy_list = nullptr;
+    int32_t* d_pend = nullptr;
+    uint4* d_dyn = nullptr;
+    uint16_t* d_class = nullptr;
+    ClassSlot* d_class_slots = nullptr;
+    unsigned long long* d_prof = nullptr;
+    int* d_sweep_done = nullptr;
+    int companion_ctas = 0;
     uint64_t* d_memo = nullptr;
     double now0 = 0.0;
+    bool const_clock = true;
     std::vector<int32_t> pod_type_host;
 
     nhd_timing timing;
@@ -227,7 +237,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -260,12 +270,21 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, p->device));
     h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     CK(cudaMalloc((void**)&h->d_memo, (size_t)MEMO_SLOTS * 16));
     CK(cudaMemsetAsync(h->d_memo, 0, (size_t)MEMO_SLOTS * 16, h->stream));
+    CK(cudaMalloc((void**)&h->d_sweep_done, 4));
+    { const char* e = getenv("NHD_COMPANION_CTAS"); h->companion_ctas = e ? atoi(e) : 0; }
+    CK(cudaMalloc((void**)&h->d_prof, 64 * 8));
+    CK(cudaMemsetAsync(h->d_prof, 0, 64 * 8, h->stream));
+    CK(cudaMalloc((void**)&h->d_class_slots, (size_t)CLASS_SLOTS * sizeof(ClassSlot)));
+    CK(cudaMemsetAsync(h->d_class_slots, 0, (size_t)CLASS_SLOTS * sizeof(ClassSlot), h->stream));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             FILTER_STAGES * SUPER_BYTES + TYPES_SMEM_MAX * (int)sizeof(PodType)));
+    CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    CK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     if (p->world_size > 1) {
         if (!g_nccl.load()) return fail(h, NHD_ERR_NCCL, "libnccl.so.2 not loadable");
         ncclUniqueId_ id;
@@ -298,6 +317,11 @@ static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, co
     ingest_kernel<<<(total + threads - 1) / threads, threads, 0, h->stream>>>(
         (const uint4*)h->d_stage, d_idx, n, h->d_nodes);
     CK(cudaGetLastError());
+    /* hardware classes of the (re)written nodes */
+    classify_claim_kernel<<<(n + threads - 1) / threads, threads, 0, h->stream>>>(h->d_nodes, d_idx, n, h->d_class_slots, h->d_class);
+    CK(cudaGetLastError());
+    classify_verify_kernel<<<(n + threads - 1) / threads, threads, 0, h->stream>>>(h->d_nodes, d_idx, n, h->d_class_slots, h->d_class);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return NHD_OK;
 }
@@ -316,18 +340,22 @@ extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node
     const int n_super = std::max(1, (n_nodes + SUPER_NODES - 1) / SUPER_NODES);
     const size_t bytes = (size_t)n_super * SUPER_BYTES;
     if (bytes != h->nodes_bytes) {
-        cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_busy_list);
-        h->d_nodes = h->d_snapshot = nullptr; h->d_busy_list = nullptr;
+        cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_busy_list); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_pend);
+        h->d_nodes = h->d_snapshot = nullptr; h->d_busy_list = nullptr; h->d_dyn = nullptr; h->d_class = nullptr; h->d_pend = nullptr;
         h->nodes_bytes = 0;
         CK(cudaMalloc((void**)&h->d_nodes, bytes));
         CK(cudaMalloc((void**)&h->d_snapshot, bytes));
         CK(cudaMalloc((void**)&h->d_busy_list, ((size_t)n_super * SUPER_NODES + 64) * 4));
+        CK(cudaMalloc((void**)&h->d_dyn, (size_t)n_super * SUPER_NODES * sizeof(NodeDyn)));
+        CK(cudaMalloc((void**)&h->d_class, (size_t)n_super * SUPER_NODES * sizeof(uint16_t)));
+        CK(cudaMalloc((void**)&h->d_pend, (size_t)n_super * SUPER_NODES * sizeof(int32_t)));
         h->nodes_bytes = bytes;
     }
     h->n_nodes = n_nodes;
     h->n_super = n_super;
     h->words = n_super * SUPER_NODES / 64;
     CK(cudaMemsetAsync(h->d_nodes, 0, bytes, h->stream));     /* padding nodes: inactive */
+    CK(cudaMemsetAsync(h->d_class, 0xFF, (size_t)n_super * SUPER_NODES * sizeof(uint16_t), h->stream));
     h->loaded = true;
     h->have_snapshot = false;
     h->staged = h->solved = false;
@@ -474,7 +502,7 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
         h->pods_cap = n_pods;
     }
     CK(grow_dev(h->d_bitmaps, h->bitmaps_cap, (size_t)(T + 2) * h->words * 8));
-    CK(grow_dev(h->d_cursors, h->cursors_cap, (size_t)std::max(T, 1) * 2 * 4));
+    CK(grow_dev(h->d_cursors, h->cursors_cap, (size_t)std::max(T, 1) * 3 * 4));
     if (T) CK(cudaMemcpyAsync(h->d_types, h->h_batch, types_bytes, cudaMemcpyHostToDevice, h->stream));
     if (n_pods) {
         CK(cudaMemcpyAsync(h->d_pod_type, h->h_batch + off_pt, (size_t)n_pods * 4, cudaMemcpyHostToDevice, h->stream));
@@ -483,6 +511,8 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
     h->n_pods = n_pods;
     h->n_types = T;
     h->now0 = n_pods ? now[0] : 0.0;
+    h->const_clock = true;
+    for (int i = 1; i < n_pods; i++) if (now[i] != now[0]) { h->const_clock = false; break; }
     h->staged = true;
     return NHD_OK;
 }
@@ -510,13 +540,14 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     const int super_lo = (int)((long)h->n_super * rk / ws), super_hi = (int)((long)h->n_super * (rk + 1) / ws);
     const size_t bm_bytes = (size_t)(T + 2) * W * 8;
     if (ws > 1) CK(cudaMemsetAsync(h->d_bitmaps, 0, bm_bytes, h->stream));
-    if (super_hi > super_lo && h->n_pods > 0) {
+    if (h->n_pods > 0) {
         FilterArgs fa;
         fa.nodes = h->d_nodes; fa.types = h->d_types; fa.n_types = T; fa.n_nodes = h->n_nodes;
-        fa.super_lo = super_lo; fa.super_hi = super_hi; fa.words = W; fa.bitmaps = h->d_bitmaps;
+        fa.n_super = h->n_super; fa.super_lo = super_lo; fa.super_hi = super_hi; fa.words = W;
+        fa.bitmaps = h->d_bitmaps; fa.dyn = h->d_dyn; fa.class_id = h->d_class;
         fa.now0 = h->now0; fa.min_busy = h->params.min_busy_secs;
         memcpy(fa.cap, h->cap, sizeof(fa.cap));
-        const int grid = std::min(super_hi - super_lo, h->sm_count * 2);
+        const int grid = std::min(h->n_super, h->sm_count * 2);
         const size_t smem = FILTER_STAGES * SUPER_BYTES + (T <= TYPES_SMEM_MAX ? (size_t)T * sizeof(PodType) : 0);
         filter_kernel<<<grid, FILTER_THREADS, smem, h->stream>>>(fa);
         CK(cudaGetLastError());
@@ -537,12 +568,36 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         SweepArgs sa;
         sa.nodes = h->d_nodes; sa.types = h->d_types; sa.pod_type = h->d_pod_type; sa.now = h->d_now; sa.out = h->d_out;
         sa.n_pods = h->n_pods; sa.n_types = T; sa.n_nodes = h->n_nodes; sa.words = W;
-        sa.bitmaps = h->d_bitmaps; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list; sa.memo = h->d_memo;
+        sa.dual = (h->const_clock && h->params.reserved_ != 1) ? 1 : 0;     /* reserved_ == 1 forces the single-warp sweep (tests) */
+        sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
+        sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend; sa.sweep_done = h->d_sweep_done;
+        CK(cudaMemsetAsync(h->d_sweep_done, 0, 4, h->stream));
+        const int sweep_grid = 1 + std::max(0, h->companion_ctas);
         sa.min_busy = h->params.min_busy_secs;
         memcpy(sa.cap, h->cap, sizeof(sa.cap));
-        sweep_kernel<<<1, 32, 0, h->stream>>>(sa);
+        /* shared memory: memo front | pod types | cursors | (bitmaps when they fit) */
+        size_t smem = (size_t)SMEMO_SLOTS * 16 + (size_t)DMEMO_SLOTS * 48 + (size_t)DCACHE_SLOTS * 36 + 16 +
+                      (size_t)CLSNIC_SLOTS * 32;
+        if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
+        smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
+        const size_t with_bitmaps = smem + bm_bytes;
+        if (with_bitmaps <= (size_t)h->smem_optin) {
+            sweep_kernel<true><<<sweep_grid, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);
+        } else {
+            sweep_kernel<false><<<sweep_grid, SWEEP_THREADS, smem, h->stream>>>(sa);
+        }
         CK(cudaGetLastError());
-        launches++;
+        FinishArgs fin;
+        fin.nodes = h->d_nodes; fin.types = h->d_types; fin.pod_type = h->d_pod_type; fin.out = h->d_out;
+        fin.dyn = h->d_dyn; fin.n_pods = h->n_pods;
+        const int fthreads = 128, fgrid = (h->n_pods + fthreads - 1) / fthreads;
+        resolve_kernel<<<(h->n_pods + 63) / 64, 64, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        assign_cores_kernel<<<fgrid, fthreads, 0, h->stream>>>(fin);
+        CK(cudaGetLastError());
+        commit_kernel<<<fgrid, fthreads, 0, h->stream>>>(fin);
+        CK(cudaGetLastError());
+        launches += 4;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
     h->timing.n_launches = launches;
@@ -618,5 +673,16 @@ extern "C" int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* wor
         if (n_pods < h->n_pods) return NHD_ERR_INVALID;
         memcpy(pod_type, h->pod_type_host.data(), (size_t)h->n_pods * 4);
     }
+    return NHD_OK;
+}
+
+/* debug: 16 cycle accumulators + 16 counters of the last sweep (only filled by NHD_PROFILE builds) */
+extern "C" int32_t nhd_debug_counters(nhd_handle* h, uint64_t* out32)
+{
+    if (!h || !out32) return NHD_ERR_INVALID;
+    CK(cudaSetDevice(h->params.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out32, h->d_prof, 64 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->d_prof, 0, 64 * 8));
     return NHD_OK;
 }

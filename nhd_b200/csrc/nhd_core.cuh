@@ -67,13 +67,8 @@ NHD_HD int ctz64(uint64_t x)      /* x != 0 */
 /* index of the n-th (0-based) set bit of x, -1 if fewer */
 NHD_HD int nth_bit32(uint32_t x, int n)
 {
-#ifdef __CUDA_ARCH__
-    unsigned r = __fns(x, 0, n + 1);
-    return r == 0xFFFFFFFFu ? -1 : (int)r;
-#else
-    for (; n > 0 && x; n--) x &= x - 1;
-    return x ? __builtin_ctz(x) : -1;
-#endif
+    for (; n > 0 && x; n--) x &= x - 1;          /* n is tiny (a per-NUMA NIC index) */
+    return x ? ctz32(x) : -1;
 }
 
 /* 256-bit core mask (logical core c = bit c) */
@@ -140,7 +135,11 @@ struct PodType {
     uint8_t cl_smt[NHD_MAX_GROUPS + 1];    /* physical cores needed on an SMT node, [G] = misc */
     uint8_t cl_nosmt[NHD_MAX_GROUPS + 1];  /* ... on a non-SMT node */
     uint8_t total_gpus;
-    uint8_t pad_[5];
+    uint8_t need_smt;                  /* sum of cl_smt (saturated at 255): no tuple ever asks a socket for more */
+    uint8_t need_nosmt;
+    uint8_t max_smt;                   /* largest single entry of cl_smt: some socket must offer that much */
+    uint8_t max_nosmt;
+    uint8_t has_bw;                    /* some group asks for NIC bandwidth (rx or tx > 0) */
 };
 
 NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
@@ -171,7 +170,15 @@ NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
     }
     t.total_gpus = (uint8_t)gpus;
     t.needs_gpu = gpus > 0;
-    for (int i = 0; i < 5; i++) t.pad_[i] = 0;
+    int ns = 0, nn = 0;
+    for (int g = 0; g <= NHD_MAX_GROUPS; g++) { ns += t.cl_smt[g]; nn += t.cl_nosmt[g]; }
+    t.need_smt = (uint8_t)(ns > 255 ? 255 : ns);
+    t.need_nosmt = (uint8_t)(nn > 255 ? 255 : nn);
+    int ms = 0, mn = 0, bw = 0;
+    for (int g = 0; g <= NHD_MAX_GROUPS; g++) { ms = t.cl_smt[g] > ms ? t.cl_smt[g] : ms; mn = t.cl_nosmt[g] > mn ? t.cl_nosmt[g] : mn; }
+    for (int g = 0; g < p.n_groups && g < NHD_MAX_GROUPS; g++)
+        if (p.groups[g].rx_gbps > 0.0 || p.groups[g].tx_gbps > 0.0) bw = 1;
+    t.max_smt = (uint8_t)ms; t.max_nosmt = (uint8_t)mn; t.has_bw = (uint8_t)bw;
 }
 
 /* ---------------------------------------------------------------- node queries */
@@ -252,7 +259,10 @@ NHD_HD bool node_gates(const nhd_node_rec& r, const PodType& t)
 /* tuple #idx of itertools.product(range(K), repeat=L): first element most significant */
 NHD_HD void tuple_digits(int idx, int K, int L, uint8_t* p)
 {
-    for (int i = L - 1; i >= 0; i--) { p[i] = (uint8_t)(idx % K); idx /= K; }
+    if (K == 2) { for (int i = L - 1; i >= 0; i--) { p[i] = (uint8_t)(idx & 1); idx >>= 1; } }
+    else if (K == 4) { for (int i = L - 1; i >= 0; i--) { p[i] = (uint8_t)(idx & 3); idx >>= 2; } }
+    else if (K == 1) { for (int i = 0; i < L; i++) p[i] = 0; }
+    else { for (int i = L - 1; i >= 0; i--) { p[i] = (uint8_t)(idx % K); idx /= K; } }
 }
 NHD_HD int ipow(int K, int L) { int r = 1; for (int i = 0; i < L; i++) r *= K; return r; }
 
@@ -754,6 +764,8 @@ NHD_HDN void assign_pod(nhd_node_rec& r, const PodType& t, const Mapping& m, dou
         r.busy_time = bt;
         if (hp_taken) r.free_hugepages_gb -= t.pod.hugepages_gb;   /* the unwind never restores hugepages */
         b->n_cores = b->n_gpus = b->n_claimed = 0;
+        for (int i = 0; i < NHD_MAX_POD_CORES; i++) b->cores[i] = 0;
+        for (int i = 0; i < NHD_MAX_POD_GPUS; i++) b->gpu_index[i] = 0;
         b->status = n_nic_rec ? NHD_REF_WOULD_CRASH : NHD_ASSIGN_FAILED;
         return;
     }
@@ -763,6 +775,255 @@ NHD_HDN void assign_pod(nhd_node_rec& r, const PodType& t, const Mapping& m, dou
     b->n_claimed = (uint8_t)ncl;
     for (int i = 0; i < ncl; i++) r.nic_inuse |= 1u << b->claimed_nics[i];          /* Node.py:644-646 */
     b->status = NHD_PLACED;
+}
+
+
+/* ================================================================================== */
+/* Two-stage placement: decisions on a per-node summary, core ids deferred             */
+/* ================================================================================== */
+
+/*
+ * NodeDyn — the mutable summary of one node the sequential sweep works on (32 bytes).
+ *
+ * Every decision of the reference path depends on the 256-bit core mask only through
+ * Node.GetFreeCpuCores (Node.py:250-264), i.e. the number of fully free physical cores per
+ * NUMA node.  Node.GetFreeCpuBatch (Node.py:502-519) always hands out the LOWEST eligible
+ * ids of a socket, so whatever a batch of pods took from a socket is a prefix of the
+ * snapshot's eligible-core list; `consumed[k]` is the length of that prefix.  The sweep
+ * therefore tracks counts only, and the actual core ids are reconstructed afterwards, for
+ * all pods in parallel, from the snapshot mask and the pod's prefix offsets
+ * (assign_cores_from_snapshot).
+ */
+struct NodeDyn {
+    uint8_t  fc[NHD_MAX_NUMA];        /* free physical cores per NUMA node (current)              */
+    uint8_t  consumed[NHD_MAX_NUMA];  /* eligible cores consumed since the snapshot, per NUMA node */
+    uint16_t gpu_used;
+    uint16_t info;                    /* bit0 touched by this batch, bit1 SMT node, bits 2-4 n_numa */
+    uint32_t nic_inuse;
+    int32_t  free_hugepages_gb;
+    uint16_t hw_class;                /* id of the node's static hardware description, 0xFFFF = none */
+    uint8_t  n_gpus;
+    uint8_t  n_nics;
+    double   busy_time;
+};
+#define NHD_DYN_TOUCHED 1
+#define NHD_DYN_SMT     2
+#define NHD_NO_CLASS    0xFFFF
+static_assert(sizeof(NodeDyn) == 32, "NodeDyn must be two 16-byte chunks");
+
+NHD_HD void make_dyn(const nhd_node_rec& r, NodeDyn& d)
+{
+    int fc[NHD_MAX_NUMA] = {0, 0, 0, 0};
+    free_cores(r, fc);
+    for (int k = 0; k < NHD_MAX_NUMA; k++) { d.fc[k] = (uint8_t)fc[k]; d.consumed[k] = 0; }
+    d.gpu_used = r.gpu_used;
+    d.info = (uint16_t)((rec_smt(r) ? NHD_DYN_SMT : 0) | (r.n_numa << 2));
+    d.nic_inuse = r.nic_inuse;
+    d.free_hugepages_gb = r.free_hugepages_gb;
+    d.hw_class = NHD_NO_CLASS;
+    d.n_gpus = r.n_gpus;
+    d.n_nics = r.n_nics;
+    d.busy_time = r.busy_time;
+}
+
+/* overlay the summary on a record that holds the static fields */
+NHD_HD void apply_dyn(nhd_node_rec& r, const NodeDyn& d)
+{
+    r.gpu_used = d.gpu_used;
+    r.nic_inuse = d.nic_inuse;
+    r.free_hugepages_gb = d.free_hugepages_gb;
+    r.busy_time = d.busy_time;
+}
+
+/*
+ * Cheap NECESSARY conditions for (pod type, node summary) to be feasible; true means the node
+ * cannot be in filts[1] (so skipping it is exact).  Covers the ways a node typically fills up:
+ * hugepages (Matcher.py:78), total / largest-chunk core demand (:203-212), free GPUs (:118-129)
+ * and every NIC already owned by a pod (Node.py:292) while the pod wants bandwidth.
+ */
+NHD_HD bool summary_infeasible(const PodType& t, const NodeDyn& d)
+{
+    if (t.pod.hugepages_gb > d.free_hugepages_gb) return true;
+    const bool smt = (d.info & NHD_DYN_SMT) != 0;
+    const int need = smt ? t.need_smt : t.need_nosmt, big = smt ? t.max_smt : t.max_nosmt;
+    const int sum = d.fc[0] + d.fc[1] + d.fc[2] + d.fc[3];
+    int mx = d.fc[0] > d.fc[1] ? d.fc[0] : d.fc[1];
+    const int mx2 = d.fc[2] > d.fc[3] ? d.fc[2] : d.fc[3];
+    mx = mx > mx2 ? mx : mx2;
+    if (sum < need || mx < big) return true;
+    if (t.total_gpus) {
+        const uint32_t fr = ~(uint32_t)d.gpu_used & ((1u << d.n_gpus) - 1);
+        if (popc32(fr) < t.total_gpus) return true;
+    }
+    if (t.has_bw) {
+        const uint32_t all = d.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << d.n_nics) - 1);
+        if ((d.nic_inuse & all) == all) return true;
+    }
+    return false;
+}
+
+/* stage_masks with the free-core counts taken from the summary */
+NHD_HD bool stage_masks_fc(const nhd_node_rec& r, const uint8_t* fc8, const PodType& t, const double* cap,
+                           uint64_t gsw, TMask& ma, TMask& mb, TMask& mc)
+{
+    const int K = r.n_numa, G = t.G;
+    int fg[NHD_MAX_NUMA], fc[NHD_MAX_NUMA];
+    free_gpus(r, fg);
+    for (int k = 0; k < NHD_MAX_NUMA; k++) fc[k] = fc8[k];
+    const bool smt = rec_smt(r);
+    const int np = ipow(K, G);
+    ma = tm_zero(); mb = tm_zero(); mc = tm_zero();
+    uint8_t p[NHD_MAX_GROUPS], idx[NHD_MAX_GROUPS], li[NHD_MAX_GROUPS];
+    bool anyA = false, anyB = false, anyC = false;
+    for (int pi = 0; pi < np; pi++) {
+        tuple_digits(pi, K, G, p);
+        if (gpu_ok(t, p, K, fg)) { tm_set(ma, pi); anyA = true; }
+        for (int m = 0; m < K; m++)
+            if (cpu_ok(t, p, m, K, fc, smt)) { tm_set(mb, pi * K + m); anyB = true; }
+        if (nic_first_fit(r, t, p, K, cap, gsw, idx, li)) { tm_set(mc, pi); anyC = true; }
+    }
+    return anyA && anyB && anyC;
+}
+
+/* physical cores a GetFreeCpuBatch(num, smt) call removes from a socket's eligible list,
+ * given `avail` eligible cores there (Node.py:502-519): SMT pairs take one core per two ids;
+ * a non-SMT request on an SMT node takes one core per id and, once the first-half ids run
+ * out, continues with the siblings of the cores it just took. */
+NHD_HD int batch_width(bool smt_node, bool smt_req, int num, int avail)
+{
+    if (!smt_node) return num;
+    if (smt_req) return (num + 1) / 2;
+    return num < avail ? num : avail;
+}
+
+/*
+ * Everything of SetPhysicalIdsFromMapping except the core ids (Node.py:663-841), on the
+ * summary: GPU picks, NIC claim order, hugepages, busy stamp, and the per-socket core
+ * accounting.  r holds the node's static fields with the summary overlaid (apply_dyn).
+ * b->cores[0..3] temporarily carries the pod's prefix offsets for assign_cores_from_snapshot.
+ */
+NHD_HD void assign_resources(const nhd_node_rec& r, NodeDyn& d, const PodType& t, const Mapping& m, double now,
+                             nhd_binding* b)
+{
+    const int G = t.G;
+    const bool smt_node = (d.info & NHD_DYN_SMT) != 0;
+    d.busy_time = now;                                             /* NHDScheduler.py:289 */
+    d.info |= NHD_DYN_TOUCHED;
+    b->n_groups = (uint8_t)G;
+    for (int g = 0; g < G; g++) {
+        b->gpu_numa[g] = m.gpu_numa[g];
+        b->cpu_numa[g] = m.gpu_numa[g];
+        b->nic_numa[g] = m.gpu_numa[g];
+        b->nic_idx[g] = m.nic_idx[g];
+        b->nic_list_index[g] = m.nic_li[g];
+    }
+    b->cpu_numa[G] = m.misc_numa;
+
+    uint16_t gpu_used = d.gpu_used;
+    int ng = 0, n_nic_rec = 0;
+    uint8_t nic_rec[NHD_MAX_GROUPS];
+    bool fail = false;
+    for (int g = 0; g < G && !fail; g++) {
+        const nhd_pod_group& pg = t.pod.groups[g];
+        const int numa = m.gpu_numa[g];
+        const int nsw = pg.n_gpus ? nic_switch(r, m.nic_li[g]) : 0;
+        for (int j = 0; j < pg.n_gpus; j++) {                       /* Node.py:707-726 */
+            uint32_t fr = ~(uint32_t)gpu_used & ((1u << r.n_gpus) - 1);
+            int dev = -1;
+            for (uint32_t f = fr; f; f &= f - 1) {
+                int i = ctz32(f);
+                if (gpu_switch(r, i) == nsw) { dev = i; break; }
+            }
+            if (dev < 0) {
+                if (t.pci) { fail = true; break; }
+                uint32_t f = fr & r.gpu_numa_mask[numa];
+                if (f) dev = ctz32(f);
+            }
+            if (dev < 0) { fail = true; break; }
+            gpu_used |= (uint16_t)(1u << dev);
+            if (ng < NHD_MAX_POD_GPUS) b->gpu_index[ng] = (uint8_t)dev;
+            ng++;
+        }
+        if (fail) break;
+        if (pg.flags & NHD_GRP_HAS_NIC_CORES) nic_rec[n_nic_rec++] = m.nic_li[g];
+    }
+    if (fail) {                                                      /* Node.py:825-837 */
+        b->n_cores = b->n_gpus = b->n_claimed = 0;
+        for (int i = 0; i < NHD_MAX_POD_GPUS; i++) b->gpu_index[i] = 0;
+        b->status = n_nic_rec ? NHD_REF_WOULD_CRASH : NHD_ASSIGN_FAILED;
+        return;
+    }
+    /* core accounting in call order: per group the proc batch then the helper batch, then misc */
+    uint8_t fc[NHD_MAX_NUMA];
+    for (int k = 0; k < NHD_MAX_NUMA; k++) { fc[k] = d.fc[k]; b->cores[k] = d.consumed[k]; }
+    for (int g = 0; g < G; g++) {
+        const nhd_pod_group& pg = t.pod.groups[g];
+        const int k = m.gpu_numa[g];
+        int w = batch_width(smt_node, (pg.flags & NHD_GRP_PROC_SMT) != 0, t.tot[g], fc[k]);
+        fc[k] = (uint8_t)(fc[k] - w);
+        w = batch_width(smt_node, (pg.flags & NHD_GRP_HELPER_SMT) != 0, pg.n_helpers, fc[k]);
+        fc[k] = (uint8_t)(fc[k] - w);
+    }
+    {
+        const int k = m.misc_numa;
+        int w = batch_width(smt_node, (t.pod.flags & NHD_POD_MISC_SMT) != 0, t.pod.n_misc, fc[k]);
+        fc[k] = (uint8_t)(fc[k] - w);
+    }
+    for (int k = 0; k < NHD_MAX_NUMA; k++) {
+        d.consumed[k] = (uint8_t)(d.consumed[k] + (d.fc[k] - fc[k]));
+        d.fc[k] = fc[k];
+    }
+    d.gpu_used = gpu_used;
+    if (t.pod.hugepages_gb > 0) d.free_hugepages_gb -= t.pod.hugepages_gb;
+    b->n_gpus = (uint8_t)ng;
+    const int ncl = claimed_nic_order(nic_rec, n_nic_rec, b->claimed_nics);
+    b->n_claimed = (uint8_t)ncl;
+    for (int i = 0; i < ncl; i++) d.nic_inuse |= 1u << b->claimed_nics[i];
+    b->status = NHD_PLACED;
+}
+
+/*
+ * The core ids of one placed pod, from the node's SNAPSHOT record (state at the start of the
+ * batch) and the pod's prefix offsets (b->cores[0..3] as left by assign_resources): the first
+ * offsets[k] eligible cores of socket k went to earlier pods of the batch.  Fills b->cores /
+ * b->n_cores and returns the logical ids taken as a mask.
+ */
+NHD_HDN M256 assign_cores_from_snapshot(const nhd_node_rec& snap, const PodType& t, nhd_binding* b)
+{
+    nhd_node_rec r = snap;
+    const int per = r.phys_cores / r.n_numa;
+    int offs[NHD_MAX_NUMA];
+    for (int k = 0; k < NHD_MAX_NUMA; k++) { offs[k] = b->cores[k]; b->cores[k] = 0; }
+    for (int k = 0; k < r.n_numa; k++) {
+        int off = offs[k];
+        M256 e = m_and(eligible_phys(r), m_range(k * per, (k + 1) * per));
+        for (int w = 0; w < 4 && off > 0; w++) {
+            uint64_t bits = e.w[w];
+            while (bits && off > 0) {
+                mark_used(r, 64 * w + ctz64(bits));                /* a used first-half id retires the whole core */
+                bits &= bits - 1;
+                off--;
+            }
+        }
+    }
+    const M256 before = rec_used(r);
+    uint8_t batch[NHD_MAX_POD_CORES + 2];
+    int nc = 0;
+    const int G = t.G;
+    for (int g = 0; g < G; g++) {
+        const nhd_pod_group& pg = t.pod.groups[g];
+        const int numa = b->gpu_numa[g];
+        int n = cpu_batch(r, numa, t.tot[g], (pg.flags & NHD_GRP_PROC_SMT) != 0, batch);
+        for (int k = 0; k < n; k++) { mark_used(r, batch[k]); if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[k]; nc++; }
+        n = cpu_batch(r, numa, pg.n_helpers, (pg.flags & NHD_GRP_HELPER_SMT) != 0, batch);
+        for (int k = 0; k < n; k++) { mark_used(r, batch[k]); if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[k]; nc++; }
+    }
+    {
+        int n = cpu_batch(r, b->cpu_numa[G], t.pod.n_misc, (t.pod.flags & NHD_POD_MISC_SMT) != 0, batch);
+        for (int k = 0; k < n; k++) { mark_used(r, batch[k]); if (nc < NHD_MAX_POD_CORES) b->cores[nc] = batch[k]; nc++; }
+    }
+    b->n_cores = (uint8_t)nc;
+    return m_andnot(rec_used(r), before);
 }
 
 } // namespace nhd

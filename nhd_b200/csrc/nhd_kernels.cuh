@@ -89,6 +89,72 @@ __global__ void export_kernel(const uint8_t* __restrict__ tiled, int first, int 
     aos[i] = *reinterpret_cast<const uint4*>(tiled + chunk_off(first + rec, c));
 }
 
+/* ------------------------------------------------------------------ hardware classes */
+
+/*
+ * Nodes with the same static hardware description (NUMA count, SMT, GPU / NIC placement,
+ * switches, link speeds) get the same small class id, so that decisions can be memoised per
+ * (pod type, class, free counts).  Ids are exact: a slot is claimed by 64-bit hash and every
+ * node then verifies the full 68-byte key against its slot; a mismatch (hash collision) or a
+ * full table just leaves the node without a class (NHD_NO_CLASS), which only bypasses the memo.
+ */
+constexpr int CLASS_SLOTS = 4096;
+constexpr int CLASS_KEY_WORDS = 17;
+struct ClassSlot { unsigned long long hash; uint32_t key[CLASS_KEY_WORDS]; uint32_t pad; };
+
+__device__ __forceinline__ unsigned long long static_key(const uint8_t* nodes, int node, uint32_t* key)
+{
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint4 q = *reinterpret_cast<const uint4*>(nodes + chunk_off(node, 4 + c));
+        key[4 * c] = q.x; key[4 * c + 1] = q.y; key[4 * c + 2] = q.z; key[4 * c + 3] = q.w;
+    }
+    const uint4 c2 = *reinterpret_cast<const uint4*>(nodes + chunk_off(node, 2));
+    /* n_gpus, n_nics (bytes 2,3 of word 0), n_numa and the SMT flag (bytes 0,1 of word 3) */
+    key[16] = (c2.x >> 16) | ((c2.w & 0xFF) << 16) | (((c2.w >> 8) & NHD_NODE_SMT) << 24);
+    unsigned long long h = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int i = 0; i < CLASS_KEY_WORDS; i++) { h ^= key[i]; h *= 0xff51afd7ed558ccdULL; h ^= h >> 29; }
+    return h | 1ULL;                                   /* 0 marks an empty slot */
+}
+
+__global__ void classify_claim_kernel(const uint8_t* __restrict__ nodes, const int32_t* __restrict__ idx, int n,
+                                      ClassSlot* slots, uint16_t* class_id)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int node = idx ? idx[i] : i;
+    uint32_t key[CLASS_KEY_WORDS];
+    const unsigned long long h = static_key(nodes, node, key);
+    uint16_t cid = NHD_NO_CLASS;
+    for (int probe = 0; probe < 64; probe++) {
+        const int s = (int)((h + (unsigned long long)probe * 0x9E37ULL) & (CLASS_SLOTS - 1));
+        const unsigned long long old = atomicCAS(&slots[s].hash, 0ULL, h);
+        if (old == 0ULL) {
+            for (int w = 0; w < CLASS_KEY_WORDS; w++) slots[s].key[w] = key[w];
+            cid = (uint16_t)s;
+            break;
+        }
+        if (old == h) { cid = (uint16_t)s; break; }
+    }
+    class_id[node] = cid;
+}
+
+__global__ void classify_verify_kernel(const uint8_t* __restrict__ nodes, const int32_t* __restrict__ idx, int n,
+                                       const ClassSlot* __restrict__ slots, uint16_t* class_id)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int node = idx ? idx[i] : i;
+    const uint16_t cid = class_id[node];
+    if (cid == NHD_NO_CLASS) return;
+    uint32_t key[CLASS_KEY_WORDS];
+    static_key(nodes, node, key);
+    bool same = true;
+    for (int w = 0; w < CLASS_KEY_WORDS; w++) same = same && (slots[cid].key[w] == key[w]);
+    if (!same) class_id[node] = NHD_NO_CLASS;
+}
+
 /* ------------------------------------------------------------------ TMA / mbarrier helpers */
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,9 +193,12 @@ struct FilterArgs {
     const PodType* types;
     int n_types;
     int n_nodes;
-    int super_lo, super_hi;      /* this rank's shard, in super-tiles */
+    int n_super;                 /* all super-tiles (summaries are produced for every node)  */
+    int super_lo, super_hi;      /* this rank's shard, in super-tiles (bitmaps only for it)   */
     int words;                   /* u64 words per bitmap */
     uint64_t* bitmaps;           /* [n_types + 2][words]: F[0..T), NOGPU, BUSY */
+    uint4* dyn;                  /* [n_nodes padded][2]: NodeDyn summaries */
+    const uint16_t* class_id;    /* hardware class of every node */
     double now0;                 /* clock of the first pod, for the BUSY snapshot */
     double min_busy;
     double cap[NHD_MAX_SPEED_CLASSES];
@@ -144,7 +213,7 @@ filter_kernel(const FilterArgs a)
     __shared__ __align__(8) uint64_t full_bar[FILTER_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_my = (a.super_hi - a.super_lo - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_my = (a.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (n_my <= 0) return;
 
     if (tid == 0) {
@@ -154,7 +223,7 @@ filter_kernel(const FilterArgs a)
     __syncthreads();
 
     auto issue = [&](int it) {                                          /* thread 0 only */
-        int st = a.super_lo + blockIdx.x + it * gridDim.x;
+        int st = blockIdx.x + it * gridDim.x;
         int s = it % FILTER_STAGES;
         mbar_expect_tx(&full_bar[s], SUPER_BYTES);
         tma_load_1d(stage_buf + s * SUPER_BYTES, a.nodes + (size_t)st * SUPER_BYTES, SUPER_BYTES, &full_bar[s]);
@@ -177,7 +246,7 @@ filter_kernel(const FilterArgs a)
 
     for (int it = 0; it < n_my; it++) {
         const int s = it % FILTER_STAGES;
-        const int st = a.super_lo + blockIdx.x + it * gridDim.x;
+        const int st = blockIdx.x + it * gridDim.x;
         mbar_wait(&full_bar[s], (it / FILTER_STAGES) & 1);
 
         RecU u;
@@ -190,8 +259,18 @@ filter_kernel(const FilterArgs a)
 
         const int node = st * SUPER_NODES + tid;
         const bool valid = node < a.n_nodes;
-        const size_t w32 = (size_t)node >> 5;
 
+        /* per-node summary for the sweep (every rank needs all of them) */
+        {
+            union { NodeDyn d; uint4 q[2]; } du;
+            if (valid) { make_dyn(u.r, du.d); du.d.hw_class = a.class_id[node]; }
+            else { du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0]; }
+            a.dyn[(size_t)node * 2] = du.q[0];
+            a.dyn[(size_t)node * 2 + 1] = du.q[1];
+        }
+        if (st < a.super_lo || st >= a.super_hi) continue;              /* bitmaps: own shard only */
+
+        const size_t w32 = (size_t)node >> 5;
         for (int t = 0; t < a.n_types; t++) {
             bool f = valid && node_feasible(u.r, types[t], a.cap);
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, f);
@@ -208,6 +287,29 @@ filter_kernel(const FilterArgs a)
 
 /* ------------------------------------------------------------------ select + assign sweep */
 
+#ifdef NHD_PROFILE
+#define PROF_DECL long long prof_t0 = clock64(); long long prof_acc[16] = {0}; long long prof_cnt[16] = {0};
+#define PROF_MARK(i) do { long long t_ = clock64(); prof_acc[i] += t_ - prof_t0; prof_cnt[i]++; prof_t0 = t_; } while (0)
+#define PROF_COUNT(i) do { prof_cnt[i]++; } while (0)
+#define PROF2_DECL long long p2_t0 = clock64();
+#define PROF2(i) do { long long t_ = clock64(); if (cx.lane == 0) atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - p2_t0)); p2_t0 = t_; } while (0)
+#define PROF_FLUSH(buf) do { if (lane == 0) for (int i_ = 0; i_ < 16; i_++) { (buf)[i_] = (unsigned long long)prof_acc[i_]; (buf)[32 + i_] = (unsigned long long)prof_cnt[i_]; } } while (0)
+#else
+#define PROF2_DECL
+#define PROF2(i)
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_COUNT(i)
+#define PROF_FLUSH(buf)
+#endif
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int SMEMO_SLOTS = 512;                  /* shared-memory front of the mapping memo (16 B)  */
+constexpr int DMEMO_SLOTS = 512;                  /* decision memo (48 B entries)                    */
+
+constexpr int DCACHE_SLOTS = 128;                 /* node-summary cache (32 B entries + tag)          */
+constexpr int SWEEP_TYPES_SMEM_MAX = 64;
+
 struct SweepArgs {
     uint8_t* nodes;
     const PodType* types;
@@ -215,83 +317,713 @@ struct SweepArgs {
     const double* now;
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
+    int dual;                    /* 1: constant clock -> GPU pods and CPU-only pods on two warps */
     uint64_t* bitmaps;           /* [n_types + 2][words] */
-    int32_t* cursors;            /* [n_types][2] first possibly non-empty word (pass 0 = GPU-less nodes) */
+    uint4* dyn;                  /* NodeDyn summaries */
+    int32_t* cursors;            /* global fallback: [n_types][2] */
     int32_t* busy_list;          /* nodes whose BUSY bit is set */
-    uint64_t* memo;              /* MEMO_SLOTS x 2 words */
+    int32_t* pend_pod;           /* [n_nodes] pod whose resolution is pending on the node */
+    uint64_t* memo;              /* MEMO_SLOTS x 2 words (global, persists across batches) */
+    unsigned long long* prof;    /* debug counters (NHD_PROFILE builds) */
+    int* sweep_done;             /* set by block 0 when the sweep has finished */
     double min_busy;
     double cap[NHD_MAX_SPEED_CLASSES];
 };
 
-/* mapping memo: (K, G, stage masks) -> (gtuple index, misc NUMA) for K^(G+1) <= 32 */
+/* mapping memo: (K, G, stage-mask ballots) -> (gtuple index, misc NUMA), for K^(G+1) <= 32.
+ * The three ballots are indexed by q = p*K + m (A and C use the m == 0 lanes). */
 __device__ __forceinline__ uint64_t memo_mix(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
 
-__device__ bool choose_mapping_memo(uint64_t* memo, int K, int G, const TMask& ma, const TMask& mb, const TMask& mc,
-                                    int* ps, int* ms)
+/* lane-0 only.  Returns -1 infeasible, else ps | ms << 8 */
+__device__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G, uint32_t balA, uint32_t balB, uint32_t balC)
 {
-    const int nq = ipow(K, G + 1);
-    if (nq > 32) return choose_mapping(K, G, ma, mb, mc, ps, ms);
-    const uint64_t key = (ma.w[0] & 0xFFFF) | ((mb.w[0] & 0xFFFFFFFFULL) << 16) | ((mc.w[0] & 0xFFFF) << 48);
-    const uint64_t tag = 0x8000000000000000ULL | ((uint64_t)K << 8) | (uint64_t)G;     /* bit 63 = occupied */
-    uint64_t h = memo_mix(key ^ (tag * 0x9E3779B97F4A7C15ULL));
-    int free_slot = -1;
+    const uint32_t tag = 0x80000000u | ((uint32_t)K << 24) | ((uint32_t)G << 16);
+    const uint64_t h = memo_mix(((uint64_t)balA << 32 | balB) ^ ((uint64_t)balC * 0x9E3779B97F4A7C15ULL) ^ tag);
+    const int ss = (int)(h & smemo_mask);
+    const uint4 e = smemo[ss];
+    if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
+        const int v = (int)(e.w & 0xFFFF);
+        return v == 0xFFFF ? -1 : v;
+    }
+    /* global memo: key = two words */
+    const uint64_t k0 = (uint64_t)balA << 32 | balB, k1tag = ((uint64_t)tag << 32) | balC;
+    int free_slot = -1, val = -2;
     for (int probe = 0; probe < 8; probe++) {
-        const int s = (int)((h + probe) & (MEMO_SLOTS - 1));
-        const uint64_t k0 = memo[2 * s], k1 = memo[2 * s + 1];
-        if (!(k1 >> 63)) { free_slot = s; break; }
-        if (k0 == key && (k1 & 0x800000000000FFFFULL) == tag) {
-            const int v = (int)((k1 >> 16) & 0xFFFF);
-            if (v == 0xFFFF) return false;
-            *ps = v & 0xFF; *ms = v >> 8;
-            return true;
+        const int s = (int)(((h >> 16) + probe) & (MEMO_SLOTS - 1));
+        const ulonglong2 ge = __ldcg(reinterpret_cast<const ulonglong2*>(gmemo) + s);   /* one 16-byte access: two warps share this table */
+        const uint64_t g0 = ge.x, g1 = ge.y;
+        if (!(g1 >> 63)) { free_slot = s; break; }
+        if (g0 == k0 && (g1 & 0xFFFF0000FFFFFFFFULL) == k1tag) { val = (int)((g1 >> 32) & 0xFFFF); break; }
+    }
+    if (val == -2) {
+        TMask ma = tm_zero(), mb = tm_zero(), mc = tm_zero();
+        mb.w[0] = balB;
+        const int np = ipow(K, G);
+        for (int p = 0; p < np; p++) {
+            if ((balA >> (p * K)) & 1) tm_set(ma, p);
+            if ((balC >> (p * K)) & 1) tm_set(mc, p);
+        }
+        int ps, ms;
+        val = choose_mapping(K, G, ma, mb, mc, &ps, &ms) ? (ps | (ms << 8)) : 0xFFFF;
+        if (free_slot >= 0) {
+            reinterpret_cast<ulonglong2*>(gmemo)[free_slot] = make_ulonglong2(k0, k1tag | ((uint64_t)val << 32));
         }
     }
-    const bool ok = choose_mapping(K, G, ma, mb, mc, ps, ms);
-    if (free_slot >= 0) {
-        const uint64_t v = ok ? (uint64_t)((*ps & 0xFF) | (*ms << 8)) : 0xFFFFULL;
-        memo[2 * free_slot] = key;
-        memo[2 * free_slot + 1] = tag | (v << 16);
-    }
-    return ok;
-}
-
-__device__ bool evaluate_mapping_memo(uint64_t* memo, const nhd_node_rec& r, const PodType& t, const double* cap, Mapping* out)
-{
-    const int K = r.n_numa, G = t.G;
-    const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
-    TMask ma, mb, mc;
-    if (!stage_masks(r, t, cap, gsw, ma, mb, mc)) return false;
-    int ps, ms;
-    if (!choose_mapping_memo(memo, K, G, ma, mb, mc, &ps, &ms)) return false;
-    tuple_digits(ps, K, G, out->gpu_numa);
-    out->misc_numa = (uint8_t)ms;
-    nic_first_fit(r, t, out->gpu_numa, K, cap, gsw, out->nic_idx, out->nic_li);
-    return true;
+    smemo[ss] = make_uint4(balA, balB, balC, tag | (uint32_t)val);
+    return val == 0xFFFF ? -1 : val;
 }
 
 /*
- * One warp walks the pods in order.  Bitmap scanning, busy-list maintenance and record
- * transfers use all 32 lanes; the evaluation of the (usually single) candidate and the
- * assignment run on lane 0.
+ * Decision memo entry (48 B).  Everything AttemptScheduling decides for (pod type, node) apart
+ * from the core ids is a pure function of
+ *     pod type, hardware class of the node, which GPUs and NICs are taken, and, per NUMA node,
+ *     the largest per-socket demand any NUMA tuple of this type can make that still fits the
+ *     free physical cores (the tuple predicates of Matcher.py:204-212 compare the free count
+ *     with sums of sub-sets of the type's per-group demands and nothing else),
+ * which is exactly the key.  Values are only ever produced by the full evaluation below.
  */
-__global__ void __launch_bounds__(32, 1)
+struct DEntry {
+    unsigned long long a;        /* type(12) | class(12) | gpu_used(16) | effective fc 4 x 6 */
+    uint32_t nic_inuse;
+    uint8_t  state;              /* 0 empty, 1 no mapping, 2 placed, 3 assignment fails */
+    uint8_t  ms, ncl, ng;
+    uint32_t pn, idx, li;        /* per-group NUMA node / per-NUMA NIC index / NIC list index, one byte each */
+    uint32_t claimed;            /* claimed NIC list indices in CPython set order */
+    uint32_t gi;                 /* first four picked GPU indices */
+    uint16_t gpu_used_new;
+    uint8_t  fail_status;
+    uint8_t  pad_;
+    uint32_t pad2_[2];
+};
+static_assert(sizeof(DEntry) == 48, "DEntry is three 16-byte chunks");
+
+struct PMap { uint32_t pn, idx, li, ms; };      /* a mapping, one byte per group */
+
+__device__ __forceinline__ uint32_t pack_digits(int ps, int K, int G)
+{
+    uint8_t d[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+    tuple_digits(ps, K, G, d);
+    return (uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24);
+}
+
+/*
+ * Full evaluation of (pod type, node) — memo miss path.  All 32 lanes enter with the same
+ * arguments; for K^(G+1) <= 32 each lane owns one (G+1)-tuple and the stage masks are warp
+ * ballots, otherwise lane 0 enumerates.  Returns feasibility and the mapping (uniform).
+ */
+__device__ bool evaluate_full(const SweepArgs& a, uint4* smemo, int smemo_mask, const nhd_node_rec& r, const NodeDyn& d,
+                              const PodType& t, int lane, PMap& pm)
+{
+    const int K = r.n_numa, G = t.G;
+    const bool smt = rec_smt(r);
+    const int nq = ipow(K, G + 1);
+    if (nq <= 32) {
+        const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+        int fg[NHD_MAX_NUMA], fc[NHD_MAX_NUMA];
+        free_gpus(r, fg);
+        for (int k = 0; k < NHD_MAX_NUMA; k++) fc[k] = d.fc[k];
+        uint8_t dg[NHD_MAX_GROUPS + 1], idx[NHD_MAX_GROUPS] = {0, 0, 0, 0}, li[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+        bool okA = false, okB = false, okC = false;
+        if (lane < nq) {
+            tuple_digits(lane, K, G + 1, dg);
+            const int mm = dg[G];
+            okB = cpu_ok(t, dg, mm, K, fc, smt);
+            if (mm == 0) {
+                okA = gpu_ok(t, dg, K, fg);
+                okC = nic_first_fit(r, t, dg, K, a.cap, gsw, idx, li);
+            }
+        }
+        const uint32_t balA = __ballot_sync(0xFFFFFFFFu, okA);
+        const uint32_t balB = __ballot_sync(0xFFFFFFFFu, okB);
+        const uint32_t balC = __ballot_sync(0xFFFFFFFFu, okC);
+        if (!(balA && balB && balC)) return false;
+        int v = -1;
+        if (lane == 0) v = choose_mapping_memo(smemo, smemo_mask, a.memo, K, G, balA, balB, balC);
+        v = __shfl_sync(0xFFFFFFFFu, v, 0);
+        if (v < 0) return false;
+        const int ps = v & 0xFF;
+        uint32_t pk = 0, pl = 0;
+        for (int g = 0; g < NHD_MAX_GROUPS; g++) { pk |= (uint32_t)idx[g] << (8 * g); pl |= (uint32_t)li[g] << (8 * g); }
+        pm.idx = __shfl_sync(0xFFFFFFFFu, pk, ps * K);
+        pm.li = __shfl_sync(0xFFFFFFFFu, pl, ps * K);
+        pm.pn = pack_digits(ps, K, G);
+        pm.ms = (uint32_t)(v >> 8);
+        return true;
+    }
+    /* large enumerations: scalar on lane 0 */
+    uint32_t okl = 0, pk = 0, pl = 0;
+    int ps = 0, ms = 0;
+    if (lane == 0) {
+        const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+        TMask ma, mb, mc;
+        if (stage_masks_fc(r, d.fc, t, a.cap, gsw, ma, mb, mc) && choose_mapping(K, G, ma, mb, mc, &ps, &ms)) {
+            uint8_t dg[NHD_MAX_GROUPS], idx[NHD_MAX_GROUPS] = {0, 0, 0, 0}, li[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+            tuple_digits(ps, K, G, dg);
+            nic_first_fit(r, t, dg, K, a.cap, gsw, idx, li);
+            for (int g = 0; g < NHD_MAX_GROUPS; g++) { pk |= (uint32_t)idx[g] << (8 * g); pl |= (uint32_t)li[g] << (8 * g); }
+            okl = 1;
+        }
+    }
+    okl = __shfl_sync(0xFFFFFFFFu, okl, 0);
+    if (!okl) return false;
+    ps = __shfl_sync(0xFFFFFFFFu, ps, 0);
+    pm.ms = (uint32_t)__shfl_sync(0xFFFFFFFFu, ms, 0);
+    pm.idx = __shfl_sync(0xFFFFFFFFu, pk, 0);
+    pm.li = __shfl_sync(0xFFFFFFFFu, pl, 0);
+    pm.pn = pack_digits(ps, K, G);
+    return true;
+}
+
+/* resource part of one decision: GPU picks (Node.py:707-726) and NIC claim order
+ * (NHDScheduler.py:302), a pure function of (pod type, mapping, gpu_used, static GPU/NIC layout) */
+struct Picks {
+    unsigned long long gi_lo, gi_hi;     /* gpu_index[16] */
+    uint32_t claimed, gpu_used_new;
+    int ng, ncl, fail_status;            /* fail_status: 0 or NHD_ASSIGN_FAILED / NHD_REF_WOULD_CRASH */
+};
+
+__device__ void compute_picks(const nhd_node_rec& r, const PodType& t, const PMap& pm, uint32_t gpu_used, int n_gpus, Picks& pk)
+{
+    const int G = t.G;
+    pk.gi_lo = pk.gi_hi = 0; pk.claimed = 0; pk.ng = pk.ncl = 0; pk.fail_status = 0;
+    int n_rec = 0;
+    uint8_t rec[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+    bool fail = false;
+    for (int g = 0; g < G && !fail; g++) {
+        const nhd_pod_group& pg = t.pod.groups[g];
+        const int numa = (pm.pn >> (8 * g)) & 0xFF, lig = (pm.li >> (8 * g)) & 0xFF;
+        if (pg.n_gpus) {
+            const int nsw = nic_switch(r, lig);
+            for (int jg = 0; jg < pg.n_gpus; jg++) {
+                const uint32_t fr = ~gpu_used & ((1u << n_gpus) - 1);
+                int dev = -1;
+                for (uint32_t f = fr; f; f &= f - 1) {              /* GetFreePciGpuFromNic :648-655 */
+                    const int gi = ctz32(f);
+                    if (gpu_switch(r, gi) == nsw) { dev = gi; break; }
+                }
+                if (dev < 0) {
+                    if (t.pci) { fail = true; break; }              /* :711-713 */
+                    const uint32_t f = fr & r.gpu_numa_mask[numa];  /* GetNextGpuFree :495-500 */
+                    if (f) dev = ctz32(f);
+                }
+                if (dev < 0) { fail = true; break; }
+                gpu_used |= 1u << dev;
+                if (pk.ng < 8) pk.gi_lo |= (unsigned long long)dev << (8 * pk.ng);
+                else if (pk.ng < 16) pk.gi_hi |= (unsigned long long)dev << (8 * (pk.ng - 8));
+                pk.ng++;
+            }
+            if (fail) break;
+        }
+        if (pg.flags & NHD_GRP_HAS_NIC_CORES) rec[n_rec++] = (uint8_t)lig;
+    }
+    if (fail) {                                                      /* Node.py:825-837 */
+        pk.fail_status = n_rec ? NHD_REF_WOULD_CRASH : NHD_ASSIGN_FAILED;
+        pk.gi_lo = pk.gi_hi = 0; pk.ng = 0;
+        return;
+    }
+    pk.gpu_used_new = gpu_used;
+    uint8_t outc[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+    pk.ncl = claimed_nic_order(rec, n_rec, outc);
+    pk.claimed = (uint32_t)outc[0] | ((uint32_t)outc[1] << 8) | ((uint32_t)outc[2] << 16) | ((uint32_t)outc[3] << 24);
+}
+
+/* set / clear one bit of a 64-bit bitmap word with a native 32-bit atomic (works for shared and global) */
+__device__ __forceinline__ void bit_set(uint64_t* words, int bit)
+{
+    atomicOr(reinterpret_cast<unsigned int*>(words) + (bit >> 5), 1u << (bit & 31));
+}
+__device__ __forceinline__ void bit_clear(uint64_t* words, int bit)
+{
+    atomicAnd(reinterpret_cast<unsigned int*>(words) + (bit >> 5), ~(1u << (bit & 31)));
+}
+
+#define NHD_PENDING      100          /* internal binding status: node chosen, mapping not resolved yet */
+#define NHD_DYN_PENDING  0x20         /* NodeDyn.info: the node's first pod of this batch is still unresolved */
+
+/* per-warp view of the sweep's shared-memory tables */
+struct ClsNic;
+struct SweepCtx {
+    uint4* smemo;            /* mapping memo front      */
+    uint4* dmemo;            /* decision memo           */
+    uint4* dcache;           /* node-summary cache      */
+    int32_t* dtag;
+    const uint8_t* s_eff;    /* effective free-core tables [T][2][64] */
+    const PodType* types;
+    bool types_in_smem;
+    int lane;
+    int smemo_mask, dmemo_mask, dcache_mask;   /* table sizes - 1 (halved when two warps sweep) */
+    int32_t* peer_dtag;      /* summary-cache tags of the other sweeping warp (two-warp mode), else null */
+    const uint16_t* s_needb; /* [T][2][32] per-tuple socket demand for 2-NUMA nodes: need0 | need1 << 8 */
+    struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 32 B: static NIC layout per hardware class */
+};
+
+union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
+
+__device__ __forceinline__ void load_dyn(const SweepArgs& a, const SweepCtx& cx, int node, DynU& du)
+{
+    const int cs = node & cx.dcache_mask;
+    if (cx.dtag[cs] == node) { du.q[0] = cx.dcache[2 * cs]; du.q[1] = cx.dcache[2 * cs + 1]; }
+    else { du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]); }   /* L2: the sweep also updates summaries with atomics */
+}
+
+/* HBM copy (later batches / commit_kernel read it) + shared-memory cache */
+__device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx, int node, const DynU& du)
+{
+    if (cx.lane < 2) {
+        a.dyn[(size_t)node * 2 + cx.lane] = du.q[cx.lane];
+        cx.dcache[2 * (node & cx.dcache_mask) + cx.lane] = du.q[cx.lane];
+    }
+    if (cx.lane == 2) cx.dtag[node & cx.dcache_mask] = node;
+    /* the other sweeping warp may hold an older copy of this node (spills, revisits) */
+    if (cx.lane == 3 && cx.peer_dtag && cx.peer_dtag[node & cx.dcache_mask] == node) cx.peer_dtag[node & cx.dcache_mask] = -1;
+}
+
+/* claimed NIC order, list({x[0] for x in nic_list}) (NHDScheduler.py:302), registers only:
+ * the 8-slot CPython set table lives in one 64-bit word (slot byte = NIC index + 1) */
+__device__ __forceinline__ uint32_t claimed_order_packed(uint32_t rec, int n_rec, int& ncl)
+{
+    unsigned long long slots = 0;
+    for (int e = 0; e < n_rec; e++) {
+        const uint32_t v = (rec >> (8 * e)) & 0xFF;
+        uint32_t i = v & 7, perturb = v;
+        for (;;) {
+            const uint32_t sl = (uint32_t)(slots >> (8 * i)) & 0xFF;
+            if (sl == 0) { slots |= (unsigned long long)(v + 1) << (8 * i); break; }
+            if (sl == v + 1) break;
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & 7;
+        }
+    }
+    uint32_t out = 0;
+    ncl = 0;
+    for (int i = 0; i < 8; i++) {
+        const uint32_t sl = (uint32_t)(slots >> (8 * i)) & 0xFF;
+        if (sl) { out |= (sl - 1) << (8 * ncl); ncl++; }
+    }
+    return out;
+}
+
+/* static NIC layout of one hardware class, cached in shared memory (32 B) */
+struct ClsNic { uint32_t tag; uint32_t m0, m1, pad; unsigned long long sp0, sp1; };
+constexpr int CLSNIC_SLOTS = 64;
+
+/*
+ * CPU-only pod, NUMA mode, on a 2-NUMA node (the reference's deployment shape) — the decision
+ * factorises and is computed directly, without enumerating joint NIC choices:
+ *   CPU stage   (Matcher.py:203-212)  lane q compares the type's precomputed per-socket demand of
+ *               tuple q with the two free-core counts: one ballot;
+ *   GPU stage   (Matcher.py:118-129)  no GPUs requested: every tuple passes;
+ *   NIC stage   (Matcher.py:242-268)  NICs of different NUMA nodes do not interact (no PCI pruning in
+ *               NUMA mode), so the first surviving entry for a tuple is the pair of first
+ *               surviving sub-assignments of {groups on NUMA 0} and {groups on NUMA 1}.  Lane
+ *               k*16 + S solves "groups S on the NICs of NUMA k" with the reference's own
+ *               order (first group most significant, fp64 subtraction in group order); tuple
+ *               lanes then read their two halves with shuffles;
+ *   GetNumaGroupIdx (Matcher.py:423-452)  mapping memo on the three masks.
+ * Same results as evaluate_full + compute_picks; returns 1 (not a candidate) or 2 (placed).
+ */
+__device__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
+                            const DynU& du, PMap& pm, Picks& pk, bool& missed)
+{
+    PROF2_DECL
+    const int lane = cx.lane, G = t.G, nq = 1 << (G + 1), gmask = (1 << G) - 1;
+    const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
+    const uint32_t nb = cx.s_needb[(ti * 2 + (smt ? 1 : 0)) * 32 + lane];
+    const bool okB = lane < nq && (nb & 0xFF) <= du.d.fc[0] && (nb >> 8) <= du.d.fc[1];
+    const uint32_t balB = __ballot_sync(0xFFFFFFFFu, okB);
+    if (!balB) return 1;
+    const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
+
+    /* static NIC layout of the node's hardware class */
+    ClsNic* ce = &cx.clsnic[du.d.hw_class & (CLSNIC_SLOTS - 1)];
+    uint32_t m0, m1;
+    unsigned long long sp0, sp1;
+    if (ce->tag == (uint32_t)du.d.hw_class + 1u) {
+        m0 = ce->m0; m1 = ce->m1; sp0 = ce->sp0; sp1 = ce->sp1;
+    } else {
+        missed = true;
+        const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
+        const uint4 c7 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 7));
+        m0 = c5.x; m1 = c5.y;
+        sp0 = (unsigned long long)c7.x | ((unsigned long long)c7.y << 32);
+        sp1 = (unsigned long long)c7.z | ((unsigned long long)c7.w << 32);
+        __syncwarp();
+        if (lane == 0) { ce->m0 = m0; ce->m1 = m1; ce->sp0 = sp0; ce->sp1 = sp1; ce->pad = 0; ce->tag = (uint32_t)du.d.hw_class + 1u; }
+        __syncwarp();
+    }
+
+    PROF2(0);   /* B mask + class layout */
+    /* ---- sub-problems: lane = k * 16 + S ---- */
+    const int k = lane >> 4, S = lane & 15;
+    const uint32_t mk = k ? m1 : m0;
+    const uint32_t inuse = du.d.nic_inuse;
+    bool feas = false;
+    uint32_t r_idx = 0, r_li = 0;                      /* one byte per member of S, in group order */
+    if (S <= gmask) {
+        /* members of S in group order, and their demands, in registers */
+        const int n = popc32((uint32_t)S);
+        int sr = S;
+        const int g0 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g1 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g2 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g3 = sr ? ctz32((uint32_t)sr) : 0;
+        const double rx[NHD_MAX_GROUPS] = {t.pod.groups[g0].rx_gbps, t.pod.groups[g1].rx_gbps, t.pod.groups[g2].rx_gbps, t.pod.groups[g3].rx_gbps};
+        const double tx[NHD_MAX_GROUPS] = {t.pod.groups[g0].tx_gbps, t.pod.groups[g1].tx_gbps, t.pod.groups[g2].tx_gbps, t.pod.groups[g3].tx_gbps};
+        auto capof = [&](int l) -> double {
+            if ((inuse >> l) & 1) return 0.0;
+            const int sc = (int)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF);
+            return a.cap[sc];
+        };
+        if (n == 0) feas = true;
+        else if (mk != 0) {
+            for (uint32_t f0 = mk; f0 && !feas; f0 &= f0 - 1) {
+                const int l0 = ctz32(f0);
+                const double c0 = capof(l0);
+                const double r0 = c0 - rx[0], t0 = c0 - tx[0];
+                if (r0 < 0 || t0 < 0) continue;
+                if (n == 1) { feas = true; r_li = l0; break; }
+                for (uint32_t f1 = mk; f1 && !feas; f1 &= f1 - 1) {
+                    const int l1 = ctz32(f1);
+                    const double c1 = capof(l1);
+                    const double r1 = (l1 == l0 ? r0 : c1) - rx[1], t1 = (l1 == l0 ? t0 : c1) - tx[1];
+                    if (r1 < 0 || t1 < 0) continue;
+                    if (n == 2) { feas = true; r_li = l0 | (l1 << 8); break; }
+                    for (uint32_t f2 = mk; f2 && !feas; f2 &= f2 - 1) {
+                        const int l2 = ctz32(f2);
+                        const double c2 = capof(l2);
+                        const double b2r = l2 == l1 ? r1 : (l2 == l0 ? r0 : c2), b2t = l2 == l1 ? t1 : (l2 == l0 ? t0 : c2);
+                        const double r2 = b2r - rx[2], t2 = b2t - tx[2];
+                        if (r2 < 0 || t2 < 0) continue;
+                        if (n == 3) { feas = true; r_li = l0 | (l1 << 8) | (l2 << 16); break; }
+                        for (uint32_t f3 = mk; f3; f3 &= f3 - 1) {
+                            const int l3 = ctz32(f3);
+                            const double c3 = capof(l3);
+                            const double b3r = l3 == l2 ? r2 : (l3 == l1 ? r1 : (l3 == l0 ? r0 : c3));
+                            const double b3t = l3 == l2 ? t2 : (l3 == l1 ? t1 : (l3 == l0 ? t0 : c3));
+                            if (b3r - rx[3] < 0 || b3t - tx[3] < 0) continue;
+                            feas = true; r_li = l0 | (l1 << 8) | (l2 << 16) | ((uint32_t)l3 << 24);
+                            break;
+                        }
+                    }
+                }
+            }
+            if (feas)
+                for (int e = 0; e < n; e++) {
+                    const int l = (r_li >> (8 * e)) & 0xFF;
+                    r_idx |= (uint32_t)popc32(mk & ((1u << l) - 1)) << (8 * e);      /* NodeNic.idx = rank inside the NUMA node */
+                }
+        }
+    }
+    PROF2(1);   /* per-NUMA sub-problems */
+    /* ---- tuple lanes combine their two halves ---- */
+    bool okC = lane < nq && !(lane & 1);
+    {
+        /* every lane takes part in the shuffles; only tuple lanes use the result */
+        const int p = (lane >> 1) & gmask;
+        int s1 = 0;
+        for (int g = 0; g < G; g++) s1 |= ((p >> (G - 1 - g)) & 1) << g;
+        const int s0 = gmask & ~s1;
+        const int f0 = __shfl_sync(0xFFFFFFFFu, (int)feas, s0);
+        const int f1 = __shfl_sync(0xFFFFFFFFu, (int)feas, 16 + s1);
+        okC = okC && f0 && f1;
+    }
+    const uint32_t balC = __ballot_sync(0xFFFFFFFFu, okC);
+    if (!balC) return 1;
+    PROF2(2);   /* combine */
+    int v = -1;
+    if (lane == 0) v = choose_mapping_memo(cx.smemo, cx.smemo_mask, a.memo, 2, G, balA, balB, balC);
+    v = __shfl_sync(0xFFFFFFFFu, v, 0);
+    PROF2(3);   /* mapping memo */
+    if (v < 0) return 1;
+    const int ps = v & 0xFF;
+    pm.ms = (uint32_t)(v >> 8);
+    int s1 = 0;
+    pm.pn = 0;
+    for (int g = 0; g < G; g++) { const int dgt = (ps >> (G - 1 - g)) & 1; pm.pn |= (uint32_t)dgt << (8 * g); s1 |= dgt << g; }
+    const int s0 = gmask & ~s1;
+    const uint32_t li0 = __shfl_sync(0xFFFFFFFFu, r_li, s0), li1 = __shfl_sync(0xFFFFFFFFu, r_li, 16 + s1);
+    const uint32_t ix0 = __shfl_sync(0xFFFFFFFFu, r_idx, s0), ix1 = __shfl_sync(0xFFFFFFFFu, r_idx, 16 + s1);
+    pm.idx = pm.li = 0;
+    uint32_t rec = 0;
+    int n_rec = 0, e0 = 0, e1 = 0;
+    for (int g = 0; g < G; g++) {
+        uint32_t l, x;
+        if ((s1 >> g) & 1) { l = (li1 >> (8 * e1)) & 0xFF; x = (ix1 >> (8 * e1)) & 0xFF; e1++; }
+        else { l = (li0 >> (8 * e0)) & 0xFF; x = (ix0 >> (8 * e0)) & 0xFF; e0++; }
+        pm.li |= l << (8 * g);
+        pm.idx |= x << (8 * g);
+        if (t.pod.groups[g].flags & NHD_GRP_HAS_NIC_CORES) { rec |= l << (8 * n_rec); n_rec++; }
+    }
+    PROF2(4);   /* expand */
+    pk.claimed = claimed_order_packed(rec, n_rec, pk.ncl);
+    pk.gi_lo = pk.gi_hi = 0; pk.ng = 0; pk.fail_status = 0;
+    pk.gpu_used_new = du.d.gpu_used;
+    PROF2(5);   /* claim order */
+    return 2;
+}
+
+/*
+ * What would AttemptScheduling do with a pod of type ti on this node, given its summary?
+ * Returns 1 (FindNode would not offer the node), 2 (placed) or 3 (SetPhysicalIdsFromMapping
+ * fails) plus the mapping and the resource picks.  Decision memo first, full evaluation on a miss.
+ */
+__device__ int resolve_decision(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
+                                const DynU& du, PMap& pm, Picks& pk, bool& missed)
+{
+    missed = false;
+    if (summary_infeasible(t, du.d)) return 1;
+    const bool fast2 = cx.s_needb && t.total_gpus == 0 && !t.pci && ((du.d.info >> 2) & 7) == 2 && du.d.hw_class != NHD_NO_CLASS && ti < 4096;
+    const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
+    const int need = smt ? t.need_smt : t.need_nosmt;
+    const bool memoable = cx.types_in_smem && du.d.hw_class != NHD_NO_CLASS && need <= 63 && t.total_gpus <= 4;
+    unsigned long long key = (unsigned long long)ti | ((unsigned long long)du.d.hw_class << 12) |
+                             ((unsigned long long)du.d.gpu_used << 24);
+    if (memoable) {
+        const uint8_t* eff = cx.s_eff + ti * 128 + (smt ? 64 : 0);
+#pragma unroll
+        for (int k = 0; k < NHD_MAX_NUMA; k++) {
+            const int cc = du.d.fc[k] < 63 ? du.d.fc[k] : 63;
+            key |= (unsigned long long)eff[cc] << (40 + 6 * k);
+        }
+    }
+    const uint32_t hsh = (uint32_t)(memo_mix(key ^ ((unsigned long long)du.d.nic_inuse << 17)));
+    uint4* de = &cx.dmemo[3 * (hsh & cx.dmemo_mask)];
+    union { DEntry e; uint4 q[3]; } eu;
+    eu.q[0] = de[0];
+    if (memoable && eu.e.state != 0 && eu.e.a == key && eu.e.nic_inuse == du.d.nic_inuse) {
+        const int state = eu.e.state;
+        if (state >= 2) {
+            eu.q[1] = de[1];
+            eu.q[2] = de[2];
+            pm.pn = eu.e.pn; pm.idx = eu.e.idx; pm.li = eu.e.li; pm.ms = eu.e.ms;
+            pk.gi_lo = eu.e.gi; pk.gi_hi = 0; pk.claimed = eu.e.claimed; pk.gpu_used_new = eu.e.gpu_used_new;
+            pk.ng = eu.e.ng; pk.ncl = eu.e.ncl; pk.fail_status = eu.e.fail_status;
+        }
+        return state;
+    }
+    missed = true;
+    int state;
+    if (fast2) {
+        /* CPU-only pod on a 2-NUMA node: direct evaluation */
+        state = resolve_cpu2(a, cx, ti, t, node, du, pm, pk, missed);
+    } else {
+    /* full evaluation on the node's static description + summary */
+    RecU u;
+#pragma unroll
+    for (int cc = 2; cc < REC_CHUNKS; cc++)
+        u.q[cc] = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, cc));
+    apply_dyn(u.r, du.d);
+    state = 1;
+    if (evaluate_full(a, cx.smemo, cx.smemo_mask, u.r, du.d, t, cx.lane, pm)) {
+        compute_picks(u.r, t, pm, du.d.gpu_used, du.d.n_gpus, pk);
+        state = pk.fail_status ? 3 : 2;
+    }
+    }
+    if (memoable && cx.lane == 0) {
+        eu.e.a = key; eu.e.nic_inuse = du.d.nic_inuse;
+        eu.e.state = (uint8_t)state; eu.e.ms = (uint8_t)pm.ms; eu.e.ncl = (uint8_t)pk.ncl; eu.e.ng = (uint8_t)pk.ng;
+        eu.e.pn = pm.pn; eu.e.idx = pm.idx; eu.e.li = pm.li;
+        eu.e.claimed = pk.claimed; eu.e.gi = (uint32_t)pk.gi_lo;
+        eu.e.gpu_used_new = (uint16_t)pk.gpu_used_new; eu.e.fail_status = (uint8_t)pk.fail_status; eu.e.pad_ = 0;
+        eu.e.pad2_[0] = eu.e.pad2_[1] = 0;
+        de[0] = eu.q[0]; de[1] = eu.q[1]; de[2] = eu.q[2];
+    }
+    __syncwarp();
+    return state;
+}
+
+/*
+ * Apply a decision: everything of SetBusy + SetPhysicalIdsFromMapping + ClaimPodNICResources
+ * (NHDScheduler.py:289-304, Node.py:663-841) except the core ids, on the summary; writes the
+ * binding header (the core ids follow in assign_cores_kernel).  Returns true when placed.
+ */
+__device__ bool apply_decision(const SweepCtx& cx, const PodType& t, int node, NodeDyn& d, const PMap& pm,
+                               const Picks& pk, double now, nhd_binding* bout)
+{
+    const int G = t.G;
+    const bool smt_node = (d.info & NHD_DYN_SMT) != 0;
+    const bool fail = pk.fail_status != 0;
+    d.busy_time = now;                                              /* NHDScheduler.py:289 */
+    d.info |= NHD_DYN_TOUCHED;
+    uint32_t w0s, w2, w14 = 0;
+    if (fail) {                                                      /* Node.py:825-837: cores/GPUs given back, busy stays */
+        w0s = (uint32_t)pk.fail_status;
+        w2 = (uint32_t)G;
+    } else {
+        /* per-socket core accounting: a group's two batches remove cl[g] cores from its socket
+         * (Matcher.py:179-194 counts exactly what Node.py:502-519 will take); the misc batch on
+         * an SMT node takes min(n, what is left) cores when it may not pair hyperthreads */
+        const uint8_t* cl = smt_node ? t.cl_smt : t.cl_nosmt;
+        uint32_t fcw = (uint32_t)d.fc[0] | ((uint32_t)d.fc[1] << 8) | ((uint32_t)d.fc[2] << 16) | ((uint32_t)d.fc[3] << 24);
+        const uint32_t fc_before = fcw;
+        w14 = (uint32_t)d.consumed[0] | ((uint32_t)d.consumed[1] << 8) | ((uint32_t)d.consumed[2] << 16) | ((uint32_t)d.consumed[3] << 24);
+        for (int g = 0; g < G; g++) fcw -= (uint32_t)cl[g] << (8 * ((pm.pn >> (8 * g)) & 0xFF));
+        {
+            const int sh = 8 * (int)pm.ms;
+            const int wd = batch_width(smt_node, (t.pod.flags & NHD_POD_MISC_SMT) != 0, t.pod.n_misc, (fcw >> sh) & 0xFF);
+            fcw -= (uint32_t)wd << sh;
+        }
+        const uint32_t cons = w14 + (fc_before - fcw);               /* per byte, no borrows: each width <= what is free */
+#pragma unroll
+        for (int k = 0; k < NHD_MAX_NUMA; k++) { d.fc[k] = (uint8_t)(fcw >> (8 * k)); d.consumed[k] = (uint8_t)(cons >> (8 * k)); }
+        d.gpu_used = (uint16_t)pk.gpu_used_new;
+        if (t.pod.hugepages_gb > 0) d.free_hugepages_gb -= t.pod.hugepages_gb;      /* Node.py:794-796 */
+        for (int e = 0; e < pk.ncl; e++) d.nic_inuse |= 1u << ((pk.claimed >> (8 * e)) & 0xFF);   /* Node.py:644-646 */
+        w0s = NHD_PLACED;
+        w2 = (uint32_t)G | ((uint32_t)pk.ng << 16) | ((uint32_t)pk.ncl << 24);
+    }
+    /* bytes: 12 gpu_numa[4] 16 cpu_numa[5] 21 nic_numa[4] 25 nic_idx[4] 29 nic_list_index[4] 33 claimed[4] 40 gpu_index[16] 56 cores */
+    const uint32_t claimed = fail ? 0u : pk.claimed;
+    const uint32_t w4 = G < 4 ? (pm.pn | (pm.ms << (8 * G))) : pm.pn;
+    const uint32_t w5 = (G == 4 ? pm.ms : 0u) | (pm.pn << 8);
+    const uint32_t w6 = (pm.pn >> 24) | (pm.idx << 8);
+    const uint32_t w7 = (pm.idx >> 24) | (pm.li << 8);
+    const uint32_t w8 = (pm.li >> 24) | (claimed << 8);
+    const uint32_t w9 = claimed >> 24;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (cx.lane == 0) v = make_uint4(w0s, (uint32_t)node, w2, pm.pn);
+    else if (cx.lane == 1) v = make_uint4(w4, w5, w6, w7);
+    else if (cx.lane == 2) v = make_uint4(w8, w9, (uint32_t)pk.gi_lo, (uint32_t)(pk.gi_lo >> 32));
+    else if (cx.lane == 3) v = make_uint4((uint32_t)pk.gi_hi, (uint32_t)(pk.gi_hi >> 32), w14, 0);
+    if (cx.lane < 8) reinterpret_cast<uint4*>(bout)[cx.lane] = v;
+    return !fail;
+}
+
+/*
+ * Decision sweep.  One CTA; warp 0 walks the pods in order (all lanes execute the scalar parts
+ * redundantly, so there is no intra-warp hand-off), the other warps only help to stage tables
+ * into shared memory.  Per pod:
+ *   first fit   cursor word of the type's feasibility bitmap (minus busy nodes; GPU-less nodes
+ *               first for CPU-only pods, Matcher.py:412-416), 32-wide ballot search when empty;
+ *   untouched?  the snapshot bit of a node no pod of this batch was bound to is exact, so a GPU
+ *               pod just takes the node (busy stamp, BUSY bit) and its mapping is worked out
+ *               later, in parallel, by resolve_kernel — or right here if the node is revisited;
+ *   validate    otherwise the node's 32-byte summary: exact cheap rejects, the decision memo,
+ *               (miss) the full tuple evaluation + GPU picks + NIC claim order;
+ *   assign      hugepages, busy stamp, per-socket core accounting, binding header, summary
+ *               write-back (Node.py:663-841 minus the core ids);
+ *   invalidate  every pod type that can no longer fit on the node loses its bit right away.
+ */
+template <bool SMEM_BITMAPS>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
 sweep_kernel(const SweepArgs a)
 {
-    const int lane = threadIdx.x;
-    const int W = a.words;
-    uint64_t* const NOGPU = a.bitmaps + (size_t)a.n_types * W;
-    uint64_t* const BUSY = a.bitmaps + (size_t)(a.n_types + 1) * W;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = a.words, T = a.n_types;
+    if (blockIdx.x != 0) {
+        /* companion CTAs: the sweep itself is one CTA; a grid that covers the chip avoids the
+         * low-occupancy issue throttle (B300_MICROARCH.md, I-cache).  They only sleep until block 0 is done. */
+        if (tid == 0) { while (atomicAdd(a.sweep_done, 0) == 0) __nanosleep(2000); }
+        return;
+    }
 
-    /* cursors start at word 0 */
-    for (int i = lane; i < a.n_types * 2; i += 32) a.cursors[i] = 0;
+    const int wid = tid >> 5;
+    const int dual = a.dual;
+    const int half = (dual && wid == 1) ? 1 : 0;          /* the second sweeping warp owns the upper halves */
+    SweepCtx cx;
+    cx.lane = lane;
+    cx.smemo_mask = (dual ? SMEMO_SLOTS / 2 : SMEMO_SLOTS) - 1;
+    cx.dmemo_mask = (dual ? DMEMO_SLOTS / 2 : DMEMO_SLOTS) - 1;
+    cx.dcache_mask = (dual ? DCACHE_SLOTS / 2 : DCACHE_SLOTS) - 1;
+    cx.smemo = reinterpret_cast<uint4*>(smem) + half * (SMEMO_SLOTS / 2);                                  /* SMEMO_SLOTS x 16 B */
+    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + half * (DMEMO_SLOTS / 2) * 3;           /* DMEMO_SLOTS x 48 B */
+    cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + half * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
+    int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
+    cx.dtag = dtag_all + half * (DCACHE_SLOTS / 2);
+    cx.peer_dtag = dual ? dtag_all + (1 - half) * (DCACHE_SLOTS / 2) : nullptr;
+    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods finished, [1] GPU pods finished */
+    cx.clsnic = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);              /* CLSNIC_SLOTS x 32 B */
+    uint8_t* p0 = reinterpret_cast<uint8_t*>(cx.clsnic + CLSNIC_SLOTS);
+    PodType* s_types = reinterpret_cast<PodType*>(p0);
+    cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
+    uint8_t* p1 = p0 + (cx.types_in_smem ? ((T * sizeof(PodType) + 15) & ~(size_t)15) : 0);
+    uint8_t* s_eff = p1;                                                        /* [T][2][64] effective-fc tables */
+    cx.s_eff = s_eff;
+    uint16_t* s_needb = reinterpret_cast<uint16_t*>(p1 + (cx.types_in_smem ? (size_t)T * 128 : 0));   /* [T][2][32] */
+    cx.s_needb = cx.types_in_smem ? s_needb : nullptr;
+    uint8_t* p2 = reinterpret_cast<uint8_t*>(s_needb) + (cx.types_in_smem ? (size_t)T * 128 : 0);
+    int32_t* s_cursors = reinterpret_cast<int32_t*>(p2);                        /* [T][3] */
+    uint64_t* s_touched = reinterpret_cast<uint64_t*>(p2 + (((size_t)T * 3 * 4 + 15) & ~(size_t)15));   /* [W] */
+    uint64_t* s_bitmaps = s_touched + W;
+
+    for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < CLSNIC_SLOTS * 2; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
+    if (tid < 4) done[tid] = 0;
+    for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
+    if (cx.types_in_smem) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.types);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_types);
+        for (int i = tid; i < T * (int)(sizeof(PodType) / 4); i += SWEEP_THREADS) dst[i] = src[i];
+        /* effective free-core count: the largest sum of a sub-set of the type's per-group demands that
+         * does not exceed c — all the tuple predicates can ever learn about a socket with c free cores */
+        for (int i = tid; i < T * 128; i += SWEEP_THREADS) {
+            const int tt = i >> 7, f = (i >> 6) & 1, c = i & 63;
+            const PodType& ty = a.types[tt];
+            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+            const int n = ty.G + 1;
+            int best = 0;
+            for (int sub = 0; sub < (1 << n); sub++) {
+                int sum = 0;
+                for (int b = 0; b < n; b++) if ((sub >> b) & 1) sum += cl[b];
+                if (sum <= c && sum > best) best = sum;
+            }
+            s_eff[i] = (uint8_t)best;
+        }
+        /* per-tuple socket demand on 2-NUMA nodes (Matcher.py:203-212 with K = 2) */
+        for (int i = tid; i < T * 64; i += SWEEP_THREADS) {
+            const int tt = i >> 6, f = (i >> 5) & 1, q = i & 31;
+            const PodType& ty = a.types[tt];
+            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+            const int L = ty.G + 1;
+            int n0 = 0, n1 = 0;
+            if (q < (1 << L)) {
+                for (int g = 0; g < L; g++) { if ((q >> (L - 1 - g)) & 1) n1 += cl[g]; else n0 += cl[g]; }
+            } else { n0 = n1 = 255; }
+            s_needb[i] = (uint16_t)((n0 > 255 ? 255 : n0) | ((n1 > 255 ? 255 : n1) << 8));
+        }
+    }
+    if (SMEM_BITMAPS) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.bitmaps);
+        uint4* dst = reinterpret_cast<uint4*>(s_bitmaps);
+        const int n16 = (T + 2) * W / 2;
+        for (int i = tid; i < n16; i += SWEEP_THREADS) dst[i] = src[i];
+    }
+    /* cursors[t*3 + 0/1]: first word that may hold a candidate (pass 0 / 1); [t*3 + 2]: first
+     * word that may hold a NON-BUSY candidate (valid while the clock stands still) */
+    int32_t* cursors = SMEM_BITMAPS ? s_cursors : a.cursors;
+    for (int i = tid; i < T * 3; i += SWEEP_THREADS) cursors[i] = 0;
+    __syncthreads();
+    if (wid >= (dual ? 2 : 1)) return;
+    const int my_class = dual ? wid : -1;                 /* 0: CPU-only pods, 1: GPU pods, -1: everything */
+
+    uint64_t* const BM = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
+    uint64_t* const NOGPU = BM + (size_t)T * W;
+    uint64_t* const BUSY = BM + (size_t)(T + 1) * W;
+    const PodType* types = cx.types_in_smem ? s_types : a.types;
+    cx.types = types;
+    const bool eager = T <= 64;
+    /* the most demanding type decides whether a placement can have made the node unfit for anybody */
+    int all_need = 0, all_big = 0, all_hp = 0, all_gpus = 0;
+    for (int tt = 0; tt < T && eager; tt++) {
+        const PodType& ty = types[tt];
+        const int nd = ty.need_smt > ty.need_nosmt ? ty.need_smt : ty.need_nosmt;
+        const int bg = ty.max_smt > ty.max_nosmt ? ty.max_smt : ty.max_nosmt;
+        all_need = nd > all_need ? nd : all_need;
+        all_big = bg > all_big ? bg : all_big;
+        all_hp = ty.pod.hugepages_gb > all_hp ? ty.pod.hugepages_gb : all_hp;
+        all_gpus = ty.total_gpus > all_gpus ? ty.total_gpus : all_gpus;
+    }
 
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
     int n_busy = 0;
-    for (int w0 = 0; w0 < W; w0 += 32) {
+    for (int w0 = 0; w0 < W && !dual; w0 += 32) {      /* (two-warp mode runs on a constant clock: no list needed) */
         uint64_t word = (w0 + lane < W) ? BUSY[w0 + lane] : 0;
         int cnt = popc64(word);
         int pre = cnt;                                   /* inclusive scan over lanes */
@@ -308,23 +1040,41 @@ sweep_kernel(const SweepArgs a)
     }
     __syncwarp();
     double cur_now = a.n_pods > 0 ? a.now[0] : 0.0;
+    int n_cls[2] = {0, 0};
+    PROF_DECL
 
-    for (int i = 0; i < a.n_pods; i++) {
-        const int ti = a.pod_type[i];
-        const PodType& t = a.types[ti];
-        const double now = a.now[i];
+    for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
+      /* the next 32 pods' types and clocks in one coalesced read */
+      const int my_ti = (i0 + lane < a.n_pods) ? a.pod_type[i0 + lane] : 0;
+      const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
+      const int jn = (a.n_pods - i0) < 32 ? (a.n_pods - i0) : 32;
+      for (int j = 0; j < jn; j++) {
+        const int i = i0 + j;
+        const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
+        const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
+        const PodType& t = types[ti];
         nhd_binding* bout = &a.out[i];
+        const int cls = t.needs_gpu ? 1 : 0;
+        const int before_cpu = n_cls[0], before_gpu = n_cls[1];      /* pods of each class ahead of this one */
+        n_cls[cls]++;
+        if (dual) {
+            if (cls != my_class) continue;
+            /* a GPU pod must see every earlier CPU-only pod resolved: one of them may have spilled onto a GPU node */
+            if (my_class == 1) { while (done[0] < before_cpu) __nanosleep(40); __threadfence_block(); }
+        }
+        PROF_MARK(0);      /* pod header */
+        do {
 
         /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
-        if (now != cur_now) {
+        if (now != cur_now && !dual) {
             if (now < cur_now) {
-                /* clock went backwards: rebuild from the records */
+                /* clock went backwards: rebuild from the summaries */
                 n_busy = 0;
                 for (int n0 = 0; n0 < W * 64; n0 += 32) {
                     int n = n0 + lane;
                     bool b = false;
                     if (n < a.n_nodes) {
-                        double bt = *reinterpret_cast<const double*>(a.nodes + chunk_off(n, 3));
+                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
                         b = (now - bt) < a.min_busy;
                     }
                     uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
@@ -340,100 +1090,273 @@ sweep_kernel(const SweepArgs a)
                     bool b = false;
                     if (e < n_busy) {
                         n = a.busy_list[e];
-                        double bt = *reinterpret_cast<const double*>(a.nodes + chunk_off(n, 3));
+                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
                         b = (now - bt) < a.min_busy;
                         if (!b) atomicAnd(reinterpret_cast<unsigned long long*>(&BUSY[n >> 6]), ~(1ULL << (n & 63)));
                     }
                     uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
                     __syncwarp();
-                    if (b) a.busy_list[kept + popc32(bal & ((1u << lane) - 1))] = n;   /* kept <= e0: no overlap hazard */
+                    if (b) a.busy_list[kept + popc32(bal & ((1u << lane) - 1))] = n;   /* kept <= e0 */
                     __syncwarp();
                     kept += popc32(bal);
                 }
                 n_busy = kept;
             }
+            for (int tt = lane; tt < T; tt += 32) cursors[tt * 3 + 2] = 0;   /* busy bits may have cleared */
             __syncwarp();
             cur_now = now;
         }
 
-        /* ---- header of the binding ---- */
-        if (lane == 0) {
-            uint4 z = make_uint4(0, 0, 0, 0);
-            for (int c = 0; c < 8; c++) reinterpret_cast<uint4*>(bout)[c] = z;
-            bout->node = -1;
-            bout->n_groups = t.G;
-            bout->status = t.valid_map ? NHD_NO_CANDIDATE : NHD_BAD_MAP_TYPE;
+        if (!t.valid_map) {
+            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_BAD_MAP_TYPE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
+            break;
         }
-        if (!t.valid_map) continue;
 
-        /* ---- first fit: pass 0 = GPU-less nodes for CPU-only pods (Matcher.py:412-416), pass 1 = any ---- */
+        /* ---- first fit ---- */
         int chosen = -1;
-        RecU u;
-        Mapping m;
+        bool deferred = false;
+        DynU du;
+        PMap pm = {0, 0, 0, 0};
+        Picks pk;
+        pk.fail_status = 0;
+        const bool skip_busy = t.needs_gpu != 0;                         /* Matcher.py:107-111 */
+        uint64_t* F = BM + (size_t)ti * W;
         for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
-            uint64_t* F = a.bitmaps + (size_t)ti * W;
-            int w0 = a.cursors[ti * 2 + pass];
-            bool cursor_fixed = false;
-            for (; w0 < W && chosen < 0; w0 += 32) {
-                const int w = w0 + lane;
-                uint64_t raw = 0;
-                if (w < W) {
-                    raw = F[w];
-                    if (pass == 0) raw &= NOGPU[w];
-                }
-                if (!cursor_fixed) {
-                    uint32_t nz = __ballot_sync(0xFFFFFFFFu, raw != 0);
-                    if (nz) { cursor_fixed = true; if (lane == 0) a.cursors[ti * 2 + pass] = w0 + ctz32(nz); }
-                    else if (lane == 0) a.cursors[ti * 2 + pass] = (w0 + 32 < W) ? w0 + 32 : W;
-                }
-                uint64_t word = raw;
-                if (t.needs_gpu && w < W) word &= ~BUSY[w];              /* Matcher.py:107-111 */
-                for (;;) {
-                    uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
-                    if (!nz) break;
-                    const int src = ctz32(nz);
-                    const uint64_t cw = __shfl_sync(0xFFFFFFFFu, word, src);
-                    const int node = (w0 + src) * 64 + ctz64(cw);
-                    int ok = 0;
-                    if (lane == 0) {
-                        load_rec(a.nodes, node, u);
-                        ok = node_gates(u.r, t) && evaluate_mapping_memo(a.memo, u.r, t, a.cap, &m);
-                    }
-                    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
-                    if (ok) { chosen = node; break; }
-                    /* resources only shrink inside a batch: the node stays infeasible for this type */
-                    if (lane == src) {
-                        word &= ~(1ULL << (node & 63));
-                        F[w] &= ~(1ULL << (node & 63));
-                    }
-                }
+            if (dual && my_class == 0 && pass == 1) {
+                /* spill onto GPU nodes: every earlier GPU pod must be in, and later ones wait for us (done[0]) */
+                while (done[1] < before_gpu) __nanosleep(40);
+                __threadfence_block();
             }
-        }
-        if (chosen < 0) continue;
+            /* (1) the cursor: first word with any candidate of this pass */
+            int c = cursors[ti * 3 + pass];
+            const int c_in = c;
+            while (c < W) {
+                const uint64_t raw = F[c] & (pass == 0 ? NOGPU[c] : ~0ULL);
+                if (raw) break;
+                int found = W;
+                for (int base = c + 1; base < W; base += 32) {
+                    const int w = base + lane;
+                    const uint64_t r = (w < W) ? (F[w] & (pass == 0 ? NOGPU[w] : ~0ULL)) : 0;
+                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                    if (nz) { found = base + ctz32(nz); break; }
+                }
+                c = found;
+            }
+            if (c != c_in) cursors[ti * 3 + pass] = c;
+            if (c >= W) continue;
+            /* (2) candidates from there on, skipping busy nodes for GPU pods */
+            int cb = c;
+            if (skip_busy) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
+            while (cb < W) {
+                uint64_t word = F[cb] & (pass == 0 ? NOGPU[cb] : ~0ULL);
+                if (skip_busy) word &= ~BUSY[cb];
+                if (!word) {
+                    int found = W;
+                    for (int base = cb + 1; base < W; base += 32) {
+                        const int w = base + lane;
+                        uint64_t r = (w < W) ? (F[w] & (pass == 0 ? NOGPU[w] : ~0ULL)) : 0;
+                        if (skip_busy && w < W) r &= ~BUSY[w];
+                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                        if (nz) { found = base + ctz32(nz); break; }
+                    }
+                    cb = found;
+                    if (skip_busy) cursors[ti * 3 + 2] = cb;
+                    continue;
+                }
+                const int node = cb * 64 + ctz64(word);
+                const uint64_t nbit = 1ULL << (node & 63);
+                PROF_MARK(1);      /* bitmap scan */
 
-        /* ---- assignment + state update (lane 0) ---- */
-        if (lane == 0) {
-            nhd_binding b;
-            {
-                uint4 z = make_uint4(0, 0, 0, 0);
-                for (int c = 0; c < 8; c++) reinterpret_cast<uint4*>(&b)[c] = z;
-            }
-            b.node = chosen;
-            assign_pod(u.r, t, m, now, &b);
-            store_rec_mutable(a.nodes, chosen, u);
-            for (int c = 0; c < 8; c++) reinterpret_cast<uint4*>(bout)[c] = reinterpret_cast<uint4*>(&b)[c];
-            if (a.min_busy > 0.0) {                       /* now - busy_time == 0 < MIN_BUSY_SECS */
-                uint64_t bit = 1ULL << (chosen & 63);
-                if (!(BUSY[chosen >> 6] & bit)) {
-                    BUSY[chosen >> 6] |= bit;
-                    a.busy_list[n_busy] = chosen;
-                    n_busy++;
+                if (skip_busy && !(s_touched[cb] & nbit)) {
+                    /* no pod of this batch was bound here: the snapshot bit is exact (and the node is not
+                     * busy), so the pod is placed; what it takes is resolved later */
+                    chosen = node;
+                    deferred = true;
+                    break;
                 }
+                load_dyn(a, cx, node, du);
+                if (du.d.info & NHD_DYN_PENDING) {
+                    /* the pod that took this node first is still unresolved: do it now, in order */
+                    const int pj = a.pend_pod[node];
+                    const int tj = a.pod_type[pj];
+                    PMap pmj = {0, 0, 0, 0};
+                    Picks pkj;
+                    pkj.fail_status = 0;
+                    du.d.info &= ~NHD_DYN_PENDING;
+                    bool mj;
+                    resolve_decision(a, cx, tj, types[tj], node, du, pmj, pkj, mj);
+                    apply_decision(cx, types[tj], node, du.d, pmj, pkj, du.d.busy_time, &a.out[pj]);
+                    store_dyn(a, cx, node, du);
+                    __syncwarp();
+                    PROF_COUNT(12);
+                }
+                /* active / maintenance / node group are static inside a batch and already part of F */
+                bool missed;
+                const int state = resolve_decision(a, cx, ti, t, node, du, pm, pk, missed);
+                if (missed) { PROF_MARK(3); } else { PROF_MARK(2); }      /* summary + decision: memo miss / hit */
+                if (state >= 2) { chosen = node; break; }
+                PROF_COUNT(8);     /* stale candidate */
+                /* resources only shrink inside a batch: the node stays infeasible for this type */
+                if (lane == 0) bit_clear(F, node);
+                __syncwarp();
             }
         }
-        n_busy = __shfl_sync(0xFFFFFFFFu, n_busy, 0);
+        if (chosen < 0) {
+            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_NO_CANDIDATE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
+            break;
+        }
+        PROF_MARK(4);      /* loop exit */
+
+        bool placed = false;
+        if (deferred) {
+            /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
+            if (lane == 0) {
+                NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + chosen;
+                gd->busy_time = now;
+                atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
+                a.pend_pod[chosen] = i;
+                reinterpret_cast<uint2*>(bout)[0] = make_uint2(NHD_PENDING, (uint32_t)chosen);
+                bit_set(s_touched, chosen);
+            }
+        } else {
+            placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
+            store_dyn(a, cx, chosen, du);
+            if (lane == 0) bit_set(s_touched, chosen);
+        }
+        PROF_MARK(5);      /* assignment */
+        if (a.min_busy > 0.0) {                                          /* now - busy_time == 0 < MIN_BUSY_SECS */
+            const uint64_t bit = 1ULL << (chosen & 63);
+            if (!(BUSY[chosen >> 6] & bit)) {
+                __syncwarp();
+                if (lane == 0) {
+                    bit_set(BUSY, chosen);
+                    if (!dual) a.busy_list[n_busy] = chosen;
+                }
+                n_busy++;
+            }
+        }
+        /* eager invalidation: pod types that can no longer fit here lose their bit now, so later
+         * pods of those types never stop at this node (exact: summary_infeasible is a necessary condition) */
+        bool roomy = false;
+        if (eager && placed) {
+            const NodeDyn& nd = du.d;
+            const int sum = nd.fc[0] + nd.fc[1] + nd.fc[2] + nd.fc[3];
+            int mx = nd.fc[0] > nd.fc[1] ? nd.fc[0] : nd.fc[1];
+            const int mx2 = nd.fc[2] > nd.fc[3] ? nd.fc[2] : nd.fc[3];
+            mx = mx > mx2 ? mx : mx2;
+            const uint32_t alln = nd.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << nd.n_nics) - 1);
+            roomy = sum >= all_need && mx >= all_big && nd.free_hugepages_gb >= all_hp && (nd.nic_inuse & alln) != alln &&
+                    (nd.n_gpus == 0 || popc32(~(uint32_t)nd.gpu_used & ((1u << nd.n_gpus) - 1)) >= all_gpus);
+        }
+        if (eager && placed && !roomy) {
+            for (int tb = 0; tb < T; tb += 32) {
+                const int tt = tb + lane;
+                if (tt < T && summary_infeasible(types[tt], du.d))
+                    bit_clear(BM + (size_t)tt * W, chosen);
+            }
+        }
+        } while (0);
         __syncwarp();
+        if (dual) {                                        /* publish: this class is done up to and including pod i */
+            __threadfence_block();
+            if (lane == 0) done[my_class] = n_cls[my_class];
+        }
+        PROF_MARK(6);      /* write-back */
+      }
     }
+    if (wid == 0) { PROF_FLUSH(a.prof); }
+    if (lane == 0) atomicAdd(a.sweep_done, 1);       /* releases the companion CTAs (both sweeping warps add; any non-zero value does) */
+}
+
+/*
+ * Pods the sweep bound to a node without working out the mapping (first pod on an untouched
+ * node): one thread per pod, all independent — the node's summary is still the snapshot's,
+ * apart from the busy stamp.  Same arithmetic as the sweep's miss path, scalar.
+ */
+__global__ void resolve_kernel(const SweepArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pods) return;
+    if (a.out[i].status != NHD_PENDING) return;
+    const int node = a.out[i].node;
+    const PodType& t = a.types[a.pod_type[i]];
+    RecU u;
+#pragma unroll
+    for (int c = 2; c < REC_CHUNKS; c++)
+        u.q[c] = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, c));
+    DynU du;
+    du.q[0] = a.dyn[(size_t)node * 2];
+    du.q[1] = a.dyn[(size_t)node * 2 + 1];
+    du.d.info &= ~NHD_DYN_PENDING;
+    apply_dyn(u.r, du.d);
+    union { nhd_binding b; uint4 q[8]; } bu;
+    for (int c = 0; c < 8; c++) bu.q[c] = make_uint4(0, 0, 0, 0);
+    bu.b.node = node;
+    const uint64_t gsw = t.pci ? free_gpus_per_switch(u.r) : 0;
+    TMask ma, mb, mc;
+    int ps = 0, ms = 0;
+    Mapping m;
+    if (stage_masks_fc(u.r, du.d.fc, t, a.cap, gsw, ma, mb, mc) && choose_mapping(u.r.n_numa, t.G, ma, mb, mc, &ps, &ms)) {
+        tuple_digits(ps, u.r.n_numa, t.G, m.gpu_numa);
+        m.misc_numa = (uint8_t)ms;
+        nic_first_fit(u.r, t, m.gpu_numa, u.r.n_numa, a.cap, gsw, m.nic_idx, m.nic_li);
+        assign_resources(u.r, du.d, t, m, du.d.busy_time, &bu.b);
+    } else {
+        bu.b.status = NHD_NO_CANDIDATE;        /* cannot happen: the snapshot bit said feasible */
+        bu.b.node = -1;
+    }
+    a.dyn[(size_t)node * 2] = du.q[0];
+    a.dyn[(size_t)node * 2 + 1] = du.q[1];
+    for (int c = 0; c < 8; c++) reinterpret_cast<uint4*>(&a.out[i])[c] = bu.q[c];
+}
+
+/* ------------------------------------------------------------------ core ids + commit */
+
+struct FinishArgs {
+    uint8_t* nodes;
+    const PodType* types;
+    const int32_t* pod_type;
+    nhd_binding* out;
+    const uint4* dyn;
+    int n_pods;
+};
+
+/* stage A: the logical core ids of every placed pod, all pods in parallel, from the records as
+ * they were at the start of the batch (the sweep never writes them) and the prefix offsets. */
+__global__ void assign_cores_kernel(const FinishArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pods) return;
+    union { nhd_binding b; uint4 q[8]; } bu;
+    for (int c = 0; c < 8; c++) bu.q[c] = reinterpret_cast<const uint4*>(&a.out[i])[c];
+    if (bu.b.status != NHD_PLACED) return;
+    RecU u;
+    load_rec(a.nodes, bu.b.node, u);
+    assign_cores_from_snapshot(u.r, a.types[a.pod_type[i]], &bu.b);
+    for (int c = 0; c < 8; c++) reinterpret_cast<uint4*>(&a.out[i])[c] = bu.q[c];
+}
+
+/* commit: fold the batch into the records (core masks by atomic OR, the rest from the summaries) */
+__global__ void commit_kernel(const FinishArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pods) return;
+    const nhd_binding* b = &a.out[i];
+    const int node = b->node;
+    if (node < 0) return;
+    if (b->status == NHD_PLACED) {
+        unsigned long long m[4] = {0, 0, 0, 0};
+        for (int k = 0; k < b->n_cores; k++) m[b->cores[k] >> 6] |= 1ULL << (b->cores[k] & 63);
+        for (int w = 0; w < 4; w++)
+            if (m[w]) atomicOr(reinterpret_cast<unsigned long long*>(a.nodes + chunk_off(node, w >> 1) + (w & 1) * 8), m[w]);
+    }
+    /* every pod bound to this node writes the node's final summary: identical values */
+    const NodeDyn d = reinterpret_cast<const NodeDyn*>(a.dyn)[node];
+    uint8_t* c2 = a.nodes + chunk_off(node, 2);
+    *reinterpret_cast<uint16_t*>(c2 + 0) = d.gpu_used;
+    *reinterpret_cast<uint32_t*>(c2 + 4) = d.nic_inuse;
+    *reinterpret_cast<int32_t*>(c2 + 8) = d.free_hugepages_gb;
+    *reinterpret_cast<double*>(a.nodes + chunk_off(node, 3)) = d.busy_time;
 }
 
 } // namespace nhd

@@ -28,7 +28,7 @@ def nccl_unique_id() -> bytes:
 
 class Solver:
     def __init__(self, speed_table, nic_bw_avail_percent=0.9, min_busy_secs=30.0, device=0,
-                 rank=0, world_size=1, nccl_id: bytes = None):
+                 rank=0, world_size=1, nccl_id: bytes = None, single_warp: bool = False):
         self._L = _lib.load()
         p = _lib.Params()
         self._L.nhd_default_params(ctypes.byref(p))
@@ -40,6 +40,7 @@ class Solver:
         for i, s in enumerate(speeds[:16]):
             p.speed_gbps[i] = s
         p.device, p.rank, p.world_size = device, rank, world_size
+        p.reserved_ = 1 if single_warp else 0      # debug: force the one-warp sweep even on a constant clock
         if world_size > 1:
             if not nccl_id or len(nccl_id) != 128:
                 raise ValueError('world_size > 1 needs the 128-byte NCCL unique id of rank 0')
@@ -127,6 +128,11 @@ class Solver:
         t = _lib.Timing()
         self._ck(self._L.nhd_last_timing(self._h, ctypes.byref(t)))
         return {k: getattr(t, k) for k, _ in t._fields_}
+
+    def debug_counters(self):
+        out = np.zeros(64, dtype='<u8')
+        self._ck(self._L.nhd_debug_counters(self._h, out.ctypes.data))
+        return out
 
     def filter_bitmaps(self):
         """Runs only the snapshot predicate kernel on the staged batch; returns

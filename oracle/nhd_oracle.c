@@ -753,6 +753,8 @@ index_error:                                               /* :825-837 */
      * the reference would NOT restore hugepages.  That raise is unreachable after a
      * successful filter, so no rollback is modelled either. */
     b->n_cores = 0; b->n_gpus = 0; b->n_claimed = 0;
+    memset(b->cores, 0, sizeof(b->cores));                 /* nothing stays assigned after the unwind */
+    memset(b->gpu_index, 0, sizeof(b->gpu_index));
     /* :831-835 indexes self.nics by a *speed*: IndexError or TypeError when any NIC speed
      * was recorded before the failure. */
     return n_used_nics ? NHD_REF_WOULD_CRASH : NHD_ASSIGN_FAILED;
@@ -824,6 +826,14 @@ static void attempt_scheduling(o_node* nodes, int n_nodes, const o_pod* top, dou
         b->nic_idx[g] = m.nic.idx[g];
     }
     for (int g = 0; g < m.cpu.len; g++) b->cpu_numa[g] = m.cpu.v[g];
+    /* nic_list_index is a pure function of the mapping (GetNicObjFromIndex, Node.py:657-661):
+     * report it for every group, also when the assignment later fails part-way */
+    for (int g = 0; g < top->n_groups; g++)
+        for (int ni = 0; ni < nodes[node].n_nics; ni++)
+            if (m.nic.idx[g] == nodes[node].nics[ni].idx && nodes[node].nics[ni].numa_node == m.nic.numa[g]) {
+                b->nic_list_index[g] = (uint8_t)ni;
+                break;
+            }
 
     nodes[node].busy_time = now;                           /* NHDScheduler.py:289, Node.py:843-845 */
     b->status = set_physical_ids_from_mapping(&nodes[node], &m, top, b);

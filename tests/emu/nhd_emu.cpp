@@ -65,4 +65,69 @@ uint64_t nhd_emu_tuple_hash(int idx, int K, int L) { return py_tuple_hash(idx, K
 
 int nhd_emu_claim_order(const uint8_t* li, int n, uint8_t* out) { return claimed_nic_order(li, n, out); }
 
+/* Two-stage flow exactly as the CUDA kernels run it: decisions on NodeDyn summaries, then the
+ * core ids of every placed pod from the snapshot records and prefix offsets, then commit. */
+int nhd_emu_solve2(double bw, double min_busy, const double* speed, int n_nodes, nhd_node_rec* recs,
+                   int n_pods, const nhd_pod* pods, const double* now, nhd_binding* out)
+{
+    double cap[NHD_MAX_SPEED_CLASSES];
+    for (int i = 0; i < NHD_MAX_SPEED_CLASSES; i++) cap[i] = speed[i] * bw;
+    std::vector<NodeDyn> dyn(n_nodes);
+    std::vector<nhd_node_rec> snap(recs, recs + n_nodes);
+    for (int n = 0; n < n_nodes; n++) make_dyn(recs[n], dyn[n]);
+    std::vector<PodType> types(n_pods);
+    for (int i = 0; i < n_pods; i++) {
+        PodType& t = types[i];
+        make_pod_type(pods[i], t);
+        nhd_binding* b = &out[i];
+        std::memset(b, 0, sizeof(*b));
+        b->node = -1;
+        b->n_groups = t.G;
+        if (!t.valid_map) { b->status = NHD_BAD_MAP_TYPE; continue; }
+        b->status = NHD_NO_CANDIDATE;
+        int first = -1, first_nogpu = -1;
+        Mapping mf, mn;
+        for (int n = 0; n < n_nodes; n++) {
+            nhd_node_rec r = snap[n];
+            apply_dyn(r, dyn[n]);
+            if (!node_gates(r, t)) continue;
+            if (t.needs_gpu && node_busy(r, now[i], min_busy)) continue;
+            const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+            TMask ma, mb, mc;
+            const bool quick_no = summary_infeasible(t, dyn[n]);    /* must only ever fire on infeasible nodes */
+            if (!stage_masks_fc(r, dyn[n].fc, t, cap, gsw, ma, mb, mc)) continue;
+            int ps, ms;
+            if (!choose_mapping(r.n_numa, t.G, ma, mb, mc, &ps, &ms)) continue;
+            if (quick_no) return -7000 - i;
+            Mapping m;
+            tuple_digits(ps, r.n_numa, t.G, m.gpu_numa);
+            m.misc_numa = (uint8_t)ms;
+            nic_first_fit(r, t, m.gpu_numa, r.n_numa, cap, gsw, m.nic_idx, m.nic_li);
+            if (first < 0) { first = n; mf = m; }
+            if (first_nogpu < 0 && r.n_gpus == 0) { first_nogpu = n; mn = m; }
+            if (t.needs_gpu || first_nogpu >= 0) break;
+        }
+        if (first < 0) continue;
+        const bool use_nogpu = !t.needs_gpu && first_nogpu >= 0;
+        const int node = use_nogpu ? first_nogpu : first;
+        nhd_node_rec r = snap[node];
+        apply_dyn(r, dyn[node]);
+        b->node = node;
+        assign_resources(r, dyn[node], t, use_nogpu ? mn : mf, now[i], b);
+    }
+    /* stage A: core ids, independent per pod */
+    std::vector<M256> taken(n_pods);
+    for (int i = 0; i < n_pods; i++)
+        if (out[i].status == NHD_PLACED) taken[i] = assign_cores_from_snapshot(snap[out[i].node], types[i], &out[i]);
+    /* commit */
+    for (int i = 0; i < n_pods; i++) {
+        if (out[i].node < 0) continue;
+        nhd_node_rec& r = recs[out[i].node];
+        if (out[i].status == NHD_PLACED)
+            for (int w = 0; w < 4; w++) r.used[w] |= taken[i].w[w];
+        apply_dyn(r, dyn[out[i].node]);
+    }
+    return 0;
+}
+
 }

@@ -6,15 +6,16 @@ import numpy as np
 from nhd_b200 import wire
 
 
-def emu_solve(emu, recs, speed_table, pods, now, bw=0.9, min_busy=30.0):
+def emu_solve(emu, recs, speed_table, pods, now, bw=0.9, min_busy=30.0, two_stage=False):
     recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE).copy()
     pods = np.ascontiguousarray(pods, dtype=wire.POD_DTYPE)
     now = np.ascontiguousarray(now, dtype='<f8')
     speed = np.ascontiguousarray(speed_table, dtype='<f8')
     out = np.zeros(len(pods), dtype=wire.BINDING_DTYPE)
-    emu.nhd_emu_solve.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    rc = emu.nhd_emu_solve(bw, min_busy, speed.ctypes.data, len(recs), recs.ctypes.data, len(pods),
+    fn = emu.nhd_emu_solve2 if two_stage else emu.nhd_emu_solve
+    fn.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rc = fn(bw, min_busy, speed.ctypes.data, len(recs), recs.ctypes.data, len(pods),
                            pods.ctypes.data, now.ctypes.data, out.ctypes.data)
     assert rc == 0, f'emu error {rc}'
     return out, recs

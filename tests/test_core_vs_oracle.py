@@ -6,15 +6,16 @@ import pytest
 from tests import helpers, ref_compare, scenarios
 
 
+@pytest.mark.parametrize('two_stage', [False, True], ids=['direct', 'two_stage'])
 @pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
-def test_core_matches_oracle_random(oracle_lib, emu, flavor):
+def test_core_matches_oracle_random(oracle_lib, emu, flavor, two_stage):
     placed = 0
     for seed in range(40):
         scn = scenarios.random_scenario(1000 + seed * 13 + len(flavor), n_nodes=8, n_pods=40, flavor=flavor,
                                         max_groups=4 if flavor != 'wild' else 3)
         recs, pods, now, layout = ref_compare.pack_scenario(scn)
         ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now)
-        eb, erecs = helpers.emu_solve(emu, recs, layout.speed_table(), pods, now)
+        eb, erecs = helpers.emu_solve(emu, recs, layout.speed_table(), pods, now, two_stage=two_stage)
         assert helpers.binding_bytes_equal(ob, eb), helpers.first_binding_diff(ob, eb)
         assert orecs.tobytes() == erecs.tobytes(), ref_compare.diff_records(orecs, erecs)[:3]
         placed += int((ob['status'] == 0).sum())
@@ -36,3 +37,16 @@ def test_snapshot_predicate_matches_oracle_candidates(oracle_lib, emu):
                 assert np.array_equal(cand, feas), (seed, cand, feas)
                 checked += int(cand.sum())
     assert checked > 50
+
+
+@pytest.mark.parametrize('config', [2, 3, 5])
+def test_two_stage_core_on_baseline_shapes(oracle_lib, emu, config):
+    """Summary-state decisions + deferred core ids (the CUDA sweep's structure) on the benchmark's
+    cluster shapes, where nodes really fill up (prefix offsets, misc-core hyperthread overflow)."""
+    import workload
+    recs, speed, pods, now = workload.make_workload(config, n_nodes=192, n_pods=1500)
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now, min_busy_secs=0.0)
+    eb, erecs = helpers.emu_solve(emu, recs, speed, pods, now, min_busy=0.0, two_stage=True)
+    assert helpers.binding_bytes_equal(ob, eb), helpers.first_binding_diff(ob, eb)
+    assert orecs.tobytes() == erecs.tobytes()
+    assert (ob['status'] == 1).sum() > 50          # the cluster ran full

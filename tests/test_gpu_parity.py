@@ -16,14 +16,21 @@ def solver_mod():
 
 
 def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0):
-    s = solver_mod.Solver(speed, min_busy_secs=min_busy)
-    try:
-        s.load_nodes(recs)
-        b = s.solve_batch(pods, now)
-        final = s.read_nodes()
-        return b, final, s.timing()
-    finally:
-        s.close()
+    """Runs the batch with the default sweep (two warps when the clock is constant) and with the
+    forced one-warp sweep; both must agree byte for byte."""
+    outs = []
+    for single in (False, True):
+        s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single)
+        try:
+            s.load_nodes(recs)
+            b = s.solve_batch(pods, now)
+            final = s.read_nodes()
+            outs.append((b, final, s.timing()))
+        finally:
+            s.close()
+    assert helpers.binding_bytes_equal(outs[0][0], outs[1][0]), helpers.first_binding_diff(outs[0][0], outs[1][0])
+    assert outs[0][1].tobytes() == outs[1][1].tobytes()
+    return outs[0]
 
 
 @pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
@@ -70,7 +77,7 @@ def test_baseline_configs_match_oracle(oracle_lib, solver_mod, config, n_nodes, 
     cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now)
     assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
     assert orecs.tobytes() == crecs.tobytes()
-    assert timing['n_launches'] == 2
+    assert timing['n_launches'] == 5      # filter, sweep, resolve, core ids, commit
 
 
 def test_clock_changes_and_busy_window(oracle_lib, solver_mod):
@@ -141,3 +148,23 @@ def test_full_size_properties(oracle_lib, solver_mod):
     untouched[placed['node']] = False
     assert recs[untouched].tobytes() == crecs[untouched].tobytes()
     assert timing['n_types'] <= 16
+
+
+def test_constant_clock_random_scenarios(oracle_lib, solver_mod):
+    """Constant clock => the two-warp sweep (GPU pods / CPU-only pods concurrently, spills
+    serialised); small clusters make CPU-only pods spill onto GPU nodes all the time."""
+    spills = 0
+    for seed in range(12):
+        scn = scenarios.random_scenario(8000 + seed * 3, n_nodes=12, n_pods=64, flavor='mixed' if seed % 3 else 'big',
+                                        max_groups=3)
+        recs, pods, _, layout = ref_compare.pack_scenario(scn)
+        for busy in (30.0, 0.0):
+            now = np.full(len(pods), 5000.0)
+            ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now, min_busy_secs=busy)
+            cb, crecs, _ = _run_cuda(solver_mod, recs, layout.speed_table(), pods, now, min_busy=busy)
+            assert helpers.binding_bytes_equal(ob, cb), (seed, busy, helpers.first_binding_diff(ob, cb))
+            assert orecs.tobytes() == crecs.tobytes()
+            placed = ob[ob['status'] == 0]
+            cpu_only = placed[placed['n_gpus'] == 0]
+            spills += int((recs['n_gpus'][cpu_only['node']] > 0).sum())
+    assert spills > 8

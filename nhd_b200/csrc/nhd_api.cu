@@ -101,6 +101,9 @@ struct nhd_handle {
     uint64_t* d_memo = nullptr;
     double now0 = 0.0;
     bool const_clock = true;
+    int n_names = 0;
+    uint64_t names_used = 0;
+    uint64_t* d_pod_groups = nullptr; size_t pod_groups_cap = 0;
     std::vector<int32_t> pod_type_host;
 
     nhd_timing timing;
@@ -237,7 +240,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done); cudaFree(h->d_pod_groups);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -458,6 +461,20 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
     CK(cudaSetDevice(h->params.device));
     h->staged = h->solved = false;
 
+    /* node-group gate (NHDScheduler.py:235-247): one distinct pod group list -> folded into the pod
+     * types; several -> types are group-agnostic and the sweep applies per-name node bitmaps */
+    bool multi_group = false;
+    uint64_t names_used = 0;
+    for (int i = 0; i < n_pods; i++) {
+        names_used |= pods[i].group_mask;
+        if (pods[i].group_mask != pods[0].group_mask) multi_group = true;
+    }
+    h->n_names = 0;
+    h->names_used = 0;
+    if (multi_group) {
+        h->names_used = names_used;
+        h->n_names = __builtin_popcountll(names_used);
+    }
     /* pod types = distinct descriptors (the reference re-derives everything per pod) */
     std::unordered_map<PodKey, int32_t, PodKeyHash> index;
     index.reserve(64);
@@ -471,6 +488,7 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
             return fail(h, NHD_ERR_UNSUPPORTED, "pod %d: %d groups on %d-NUMA nodes exceeds the tuple limits", i,
                         (int)pods[i].n_groups, h->max_numa);
         PodKey k{canonical_pod(pods[i])};
+        if (multi_group) k.p.group_mask = ~0ULL;
         auto it = index.find(k);
         if (it == index.end()) {
             PodType t;
@@ -501,7 +519,14 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
         CK(cudaMalloc((void**)&h->d_out, (size_t)n_pods * sizeof(nhd_binding)));
         h->pods_cap = n_pods;
     }
-    CK(grow_dev(h->d_bitmaps, h->bitmaps_cap, (size_t)(T + 2) * h->words * 8));
+    CK(grow_dev(h->d_bitmaps, h->bitmaps_cap, (size_t)(T + 2 + h->n_names) * h->words * 8));
+    if (multi_group) {
+        CK(grow_dev(h->d_pod_groups, h->pod_groups_cap, (size_t)n_pods * 8));
+        std::vector<uint64_t> gm(n_pods);
+        for (int i = 0; i < n_pods; i++) gm[i] = pods[i].group_mask;
+        CK(cudaMemcpyAsync(h->d_pod_groups, gm.data(), (size_t)n_pods * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(grow_dev(h->d_cursors, h->cursors_cap, (size_t)std::max(T, 1) * 3 * 4));
     if (T) CK(cudaMemcpyAsync(h->d_types, h->h_batch, types_bytes, cudaMemcpyHostToDevice, h->stream));
     if (n_pods) {
@@ -538,13 +563,13 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     /* 1. snapshot predicate kernel over this rank's node shard */
     const int ws = h->params.world_size, rk = h->params.rank;
     const int super_lo = (int)((long)h->n_super * rk / ws), super_hi = (int)((long)h->n_super * (rk + 1) / ws);
-    const size_t bm_bytes = (size_t)(T + 2) * W * 8;
+    const size_t bm_bytes = (size_t)(T + 2 + h->n_names) * W * 8;
     if (ws > 1) CK(cudaMemsetAsync(h->d_bitmaps, 0, bm_bytes, h->stream));
     if (h->n_pods > 0) {
         FilterArgs fa;
         fa.nodes = h->d_nodes; fa.types = h->d_types; fa.n_types = T; fa.n_nodes = h->n_nodes;
         fa.n_super = h->n_super; fa.super_lo = super_lo; fa.super_hi = super_hi; fa.words = W;
-        fa.bitmaps = h->d_bitmaps; fa.dyn = h->d_dyn; fa.class_id = h->d_class;
+        fa.bitmaps = h->d_bitmaps; fa.dyn = h->d_dyn; fa.class_id = h->d_class; fa.names_used = h->names_used;
         fa.now0 = h->now0; fa.min_busy = h->params.min_busy_secs;
         memcpy(fa.cap, h->cap, sizeof(fa.cap));
         const int grid = std::min(h->n_super, h->sm_count * 2);
@@ -568,6 +593,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         SweepArgs sa;
         sa.nodes = h->d_nodes; sa.types = h->d_types; sa.pod_type = h->d_pod_type; sa.now = h->d_now; sa.out = h->d_out;
         sa.n_pods = h->n_pods; sa.n_types = T; sa.n_nodes = h->n_nodes; sa.words = W;
+        sa.n_names = h->n_names; sa.names_used = h->names_used; sa.pod_groups = h->d_pod_groups;
         sa.dual = (h->const_clock && h->params.reserved_ != 1) ? 1 : 0;     /* reserved_ == 1 forces the single-warp sweep (tests) */
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend; sa.sweep_done = h->d_sweep_done;
@@ -663,7 +689,7 @@ extern "C" int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* wor
     CK(cudaSetDevice(h->params.device));
     if (n_types) *n_types = h->n_types;
     if (words_per_type) *words_per_type = h->words;
-    const int64_t need = (int64_t)(h->n_types + 2) * h->words;
+    const int64_t need = (int64_t)(h->n_types + 2) * h->words;   /* group-name bitmaps are not exported */
     if (words) {
         if (capacity_words < need) return NHD_ERR_INVALID;
         CK(cudaMemcpyAsync(words, h->d_bitmaps, (size_t)need * 8, cudaMemcpyDeviceToHost, h->stream));

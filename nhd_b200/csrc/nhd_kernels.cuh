@@ -196,7 +196,8 @@ struct FilterArgs {
     int n_super;                 /* all super-tiles (summaries are produced for every node)  */
     int super_lo, super_hi;      /* this rank's shard, in super-tiles (bitmaps only for it)   */
     int words;                   /* u64 words per bitmap */
-    uint64_t* bitmaps;           /* [n_types + 2][words]: F[0..T), NOGPU, BUSY */
+    uint64_t* bitmaps;           /* [n_types + 2 + n_names][words]: F[0..T), NOGPU, BUSY, one per node-group name in use */
+    uint64_t names_used;         /* node-group names some pod of the batch asks for (0: gate folded into the types) */
     uint4* dyn;                  /* [n_nodes padded][2]: NodeDyn summaries */
     const uint16_t* class_id;    /* hardware class of every node */
     double now0;                 /* clock of the first pod, for the BUSY snapshot */
@@ -282,6 +283,13 @@ filter_kernel(const FilterArgs a)
             out32[(size_t)a.n_types * words32 + w32] = nog;
             out32[(size_t)(a.n_types + 1) * words32 + w32] = bsy;
         }
+        /* InitialNodeFilter per group name (NHDScheduler.py:241-243): nodes carrying name j */
+        int r = 0;
+        for (uint64_t g = a.names_used; g; g &= g - 1, r++) {
+            const int jn = ctz64(g);
+            const uint32_t hasg = __ballot_sync(0xFFFFFFFFu, valid && ((u.r.group_mask >> jn) & 1));
+            if (lane == 0) out32[(size_t)(a.n_types + 2 + r) * words32 + w32] = hasg;
+        }
     }
 }
 
@@ -318,6 +326,9 @@ struct SweepArgs {
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
     int dual;                    /* 1: constant clock -> GPU pods and CPU-only pods on two warps */
+    int n_names;                 /* > 0: per-pod node-group masks, one bitmap per name after BUSY */
+    uint64_t names_used;
+    const uint64_t* pod_groups;  /* [n_pods] when n_names > 0 */
     uint64_t* bitmaps;           /* [n_types + 2][words] */
     uint4* dyn;                  /* NodeDyn summaries */
     int32_t* cursors;            /* global fallback: [n_types][2] */
@@ -539,6 +550,14 @@ __device__ __forceinline__ void bit_set(uint64_t* words, int bit)
 __device__ __forceinline__ void bit_clear(uint64_t* words, int bit)
 {
     atomicAnd(reinterpret_cast<unsigned int*>(words) + (bit >> 5), ~(1u << (bit & 31)));
+}
+
+/* bitmap word read: shared memory, or L2 (the sweep updates global bitmaps with atomics, which bypass L1) */
+template <bool SMEM>
+__device__ __forceinline__ uint64_t ldw(const uint64_t* p)
+{
+    if (SMEM) return *p;
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));
 }
 
 #define NHD_PENDING      100          /* internal binding status: node chosen, mapping not resolved yet */
@@ -992,7 +1011,7 @@ sweep_kernel(const SweepArgs a)
     if (SMEM_BITMAPS) {
         const uint4* src = reinterpret_cast<const uint4*>(a.bitmaps);
         uint4* dst = reinterpret_cast<uint4*>(s_bitmaps);
-        const int n16 = (T + 2) * W / 2;
+        const int n16 = (T + 2 + a.n_names) * W / 2;
         for (int i = tid; i < n16; i += SWEEP_THREADS) dst[i] = src[i];
     }
     /* cursors[t*3 + 0/1]: first word that may hold a candidate (pass 0 / 1); [t*3 + 2]: first
@@ -1006,6 +1025,8 @@ sweep_kernel(const SweepArgs a)
     uint64_t* const BM = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
     uint64_t* const NOGPU = BM + (size_t)T * W;
     uint64_t* const BUSY = BM + (size_t)(T + 1) * W;
+    const uint64_t* const GB = BM + (size_t)(T + 2) * W;
+    const bool multi = a.n_names > 0;
     const PodType* types = cx.types_in_smem ? s_types : a.types;
     cx.types = types;
     const bool eager = T <= 64;
@@ -1024,7 +1045,7 @@ sweep_kernel(const SweepArgs a)
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
     int n_busy = 0;
     for (int w0 = 0; w0 < W && !dual; w0 += 32) {      /* (two-warp mode runs on a constant clock: no list needed) */
-        uint64_t word = (w0 + lane < W) ? BUSY[w0 + lane] : 0;
+        uint64_t word = (w0 + lane < W) ? ldw<SMEM_BITMAPS>(&BUSY[w0 + lane]) : 0;
         int cnt = popc64(word);
         int pre = cnt;                                   /* inclusive scan over lanes */
         for (int d = 1; d < 32; d <<= 1) {
@@ -1047,11 +1068,13 @@ sweep_kernel(const SweepArgs a)
       /* the next 32 pods' types and clocks in one coalesced read */
       const int my_ti = (i0 + lane < a.n_pods) ? a.pod_type[i0 + lane] : 0;
       const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
+      const unsigned long long my_gm = (multi && i0 + lane < a.n_pods) ? a.pod_groups[i0 + lane] : 0ULL;
       const int jn = (a.n_pods - i0) < 32 ? (a.n_pods - i0) : 32;
       for (int j = 0; j < jn; j++) {
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
+        const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
         nhd_binding* bout = &a.out[i];
         const int cls = t.needs_gpu ? 1 : 0;
@@ -1121,6 +1144,14 @@ sweep_kernel(const SweepArgs a)
         pk.fail_status = 0;
         const bool skip_busy = t.needs_gpu != 0;                         /* Matcher.py:107-111 */
         uint64_t* F = BM + (size_t)ti * W;
+        /* nodes whose groups intersect the pod's (NHDScheduler.py:241); all ones when the gate is in F */
+        auto elig = [&](int w) -> uint64_t {
+            if (!multi) return ~0ULL;
+            uint64_t e = 0;
+            for (unsigned long long g = gm; g; g &= g - 1)
+                e |= ldw<SMEM_BITMAPS>(&GB[(size_t)popc64(a.names_used & ((1ULL << ctz64(g)) - 1)) * W + w]);
+            return e;
+        };
         for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
             if (dual && my_class == 0 && pass == 1) {
                 /* spill onto GPU nodes: every earlier GPU pod must be in, and later ones wait for us (done[0]) */
@@ -1131,12 +1162,12 @@ sweep_kernel(const SweepArgs a)
             int c = cursors[ti * 3 + pass];
             const int c_in = c;
             while (c < W) {
-                const uint64_t raw = F[c] & (pass == 0 ? NOGPU[c] : ~0ULL);
+                const uint64_t raw = ldw<SMEM_BITMAPS>(&F[c]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[c]) : ~0ULL);
                 if (raw) break;
                 int found = W;
                 for (int base = c + 1; base < W; base += 32) {
                     const int w = base + lane;
-                    const uint64_t r = (w < W) ? (F[w] & (pass == 0 ? NOGPU[w] : ~0ULL)) : 0;
+                    const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL)) : 0;
                     const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
                     if (nz) { found = base + ctz32(nz); break; }
                 }
@@ -1146,21 +1177,21 @@ sweep_kernel(const SweepArgs a)
             if (c >= W) continue;
             /* (2) candidates from there on, skipping busy nodes for GPU pods */
             int cb = c;
-            if (skip_busy) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
+            if (skip_busy && !multi) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
             while (cb < W) {
-                uint64_t word = F[cb] & (pass == 0 ? NOGPU[cb] : ~0ULL);
-                if (skip_busy) word &= ~BUSY[cb];
+                uint64_t word = ldw<SMEM_BITMAPS>(&F[cb]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[cb]) : ~0ULL) & elig(cb);
+                if (skip_busy) word &= ~ldw<SMEM_BITMAPS>(&BUSY[cb]);
                 if (!word) {
                     int found = W;
                     for (int base = cb + 1; base < W; base += 32) {
                         const int w = base + lane;
-                        uint64_t r = (w < W) ? (F[w] & (pass == 0 ? NOGPU[w] : ~0ULL)) : 0;
-                        if (skip_busy && w < W) r &= ~BUSY[w];
+                        uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL) & elig(w)) : 0;
+                        if (skip_busy && w < W) r &= ~ldw<SMEM_BITMAPS>(&BUSY[w]);
                         const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
                         if (nz) { found = base + ctz32(nz); break; }
                     }
                     cb = found;
-                    if (skip_busy) cursors[ti * 3 + 2] = cb;
+                    if (skip_busy && !multi) cursors[ti * 3 + 2] = cb;
                     continue;
                 }
                 const int node = cb * 64 + ctz64(word);
@@ -1226,7 +1257,7 @@ sweep_kernel(const SweepArgs a)
         PROF_MARK(5);      /* assignment */
         if (a.min_busy > 0.0) {                                          /* now - busy_time == 0 < MIN_BUSY_SECS */
             const uint64_t bit = 1ULL << (chosen & 63);
-            if (!(BUSY[chosen >> 6] & bit)) {
+            if (!(ldw<SMEM_BITMAPS>(&BUSY[chosen >> 6]) & bit)) {
                 __syncwarp();
                 if (lane == 0) {
                     bit_set(BUSY, chosen);

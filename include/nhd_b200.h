@@ -191,7 +191,13 @@ int32_t nhd_create(const nhd_params* p, nhd_handle** out);
 int32_t nhd_destroy(nhd_handle* h);
 const char* nhd_last_error(const nhd_handle* h);
 
-/* Host-side validation of wire records against the limits above. */
+/* Page-locked host buffers: records / pods / bindings placed here move to and from the device
+ * without a staging copy (anything else is staged internally). */
+int32_t nhd_alloc_pinned(uint64_t bytes, void** out);
+int32_t nhd_free_pinned(void* p);
+
+/* Host-side validation of wire records against the limits above (nhd_load_nodes runs the same
+ * check on the device). */
 int32_t nhd_validate_node(const nhd_node_rec* rec);
 int32_t nhd_validate_pod(const nhd_pod* pod);
 

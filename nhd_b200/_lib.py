@@ -13,7 +13,7 @@ EXPORTS = ('nhd_default_params', 'nhd_nccl_unique_id', 'nhd_create', 'nhd_destro
            'nhd_validate_node', 'nhd_validate_pod', 'nhd_load_nodes', 'nhd_update_nodes', 'nhd_read_nodes',
            'nhd_snapshot', 'nhd_restore', 'nhd_solve_batch', 'nhd_stage_batch', 'nhd_solve_staged',
            'nhd_fetch_bindings', 'nhd_sync', 'nhd_run_filter_only', 'nhd_last_timing', 'nhd_read_filter',
-           'nhd_debug_counters')
+           'nhd_debug_counters', 'nhd_alloc_pinned', 'nhd_free_pinned')
 
 
 class Params(ctypes.Structure):
@@ -63,6 +63,8 @@ def load():
         'nhd_last_timing': (i32, [vp, ctypes.POINTER(Timing)]),
         'nhd_read_filter': (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), vp, i64, vp, i32]),
         'nhd_debug_counters': (i32, [vp, vp]),
+        'nhd_alloc_pinned': (i32, [ctypes.c_uint64, ctypes.POINTER(vp)]),
+        'nhd_free_pinned': (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -97,6 +97,7 @@ struct nhd_handle {
     ClassSlot* d_class_slots = nullptr;
     unsigned long long* d_prof = nullptr;
     int* d_sweep_done = nullptr;
+    int* d_vresult = nullptr;
     int companion_ctas = 0;
     uint64_t* d_memo = nullptr;
     double now0 = 0.0;
@@ -160,26 +161,7 @@ static cudaError_t grow_pinned(T*& p, size_t& cap, size_t need)
 extern "C" int32_t nhd_validate_node(const nhd_node_rec* r)
 {
     if (!r) return NHD_ERR_INVALID;
-    const int K = r->n_numa;
-    if (K < 1 || K > NHD_MAX_NUMA) return NHD_ERR_UNSUPPORTED;
-    const int phys = r->phys_cores;
-    const bool smt = r->flags & NHD_NODE_SMT;
-    if (phys < 1 || phys % K != 0) return NHD_ERR_UNSUPPORTED;
-    if ((smt ? 2 * phys : phys) > NHD_MAX_LCORES) return NHD_ERR_UNSUPPORTED;
-    if (r->n_gpus > NHD_MAX_GPUS || r->n_nics > NHD_MAX_NICS) return NHD_ERR_UNSUPPORTED;
-    uint32_t gseen = 0, nseen = 0;
-    for (int k = 0; k < NHD_MAX_NUMA; k++) {
-        if (k >= K && (r->gpu_numa_mask[k] || r->nic_numa_mask[k])) return NHD_ERR_INVALID;
-        if ((gseen & r->gpu_numa_mask[k]) || (nseen & r->nic_numa_mask[k])) return NHD_ERR_INVALID;
-        gseen |= r->gpu_numa_mask[k];
-        nseen |= r->nic_numa_mask[k];
-    }
-    const uint32_t gall = r->n_gpus ? ((1u << r->n_gpus) - 1) : 0;
-    const uint32_t nall = r->n_nics == 32 ? 0xFFFFFFFFu : ((1u << r->n_nics) - 1);
-    if (gseen != gall || nseen != nall) return NHD_ERR_INVALID;
-    if ((r->gpu_used & ~gall) || (r->nic_inuse & ~nall)) return NHD_ERR_INVALID;
-    if (!std::isfinite(r->busy_time)) return NHD_ERR_INVALID;
-    return NHD_OK;
+    return validate_node_rec(*r);          /* same routine the upload path runs on the device */
 }
 
 extern "C" int32_t nhd_validate_pod(const nhd_pod* p)
@@ -240,7 +222,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done); cudaFree(h->d_pod_groups);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done); cudaFree(h->d_vresult); cudaFree(h->d_pod_groups);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -279,6 +261,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     CK(cudaMalloc((void**)&h->d_memo, (size_t)MEMO_SLOTS * 16));
     CK(cudaMemsetAsync(h->d_memo, 0, (size_t)MEMO_SLOTS * 16, h->stream));
     CK(cudaMalloc((void**)&h->d_sweep_done, 4));
+    CK(cudaMalloc((void**)&h->d_vresult, 16));
     { const char* e = getenv("NHD_COMPANION_CTAS"); h->companion_ctas = e ? atoi(e) : 0; }
     CK(cudaMalloc((void**)&h->d_prof, 64 * 8));
     CK(cudaMemsetAsync(h->d_prof, 0, 64 * 8, h->stream));
@@ -303,20 +286,46 @@ extern "C" const char* nhd_last_error(const nhd_handle* h) { return h ? h->err.c
 
 /* ------------------------------------------------------------------ cluster mirror */
 
-static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx)
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* host -> device, ingest into the tiled layout, validate on the device, classify.  Records that
+ * already sit in pinned memory (nhd_alloc_pinned) are copied straight from the caller's buffer. */
+static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx, int* max_numa)
 {
     const size_t bytes = (size_t)n * sizeof(nhd_node_rec);
     CK(grow_dev(h->d_stage, h->d_stage_cap, bytes));
-    CK(grow_pinned(h->h_stage, h->h_stage_cap, bytes));
-    memcpy(h->h_stage, recs, bytes);
-    CK(cudaMemcpyAsync(h->d_stage, h->h_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+    const void* src = recs;
+    if (!is_pinned_host(recs)) {
+        CK(grow_pinned(h->h_stage, h->h_stage_cap, bytes));
+        memcpy(h->h_stage, recs, bytes);
+        src = h->h_stage;
+    }
+    CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
     const int32_t* d_idx = nullptr;
     if (idx) {
         CK(grow_dev(h->d_idx, h->d_idx_cap, (size_t)n * 4));
         CK(cudaMemcpyAsync(h->d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
         d_idx = h->d_idx;
     }
-    const int threads = 256, total = n * REC_CHUNKS;
+    const int threads = 256;
+    int vinit[4] = {0x7FFFFFFF, 0, 1, 0};
+    CK(cudaMemcpyAsync(h->d_vresult, vinit, 16, cudaMemcpyHostToDevice, h->stream));
+    validate_kernel<<<(n + threads - 1) / threads, threads, 0, h->stream>>>((const nhd_node_rec*)h->d_stage, n, h->d_vresult);
+    CK(cudaGetLastError());
+    int vres[4];
+    CK(cudaMemcpyAsync(vres, h->d_vresult, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (vres[0] != 0x7FFFFFFF) {
+        const int32_t v = nhd_validate_node(&recs[vres[0]]);
+        return fail(h, v != NHD_OK ? v : NHD_ERR_INVALID, "node record %d rejected by nhd_validate_node", vres[0]);
+    }
+    *max_numa = vres[2];
+    const int total = n * REC_CHUNKS;
     ingest_kernel<<<(total + threads - 1) / threads, threads, 0, h->stream>>>(
         (const uint4*)h->d_stage, d_idx, n, h->d_nodes);
     CK(cudaGetLastError());
@@ -333,13 +342,6 @@ extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node
 {
     if (!h || n_nodes < 0 || (n_nodes > 0 && !recs)) return NHD_ERR_INVALID;
     CK(cudaSetDevice(h->params.device));
-    int max_numa = 1;
-    for (int i = 0; i < n_nodes; i++) {
-        int32_t v = nhd_validate_node(&recs[i]);
-        if (v != NHD_OK) return fail(h, v, "node %d: record rejected by nhd_validate_node", i);
-        max_numa = std::max(max_numa, (int)recs[i].n_numa);
-    }
-    h->max_numa = max_numa;
     const int n_super = std::max(1, (n_nodes + SUPER_NODES - 1) / SUPER_NODES);
     const size_t bytes = (size_t)n_super * SUPER_BYTES;
     if (bytes != h->nodes_bytes) {
@@ -362,8 +364,13 @@ extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node
     h->loaded = true;
     h->have_snapshot = false;
     h->staged = h->solved = false;
+    h->max_numa = 1;
     if (n_nodes == 0) { CK(cudaStreamSynchronize(h->stream)); return NHD_OK; }
-    return upload_records(h, n_nodes, recs, nullptr);
+    int mx = 1;
+    const int32_t rc = upload_records(h, n_nodes, recs, nullptr, &mx);
+    if (rc != NHD_OK) { h->loaded = false; return rc; }
+    h->max_numa = mx;
+    return NHD_OK;
 }
 
 extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx, const nhd_node_rec* recs)
@@ -373,12 +380,14 @@ extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx
     CK(cudaSetDevice(h->params.device));
     for (int i = 0; i < n; i++) {
         if (idx[i] < 0 || idx[i] >= h->n_nodes) return fail(h, NHD_ERR_INVALID, "node index %d out of range", idx[i]);
-        int32_t v = nhd_validate_node(&recs[i]);
+        int32_t v = nhd_validate_node(&recs[i]);      /* before anything is written: an update must not half-apply */
         if (v != NHD_OK) return fail(h, v, "update %d: record rejected", i);
-        h->max_numa = std::max(h->max_numa, (int)recs[i].n_numa);
     }
     if (n == 0) return NHD_OK;
-    return upload_records(h, n, recs, idx);
+    int mx = 1;
+    const int32_t rc = upload_records(h, n, recs, idx, &mx);
+    if (rc == NHD_OK) h->max_numa = std::max(h->max_numa, mx);
+    return rc;
 }
 
 extern "C" int32_t nhd_read_nodes(nhd_handle* h, int32_t first, int32_t n, nhd_node_rec* out)
@@ -638,13 +647,15 @@ extern "C" int32_t nhd_fetch_bindings(nhd_handle* h, nhd_binding* out)
     if (!h->solved) return fail(h, NHD_ERR_STATE, "nhd_fetch_bindings without a solved batch");
     CK(cudaSetDevice(h->params.device));
     const size_t bytes = (size_t)h->n_pods * sizeof(nhd_binding);
+    bool direct = false;
     if (bytes) {
         if (!out) return NHD_ERR_INVALID;
-        CK(grow_pinned(h->h_out, h->h_out_cap, bytes));
-        CK(cudaMemcpyAsync(h->h_out, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+        direct = is_pinned_host(out);
+        if (!direct) CK(grow_pinned(h->h_out, h->h_out_cap, bytes));
+        CK(cudaMemcpyAsync(direct ? (void*)out : (void*)h->h_out, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    if (bytes) memcpy(out, h->h_out, bytes);
+    if (bytes && !direct) memcpy(out, h->h_out, bytes);
     cudaEventElapsedTime(&h->timing.filter_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->timing.exchange_ms, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->timing.sweep_ms, h->ev[2], h->ev[3]);
@@ -711,4 +722,19 @@ extern "C" int32_t nhd_debug_counters(nhd_handle* h, uint64_t* out32)
     CK(cudaMemcpy(out32, h->d_prof, 64 * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemset(h->d_prof, 0, 64 * 8));
     return NHD_OK;
+}
+
+/* Page-locked host memory for records / pods / bindings: buffers from here are copied to and
+ * from the device without an intermediate staging copy. */
+extern "C" int32_t nhd_alloc_pinned(uint64_t bytes, void** out)
+{
+    if (!out) return NHD_ERR_INVALID;
+    *out = nullptr;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? NHD_OK : NHD_ERR_CUDA;
+}
+
+extern "C" int32_t nhd_free_pinned(void* p)
+{
+    if (!p) return NHD_OK;
+    return cudaFreeHost(p) == cudaSuccess ? NHD_OK : NHD_ERR_CUDA;
 }

@@ -181,6 +181,35 @@ NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
     t.max_smt = (uint8_t)ms; t.max_nosmt = (uint8_t)mn; t.has_bw = (uint8_t)bw;
 }
 
+/* ---------------------------------------------------------------- record validation */
+
+/* Limits of the packed layout and internal consistency of one nhd_node_rec (include/nhd_b200.h).
+ * 0 = ok, -1 = malformed, -2 = valid for the reference but outside the packed limits. */
+NHD_HD int validate_node_rec(const nhd_node_rec& r)
+{
+    const int K = r.n_numa;
+    if (K < 1 || K > NHD_MAX_NUMA) return -2;
+    const int phys = r.phys_cores;
+    const bool smt = (r.flags & NHD_NODE_SMT) != 0;
+    if (phys < 1 || phys % K != 0) return -2;
+    if ((smt ? 2 * phys : phys) > NHD_MAX_LCORES) return -2;
+    if (r.n_gpus > NHD_MAX_GPUS || r.n_nics > NHD_MAX_NICS) return -2;
+    uint32_t gseen = 0, nseen = 0;
+    for (int k = 0; k < NHD_MAX_NUMA; k++) {
+        if (k >= K && (r.gpu_numa_mask[k] || r.nic_numa_mask[k])) return -1;
+        if ((gseen & r.gpu_numa_mask[k]) || (nseen & r.nic_numa_mask[k])) return -1;
+        gseen |= r.gpu_numa_mask[k];
+        nseen |= r.nic_numa_mask[k];
+    }
+    const uint32_t gall = r.n_gpus ? ((1u << r.n_gpus) - 1) : 0;
+    const uint32_t nall = r.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << r.n_nics) - 1);
+    if (gseen != gall || nseen != nall) return -1;
+    if ((r.gpu_used & ~gall) || (r.nic_inuse & ~nall)) return -1;
+    const double bt = r.busy_time;
+    if (!(bt == bt) || bt > 1.7e308 || bt < -1.7e308) return -1;       /* NaN / infinity */
+    return 0;
+}
+
 /* ---------------------------------------------------------------- node queries */
 
 NHD_HD M256 rec_used(const nhd_node_rec& r) { M256 m; for (int i = 0; i < 4; i++) m.w[i] = r.used[i]; return m; }

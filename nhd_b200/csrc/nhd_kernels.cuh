@@ -81,6 +81,22 @@ __global__ void ingest_kernel(const uint4* __restrict__ aos, const int32_t* __re
     *reinterpret_cast<uint4*>(tiled + chunk_off(node, c)) = aos[i];
 }
 
+/* validation of freshly uploaded AoS records on the device: result[0] = lowest bad record index
+ * (INT_MAX if none), result[1] = its error code, result[2] = max n_numa seen */
+__global__ void validate_kernel(const nhd_node_rec* __restrict__ aos, int n, int* result)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nhd_node_rec r = aos[i];
+    const int v = validate_node_rec(r);
+    if (v != 0) {
+        const int prev = atomicMin(&result[0], i);
+        if (i < prev) result[1] = v;          /* last writer with the smallest index wins (re-checked on host) */
+    } else {
+        atomicMax(&result[2], (int)r.n_numa);
+    }
+}
+
 __global__ void export_kernel(const uint8_t* __restrict__ tiled, int first, int n, uint4* __restrict__ aos)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -26,6 +26,25 @@ def nccl_unique_id() -> bytes:
     return bytes(buf)
 
 
+def pinned_array(n, dtype):
+    """numpy array of n records in page-locked host memory (nhd_alloc_pinned): such buffers go to
+    and from the device without a staging copy.  Keep the returned array alive while in use."""
+    L = _lib.load()
+    dtype = np.dtype(dtype)
+    nbytes = max(1, n * dtype.itemsize)
+    ptr = ctypes.c_void_p()
+    rc = L.nhd_alloc_pinned(nbytes, ctypes.byref(ptr))
+    if rc != 0:
+        raise SolverError(rc, 'nhd_alloc_pinned')
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    _PINNED[id(arr)] = (ptr, buf)
+    return arr
+
+
+_PINNED = {}
+
+
 class Solver:
     def __init__(self, speed_table, nic_bw_avail_percent=0.9, min_busy_secs=30.0, device=0,
                  rank=0, world_size=1, nccl_id: bytes = None, single_warp: bool = False):
@@ -96,11 +115,12 @@ class Solver:
         self._ck(self._L.nhd_restore(self._h))
 
     # ---- batches --------------------------------------------------------------------
-    def solve_batch(self, pods, now):
+    def solve_batch(self, pods, now, out=None):
         pods = np.ascontiguousarray(pods, dtype=wire.POD_DTYPE)
         now = np.ascontiguousarray(now, dtype='<f8')
         assert len(pods) == len(now)
-        out = np.zeros(len(pods), dtype=wire.BINDING_DTYPE)
+        if out is None:
+            out = np.zeros(len(pods), dtype=wire.BINDING_DTYPE)
         self._ck(self._L.nhd_solve_batch(self._h, len(pods), pods.ctypes.data, now.ctypes.data, out.ctypes.data))
         self.n_pods = len(pods)
         return out

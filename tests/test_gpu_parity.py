@@ -170,3 +170,29 @@ def test_constant_clock_random_scenarios(oracle_lib, solver_mod):
             cpu_only = placed[placed['n_gpus'] == 0]
             spills += int((recs['n_gpus'][cpu_only['node']] > 0).sum())
     assert spills > 8
+
+
+def test_upload_validation_and_pinned_buffers(oracle_lib, solver_mod):
+    """Records are validated on the device during nhd_load_nodes; pinned buffers take the zero-copy path."""
+    recs, speed, pods, now = workload.make_workload(3, n_nodes=1000, n_pods=64)
+    s = solver_mod.Solver(speed)
+    try:
+        bad = recs.copy()
+        bad['n_numa'][517] = 7
+        with pytest.raises(solver_mod.SolverError) as ei:
+            s.load_nodes(bad)
+        assert ei.value.code == -2 and '517' in str(ei.value)
+        with pytest.raises(solver_mod.SolverError):
+            s.solve_batch(pods, now)                       # nothing loaded after a rejected upload
+        prec = solver_mod.pinned_array(len(recs), recs.dtype)
+        prec[:] = recs
+        ppods = solver_mod.pinned_array(len(pods), pods.dtype)
+        ppods[:] = pods
+        out = solver_mod.pinned_array(len(pods), ref_compare.wire.BINDING_DTYPE)
+        s.load_nodes(prec)
+        s.solve_batch(ppods, now, out=out)
+        ob, orecs = oracle_lib.solve(recs, speed, pods, now)
+        assert helpers.binding_bytes_equal(ob, out)
+        assert s.read_nodes().tobytes() == orecs.tobytes()
+    finally:
+        s.close()

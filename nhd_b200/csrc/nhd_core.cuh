@@ -26,7 +26,7 @@
 #define NHD_HDN __host__ __device__ __noinline__
 #else
 #define NHD_HD inline
-#define NHD_HDN
+#define NHD_HDN inline
 #endif
 
 namespace nhd {

@@ -366,7 +366,7 @@ __device__ __forceinline__ uint64_t memo_mix(uint64_t x)
 }
 
 /* lane-0 only.  Returns -1 infeasible, else ps | ms << 8 */
-__device__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G, uint32_t balA, uint32_t balB, uint32_t balC)
+__device__ __noinline__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G, uint32_t balA, uint32_t balB, uint32_t balC)
 {
     const uint32_t tag = 0x80000000u | ((uint32_t)K << 24) | ((uint32_t)G << 16);
     const uint64_t h = memo_mix(((uint64_t)balA << 32 | balB) ^ ((uint64_t)balC * 0x9E3779B97F4A7C15ULL) ^ tag);
@@ -442,7 +442,7 @@ __device__ __forceinline__ uint32_t pack_digits(int ps, int K, int G)
  * arguments; for K^(G+1) <= 32 each lane owns one (G+1)-tuple and the stage masks are warp
  * ballots, otherwise lane 0 enumerates.  Returns feasibility and the mapping (uniform).
  */
-__device__ bool evaluate_full(const SweepArgs& a, uint4* smemo, int smemo_mask, const nhd_node_rec& r, const NodeDyn& d,
+__device__ __noinline__ bool evaluate_full(const SweepArgs& a, uint4* smemo, int smemo_mask, const nhd_node_rec& r, const NodeDyn& d,
                               const PodType& t, int lane, PMap& pm)
 {
     const int K = r.n_numa, G = t.G;
@@ -513,7 +513,7 @@ struct Picks {
     int ng, ncl, fail_status;            /* fail_status: 0 or NHD_ASSIGN_FAILED / NHD_REF_WOULD_CRASH */
 };
 
-__device__ void compute_picks(const nhd_node_rec& r, const PodType& t, const PMap& pm, uint32_t gpu_used, int n_gpus, Picks& pk)
+__device__ __noinline__ void compute_picks(const nhd_node_rec& r, const PodType& t, const PMap& pm, uint32_t gpu_used, int n_gpus, Picks& pk)
 {
     const int G = t.G;
     pk.gi_lo = pk.gi_hi = 0; pk.claimed = 0; pk.ng = pk.ncl = 0; pk.fail_status = 0;
@@ -661,7 +661,7 @@ constexpr int CLSNIC_SLOTS = 64;
  *   GetNumaGroupIdx (Matcher.py:423-452)  mapping memo on the three masks.
  * Same results as evaluate_full + compute_picks; returns 1 (not a candidate) or 2 (placed).
  */
-__device__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
+__device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
                             const DynU& du, PMap& pm, Picks& pk, bool& missed)
 {
     PROF2_DECL
@@ -806,8 +806,8 @@ __device__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& cx, int ti, cons
  * Returns 1 (FindNode would not offer the node), 2 (placed) or 3 (SetPhysicalIdsFromMapping
  * fails) plus the mapping and the resource picks.  Decision memo first, full evaluation on a miss.
  */
-__device__ int resolve_decision(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
-                                const DynU& du, PMap& pm, Picks& pk, bool& missed)
+__device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
+                                                const DynU& du, PMap& pm, Picks& pk, bool& missed)
 {
     missed = false;
     if (summary_infeasible(t, du.d)) return 1;
@@ -876,8 +876,8 @@ __device__ int resolve_decision(const SweepArgs& a, const SweepCtx& cx, int ti, 
  * (NHDScheduler.py:289-304, Node.py:663-841) except the core ids, on the summary; writes the
  * binding header (the core ids follow in assign_cores_kernel).  Returns true when placed.
  */
-__device__ bool apply_decision(const SweepCtx& cx, const PodType& t, int node, NodeDyn& d, const PMap& pm,
-                               const Picks& pk, double now, nhd_binding* bout)
+__device__ __forceinline__ bool apply_decision(const SweepCtx& cx, const PodType& t, int node, NodeDyn& d, const PMap& pm,
+                                               const Picks& pk, double now, nhd_binding* bout)
 {
     const int G = t.G;
     const bool smt_node = (d.info & NHD_DYN_SMT) != 0;
@@ -926,6 +926,21 @@ __device__ bool apply_decision(const SweepCtx& cx, const PodType& t, int node, N
     else if (cx.lane == 3) v = make_uint4((uint32_t)pk.gi_hi, (uint32_t)(pk.gi_hi >> 32), w14, 0);
     if (cx.lane < 8) reinterpret_cast<uint4*>(bout)[cx.lane] = v;
     return !fail;
+}
+
+/* the rare in-sweep resolution of a deferred pod (node revisited): kept out of line */
+__device__ __noinline__ void resolve_pending(const SweepArgs& a, const SweepCtx& cx, int tj, const PodType& tjy, int node,
+                                             DynU& du, nhd_binding* bout)
+{
+    PMap pmj = {0, 0, 0, 0};
+    Picks pkj;
+    pkj.fail_status = 0;
+    bool mj;
+    du.d.info &= ~NHD_DYN_PENDING;
+    resolve_decision(a, cx, tj, tjy, node, du, pmj, pkj, mj);
+    apply_decision(cx, tjy, node, du.d, pmj, pkj, du.d.busy_time, bout);
+    store_dyn(a, cx, node, du);
+    __syncwarp();
 }
 
 /*
@@ -1086,18 +1101,25 @@ sweep_kernel(const SweepArgs a)
       const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
       const unsigned long long my_gm = (multi && i0 + lane < a.n_pods) ? a.pod_groups[i0 + lane] : 0ULL;
       const int jn = (a.n_pods - i0) < 32 ? (a.n_pods - i0) : 32;
-      for (int j = 0; j < jn; j++) {
+      /* which of these pods ask for GPUs: bit j of one ballot; a sweeping warp walks only its own class */
+      const uint32_t in_chunk = jn >= 32 ? 0xFFFFFFFFu : ((1u << jn) - 1);
+      const uint32_t gpu_bits = __ballot_sync(0xFFFFFFFFu, lane < jn && types[my_ti].needs_gpu) & in_chunk;
+      const int base_cpu = n_cls[0], base_gpu = n_cls[1];
+      n_cls[0] += popc32(in_chunk & ~gpu_bits);
+      n_cls[1] += popc32(gpu_bits);
+      for (uint32_t todo = !dual ? in_chunk : (my_class == 1 ? gpu_bits : (in_chunk & ~gpu_bits)); todo; todo &= todo - 1) {
+        const int j = ctz32(todo);
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
         nhd_binding* bout = &a.out[i];
-        const int cls = t.needs_gpu ? 1 : 0;
-        const int before_cpu = n_cls[0], before_gpu = n_cls[1];      /* pods of each class ahead of this one */
-        n_cls[cls]++;
+        const uint32_t below = (1u << j) - 1;
+        const int before_cpu = base_cpu + popc32(in_chunk & ~gpu_bits & below);   /* pods of each class ahead of this one */
+        const int before_gpu = base_gpu + popc32(gpu_bits & below);
+        const int done_after = (t.needs_gpu ? before_gpu : before_cpu) + 1;
         if (dual) {
-            if (cls != my_class) continue;
             /* a GPU pod must see every earlier CPU-only pod resolved: one of them may have spilled onto a GPU node */
             if (my_class == 1) { while (done[0] < before_cpu) __nanosleep(40); __threadfence_block(); }
         }
@@ -1226,15 +1248,7 @@ sweep_kernel(const SweepArgs a)
                     /* the pod that took this node first is still unresolved: do it now, in order */
                     const int pj = a.pend_pod[node];
                     const int tj = a.pod_type[pj];
-                    PMap pmj = {0, 0, 0, 0};
-                    Picks pkj;
-                    pkj.fail_status = 0;
-                    du.d.info &= ~NHD_DYN_PENDING;
-                    bool mj;
-                    resolve_decision(a, cx, tj, types[tj], node, du, pmj, pkj, mj);
-                    apply_decision(cx, types[tj], node, du.d, pmj, pkj, du.d.busy_time, &a.out[pj]);
-                    store_dyn(a, cx, node, du);
-                    __syncwarp();
+                    resolve_pending(a, cx, tj, types[tj], node, du, &a.out[pj]);
                     PROF_COUNT(12);
                 }
                 /* active / maintenance / node group are static inside a batch and already part of F */
@@ -1306,7 +1320,7 @@ sweep_kernel(const SweepArgs a)
         __syncwarp();
         if (dual) {                                        /* publish: this class is done up to and including pod i */
             __threadfence_block();
-            if (lane == 0) done[my_class] = n_cls[my_class];
+            if (lane == 0) done[my_class] = done_after;
         }
         PROF_MARK(6);      /* write-back */
       }

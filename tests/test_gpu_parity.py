@@ -196,3 +196,40 @@ def test_upload_validation_and_pinned_buffers(oracle_lib, solver_mod):
         assert s.read_nodes().tobytes() == orecs.tobytes()
     finally:
         s.close()
+
+
+def test_edge_cases_empty_and_rejected_inputs(oracle_lib, solver_mod):
+    """Empty batches / clusters, invalid map types, unschedulable pods, descriptors outside the limits."""
+    recs, speed, pods, now = workload.make_workload(3, n_nodes=300, n_pods=40)
+    s = solver_mod.Solver(speed)
+    try:
+        s.load_nodes(recs)
+        assert len(s.solve_batch(pods[:0], now[:0])) == 0                     # empty batch
+        assert s.read_nodes().tobytes() == recs.tobytes()
+        weird = pods.copy()
+        weird['map_type'][::3] = 3                                            # TOPOLOGY_MAP_NONE -> (None,)  (Matcher.py:45-47)
+        weird['hugepages_gb'][1::3] = 10_000                                  # nobody has that many hugepages
+        weird['group_mask'][2::7] = 1 << 40                                   # a node group no node carries
+        ob, orecs = oracle_lib.solve(recs, speed, weird, now)
+        cb = s.solve_batch(weird, now)
+        assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
+        assert s.read_nodes().tobytes() == orecs.tobytes()
+        assert set(np.unique(cb['status'])) >= {0, 1, 4}
+        bad = pods[:1].copy()
+        bad['n_groups'] = 0
+        with pytest.raises(solver_mod.SolverError):
+            s.solve_batch(bad, now[:1])
+        bad = pods[:1].copy()
+        bad['groups'][0][0]['n_proc'] = 200                                   # > NHD_MAX_POD_CORES
+        with pytest.raises(solver_mod.SolverError) as ei:
+            s.solve_batch(bad, now[:1])
+        assert ei.value.code == -2
+        s.load_nodes(recs[:0])                                                # empty cluster
+        out = s.solve_batch(pods[:5], now[:5])
+        assert (out['status'] == 1).all() and (out['node'] == -1).all()
+        s.load_nodes(recs[:1])                                                # one node, many pods: it fills up
+        ob, orecs = oracle_lib.solve(recs[:1], speed, pods, now)
+        cb = s.solve_batch(pods, now)
+        assert helpers.binding_bytes_equal(ob, cb) and s.read_nodes().tobytes() == orecs.tobytes()
+    finally:
+        s.close()

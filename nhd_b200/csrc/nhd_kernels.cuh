@@ -328,8 +328,9 @@ filter_kernel(const FilterArgs a)
 #endif
 
 constexpr int SWEEP_THREADS = 256;
-constexpr int SMEMO_SLOTS = 512;                  /* shared-memory front of the mapping memo (16 B)  */
-constexpr int DMEMO_SLOTS = 512;                  /* decision memo (48 B entries)                    */
+constexpr int SMEMO_SLOTS = 2048;                 /* shared-memory front of the mapping memo (16 B)  */
+constexpr int DMEMO_SLOTS = 128;                  /* decision memo (48 B entries), generic path only  */
+constexpr int SPMEMO_SLOTS = 1024;                /* NIC sub-problem memo (16 B entries)             */
 
 constexpr int DCACHE_SLOTS = 128;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
@@ -369,13 +370,15 @@ __device__ __forceinline__ uint64_t memo_mix(uint64_t x)
 __device__ __noinline__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G, uint32_t balA, uint32_t balB, uint32_t balC)
 {
     const uint32_t tag = 0x80000000u | ((uint32_t)K << 24) | ((uint32_t)G << 16);
-    const uint64_t h = memo_mix(((uint64_t)balA << 32 | balB) ^ ((uint64_t)balC * 0x9E3779B97F4A7C15ULL) ^ tag);
-    const int ss = (int)(h & smemo_mask);
+    uint32_t h32 = (balB * 0x9E3779B1u) ^ (balC * 0x85EBCA77u) ^ (balA * 0xC2B2AE3Du) ^ tag;
+    h32 ^= h32 >> 15;
+    const int ss = (int)(h32 & (uint32_t)smemo_mask);
     const uint4 e = smemo[ss];
     if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
         const int v = (int)(e.w & 0xFFFF);
         return v == 0xFFFF ? -1 : v;
     }
+    const uint64_t h = memo_mix(((uint64_t)balA << 32 | balB) ^ ((uint64_t)balC * 0x9E3779B97F4A7C15ULL) ^ tag);
     /* global memo: key = two words */
     const uint64_t k0 = (uint64_t)balA << 32 | balB, k1tag = ((uint64_t)tag << 32) | balC;
     int free_slot = -1, val = -2;
@@ -594,6 +597,7 @@ struct SweepCtx {
     int32_t* peer_dtag;      /* summary-cache tags of the other sweeping warp (two-warp mode), else null */
     const uint16_t* s_needb; /* [T][2][32] per-tuple socket demand for 2-NUMA nodes: need0 | need1 << 8 */
     struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 32 B: static NIC layout per hardware class */
+    uint4* spmemo;           /* SPMEMO_SLOTS x 16 B: first surviving NIC assignment of (type, groups S, NUMA k, NICs in use there) */
 };
 
 union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
@@ -621,6 +625,7 @@ __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx
  * the 8-slot CPython set table lives in one 64-bit word (slot byte = NIC index + 1) */
 __device__ __forceinline__ uint32_t claimed_order_packed(uint32_t rec, int n_rec, int& ncl)
 {
+    if (n_rec <= 1) { ncl = n_rec; return n_rec ? (rec & 0xFF) : 0u; }
     unsigned long long slots = 0;
     for (int e = 0; e < n_rec; e++) {
         const uint32_t v = (rec >> (8 * e)) & 0xFF;
@@ -699,6 +704,16 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     bool feas = false;
     uint32_t r_idx = 0, r_li = 0;                      /* one byte per member of S, in group order */
     if (S <= gmask) {
+      /* the sub-problem depends on (type, S, hardware class, k, which NICs of NUMA k are taken): memo */
+      const uint32_t skey = 0x80000000u | (uint32_t)ti | ((uint32_t)S << 12) | ((uint32_t)k << 16) | ((uint32_t)du.d.hw_class << 17);
+      const uint32_t inuse_k = inuse & mk;
+      uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u;
+      sh ^= sh >> 15;
+      uint4* se = &cx.spmemo[sh & (SPMEMO_SLOTS - 1)];
+      const uint4 sv = *se;
+      if (sv.x == skey && sv.y == inuse_k) {
+        feas = (sv.w >> 31) != 0; r_li = sv.z; r_idx = sv.w & 0x7FFFFFFFu;
+      } else {
         /* members of S in group order, and their demands, in registers */
         const int n = popc32((uint32_t)S);
         int sr = S;
@@ -752,6 +767,8 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
                     r_idx |= (uint32_t)popc32(mk & ((1u << l) - 1)) << (8 * e);      /* NodeNic.idx = rank inside the NUMA node */
                 }
         }
+        *se = make_uint4(skey, inuse_k, r_li, r_idx | (feas ? 0x80000000u : 0u));
+      }
     }
     PROF2(1);   /* per-NUMA sub-problems */
     /* ---- tuple lanes combine their two halves ---- */
@@ -759,8 +776,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     {
         /* every lane takes part in the shuffles; only tuple lanes use the result */
         const int p = (lane >> 1) & gmask;
-        int s1 = 0;
-        for (int g = 0; g < G; g++) s1 |= ((p >> (G - 1 - g)) & 1) << g;
+        const int s1 = (int)(__brev((unsigned)p) >> (32 - G));       /* groups on NUMA 1: digit g of the tuple is bit G-1-g of p */
         const int s0 = gmask & ~s1;
         const int f0 = __shfl_sync(0xFFFFFFFFu, (int)feas, s0);
         const int f1 = __shfl_sync(0xFFFFFFFFu, (int)feas, 16 + s1);
@@ -776,9 +792,8 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     if (v < 0) return 1;
     const int ps = v & 0xFF;
     pm.ms = (uint32_t)(v >> 8);
-    int s1 = 0;
-    pm.pn = 0;
-    for (int g = 0; g < G; g++) { const int dgt = (ps >> (G - 1 - g)) & 1; pm.pn |= (uint32_t)dgt << (8 * g); s1 |= dgt << g; }
+    const int s1 = (int)(__brev((unsigned)ps) >> (32 - G));
+    pm.pn = ((uint32_t)s1 & 1u) | (((uint32_t)s1 & 2u) << 7) | (((uint32_t)s1 & 4u) << 14) | (((uint32_t)s1 & 8u) << 21);   /* one byte per group */
     const int s0 = gmask & ~s1;
     const uint32_t li0 = __shfl_sync(0xFFFFFFFFu, r_li, s0), li1 = __shfl_sync(0xFFFFFFFFu, r_li, 16 + s1);
     const uint32_t ix0 = __shfl_sync(0xFFFFFFFFu, r_idx, s0), ix1 = __shfl_sync(0xFFFFFFFFu, r_idx, 16 + s1);
@@ -812,6 +827,7 @@ __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepC
     missed = false;
     if (summary_infeasible(t, du.d)) return 1;
     const bool fast2 = cx.s_needb && t.total_gpus == 0 && !t.pci && ((du.d.info >> 2) & 7) == 2 && du.d.hw_class != NHD_NO_CLASS && ti < 4096;
+    if (fast2) return resolve_cpu2(a, cx, ti, t, node, du, pm, pk, missed);    /* CPU-only pod on a 2-NUMA node: direct */
     const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
     const int need = smt ? t.need_smt : t.need_nosmt;
     const bool memoable = cx.types_in_smem && du.d.hw_class != NHD_NO_CLASS && need <= 63 && t.total_gpus <= 4;
@@ -842,10 +858,7 @@ __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepC
     }
     missed = true;
     int state;
-    if (fast2) {
-        /* CPU-only pod on a 2-NUMA node: direct evaluation */
-        state = resolve_cpu2(a, cx, ti, t, node, du, pm, pk, missed);
-    } else {
+    {
     /* full evaluation on the node's static description + summary */
     RecU u;
 #pragma unroll
@@ -988,7 +1001,8 @@ sweep_kernel(const SweepArgs a)
     cx.peer_dtag = dual ? dtag_all + (1 - half) * (DCACHE_SLOTS / 2) : nullptr;
     volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods finished, [1] GPU pods finished */
     cx.clsnic = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);              /* CLSNIC_SLOTS x 32 B */
-    uint8_t* p0 = reinterpret_cast<uint8_t*>(cx.clsnic + CLSNIC_SLOTS);
+    cx.spmemo = reinterpret_cast<uint4*>(cx.clsnic + CLSNIC_SLOTS);                  /* SPMEMO_SLOTS x 16 B */
+    uint8_t* p0 = reinterpret_cast<uint8_t*>(cx.spmemo + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
     uint8_t* p1 = p0 + (cx.types_in_smem ? ((T * sizeof(PodType) + 15) & ~(size_t)15) : 0);
@@ -1003,7 +1017,7 @@ sweep_kernel(const SweepArgs a)
 
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < CLSNIC_SLOTS * 2; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < CLSNIC_SLOTS * 2 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) done[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;

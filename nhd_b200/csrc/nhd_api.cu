@@ -96,9 +96,7 @@ struct nhd_handle {
     uint16_t* d_class = nullptr;
     ClassSlot* d_class_slots = nullptr;
     unsigned long long* d_prof = nullptr;
-    int* d_sweep_done = nullptr;
     int* d_vresult = nullptr;
-    int companion_ctas = 0;
     uint64_t* d_memo = nullptr;
     double now0 = 0.0;
     bool const_clock = true;
@@ -222,7 +220,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_sweep_done); cudaFree(h->d_vresult); cudaFree(h->d_pod_groups);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_vresult); cudaFree(h->d_pod_groups);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -260,9 +258,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     CK(cudaMalloc((void**)&h->d_memo, (size_t)MEMO_SLOTS * 16));
     CK(cudaMemsetAsync(h->d_memo, 0, (size_t)MEMO_SLOTS * 16, h->stream));
-    CK(cudaMalloc((void**)&h->d_sweep_done, 4));
     CK(cudaMalloc((void**)&h->d_vresult, 16));
-    { const char* e = getenv("NHD_COMPANION_CTAS"); h->companion_ctas = e ? atoi(e) : 0; }
     CK(cudaMalloc((void**)&h->d_prof, 64 * 8));
     CK(cudaMemsetAsync(h->d_prof, 0, 64 * 8, h->stream));
     CK(cudaMalloc((void**)&h->d_class_slots, (size_t)CLASS_SLOTS * sizeof(ClassSlot)));
@@ -605,9 +601,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.n_names = h->n_names; sa.names_used = h->names_used; sa.pod_groups = h->d_pod_groups;
         sa.dual = (h->const_clock && h->params.reserved_ != 1) ? 1 : 0;     /* reserved_ == 1 forces the single-warp sweep (tests) */
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
-        sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend; sa.sweep_done = h->d_sweep_done;
-        CK(cudaMemsetAsync(h->d_sweep_done, 0, 4, h->stream));
-        const int sweep_grid = 1 + std::max(0, h->companion_ctas);
+        sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
         sa.min_busy = h->params.min_busy_secs;
         memcpy(sa.cap, h->cap, sizeof(sa.cap));
         /* shared memory: memo front | pod types | cursors | (bitmaps when they fit) */
@@ -617,9 +611,9 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
         const size_t with_bitmaps = smem + bm_bytes;
         if (with_bitmaps <= (size_t)h->smem_optin) {
-            sweep_kernel<true><<<sweep_grid, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);
+            sweep_kernel<true><<<1, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);
         } else {
-            sweep_kernel<false><<<sweep_grid, SWEEP_THREADS, smem, h->stream>>>(sa);
+            sweep_kernel<false><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
         }
         CK(cudaGetLastError());
         FinishArgs fin;

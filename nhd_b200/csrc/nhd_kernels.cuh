@@ -1,26 +1,32 @@
 /*
- * nhd_kernels.cuh — sm_100a kernels of the NHD placement solver.
+ * nhd_kernels.cuh — sm_100a kernels of the NHD placement solver (one batch = 5 launches).
  *
- *   ingest_kernel   AoS wire records -> tiled device layout (and the inverse, export_kernel)
- *   filter_kernel   snapshot predicate: F[type][node] bitmaps, NOGPU and BUSY bitmaps.
- *                   Node tiles are staged into shared memory with 1-D TMA bulk copies
- *                   (cp.async.bulk + mbarrier, double buffered); one thread per node,
- *                   warp ballots produce the bitmap words.  Replaces the per-node loops of
- *                   Matcher.FilterPodResources / FilterNumaTopology / IntersectResources
+ *   ingest / validate / classify / export   layout conversion of uploaded wire records, device-side
+ *                   record validation, exact hardware-class ids of the nodes' static descriptions
+ *   filter_kernel   snapshot predicate: F[type][node] bitmaps, NOGPU / BUSY / per-group-name bitmaps
+ *                   and the 32-byte NodeDyn summaries.  Node tiles are staged into shared memory
+ *                   with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one
+ *                   thread per node, warp ballots produce the bitmap words.  Replaces the per-node
+ *                   loops of Matcher.FilterPodResources / FilterNumaTopology / IntersectResources
  *                   (nhd/Matcher.py:65-391) and NHDScheduler.InitialNodeFilter
  *                   (nhd/NHDScheduler.py:235-247).
- *   sweep_kernel    sequential select + assign: for every pod in order, first-fit over the
- *                   bitmaps (warp ballot scan), live re-validation on the node's current
- *                   record, NUMA mapping choice (CPython set order), physical core / GPU /
- *                   NIC assignment and state update.  Replaces Matcher.SelectNode /
- *                   GetNumaGroupIdx (nhd/Matcher.py:393-452), Node.SetPhysicalIdsFromMapping
- *                   (nhd/Node.py:663-841) and the SetBusy / ClaimPodNICResources calls of
+ *   sweep_kernel    the sequential part (1 CTA, one or two sweeping warps): for every pod in order,
+ *                   first fit over the bitmaps, live re-validation on the node's summary, NUMA
+ *                   mapping choice (CPython set order), GPU / NIC / hugepage / busy bookkeeping and
+ *                   the binding header.  Replaces Matcher.SelectNode / GetNumaGroupIdx
+ *                   (nhd/Matcher.py:393-452), everything of Node.SetPhysicalIdsFromMapping but the
+ *                   core ids (nhd/Node.py:663-841) and the SetBusy / ClaimPodNICResources calls of
  *                   NHDScheduler.AttemptScheduling (nhd/NHDScheduler.py:289,302-304).
+ *   resolve_kernel  pods the sweep bound to an untouched node without working out the mapping
+ *   assign_cores_kernel   Node.GetFreeCpuBatch (nhd/Node.py:502-519) for every placed pod, in
+ *                   parallel, from the snapshot core masks and per-socket prefix offsets
+ *   commit_kernel   folds the batch into the node records
  *
  * Device layout of the node array ("tiled AoSoA"): tiles of 32 nodes, 4 KB each:
  *     byte offset(node n, 16-byte chunk c) = (n / 32) * 4096 + c * 512 + (n % 32) * 16
  * so a warp reading chunk c of 32 consecutive nodes touches 512 contiguous bytes both in
  * global memory (coalesced, TMA-friendly) and in shared memory (bank-conflict free).
+ * DESIGN.md section 4 explains why the sweep is exact.
  */
 #pragma once
 
@@ -353,7 +359,6 @@ struct SweepArgs {
     int32_t* pend_pod;           /* [n_nodes] pod whose resolution is pending on the node */
     uint64_t* memo;              /* MEMO_SLOTS x 2 words (global, persists across batches) */
     unsigned long long* prof;    /* debug counters (NHD_PROFILE builds) */
-    int* sweep_done;             /* set by block 0 when the sweep has finished */
     double min_busy;
     double cap[NHD_MAX_SPEED_CLASSES];
 };
@@ -612,9 +617,10 @@ __device__ __forceinline__ void load_dyn(const SweepArgs& a, const SweepCtx& cx,
 /* HBM copy (later batches / commit_kernel read it) + shared-memory cache */
 __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx, int node, const DynU& du)
 {
+    const uint4 half = cx.lane == 0 ? du.q[0] : du.q[1];      /* a select, not an index: keeps the summary in registers */
     if (cx.lane < 2) {
-        a.dyn[(size_t)node * 2 + cx.lane] = du.q[cx.lane];
-        cx.dcache[2 * (node & cx.dcache_mask) + cx.lane] = du.q[cx.lane];
+        a.dyn[(size_t)node * 2 + cx.lane] = half;
+        cx.dcache[2 * (node & cx.dcache_mask) + cx.lane] = half;
     }
     if (cx.lane == 2) cx.dtag[node & cx.dcache_mask] = node;
     /* the other sweeping warp may hold an older copy of this node (spills, revisits) */
@@ -866,10 +872,17 @@ __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepC
         u.q[cc] = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, cc));
     apply_dyn(u.r, du.d);
     state = 1;
-    if (evaluate_full(a, cx.smemo, cx.smemo_mask, u.r, du.d, t, cx.lane, pm)) {
-        compute_picks(u.r, t, pm, du.d.gpu_used, du.d.n_gpus, pk);
-        state = pk.fail_status ? 3 : 2;
+    /* the out-of-line helpers get copies: taking the address of du / pm / pk would pin the hot
+     * path's per-pod state in local memory */
+    const NodeDyn dcopy = du.d;
+    PMap pm2 = {0, 0, 0, 0};
+    if (evaluate_full(a, cx.smemo, cx.smemo_mask, u.r, dcopy, t, cx.lane, pm2)) {
+        Picks pk2;
+        compute_picks(u.r, t, pm2, dcopy.gpu_used, dcopy.n_gpus, pk2);
+        pk = pk2;
+        state = pk2.fail_status ? 3 : 2;
     }
+    pm = pm2;
     }
     if (memoable && cx.lane == 0) {
         eu.e.a = key; eu.e.nic_inuse = du.d.nic_inuse;
@@ -978,13 +991,6 @@ sweep_kernel(const SweepArgs a)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = a.words, T = a.n_types;
-    if (blockIdx.x != 0) {
-        /* companion CTAs: the sweep itself is one CTA; a grid that covers the chip avoids the
-         * low-occupancy issue throttle (B300_MICROARCH.md, I-cache).  They only sleep until block 0 is done. */
-        if (tid == 0) { while (atomicAdd(a.sweep_done, 0) == 0) __nanosleep(2000); }
-        return;
-    }
-
     const int wid = tid >> 5;
     const int dual = a.dual;
     const int half = (dual && wid == 1) ? 1 : 0;          /* the second sweeping warp owns the upper halves */
@@ -1213,8 +1219,9 @@ sweep_kernel(const SweepArgs a)
             /* (1) the cursor: first word with any candidate of this pass */
             int c = cursors[ti * 3 + pass];
             const int c_in = c;
+            uint64_t raw = 0;
             while (c < W) {
-                const uint64_t raw = ldw<SMEM_BITMAPS>(&F[c]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[c]) : ~0ULL);
+                raw = ldw<SMEM_BITMAPS>(&F[c]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[c]) : ~0ULL);
                 if (raw) break;
                 int found = W;
                 for (int base = c + 1; base < W; base += 32) {
@@ -1230,8 +1237,12 @@ sweep_kernel(const SweepArgs a)
             /* (2) candidates from there on, skipping busy nodes for GPU pods */
             int cb = c;
             if (skip_busy && !multi) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
+            bool first = true;
             while (cb < W) {
-                uint64_t word = ldw<SMEM_BITMAPS>(&F[cb]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[cb]) : ~0ULL) & elig(cb);
+                /* first look: the cursor word was just read */
+                uint64_t word = (first && cb == c) ? raw : (ldw<SMEM_BITMAPS>(&F[cb]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[cb]) : ~0ULL));
+                first = false;
+                if (multi) word &= elig(cb);
                 if (skip_busy) word &= ~ldw<SMEM_BITMAPS>(&BUSY[cb]);
                 if (!word) {
                     int found = W;
@@ -1262,7 +1273,10 @@ sweep_kernel(const SweepArgs a)
                     /* the pod that took this node first is still unresolved: do it now, in order */
                     const int pj = a.pend_pod[node];
                     const int tj = a.pod_type[pj];
-                    resolve_pending(a, cx, tj, types[tj], node, du, &a.out[pj]);
+                    DynU dtmp;
+                    dtmp.q[0] = du.q[0]; dtmp.q[1] = du.q[1];
+                    resolve_pending(a, cx, tj, types[tj], node, dtmp, &a.out[pj]);
+                    du.q[0] = dtmp.q[0]; du.q[1] = dtmp.q[1];
                     PROF_COUNT(12);
                 }
                 /* active / maintenance / node group are static inside a batch and already part of F */
@@ -1296,10 +1310,11 @@ sweep_kernel(const SweepArgs a)
         } else {
             placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
             store_dyn(a, cx, chosen, du);
-            if (lane == 0) bit_set(s_touched, chosen);
+            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
+            if (lane == 0 && du.d.n_gpus) bit_set(s_touched, chosen);
         }
         PROF_MARK(5);      /* assignment */
-        if (a.min_busy > 0.0) {                                          /* now - busy_time == 0 < MIN_BUSY_SECS */
+        if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
             const uint64_t bit = 1ULL << (chosen & 63);
             if (!(ldw<SMEM_BITMAPS>(&BUSY[chosen >> 6]) & bit)) {
                 __syncwarp();
@@ -1340,7 +1355,6 @@ sweep_kernel(const SweepArgs a)
       }
     }
     if (wid == 0) { PROF_FLUSH(a.prof); }
-    if (lane == 0) atomicAdd(a.sweep_done, 1);       /* releases the companion CTAs (both sweeping warps add; any non-zero value does) */
 }
 
 /*

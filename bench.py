@@ -246,7 +246,7 @@ def main():
             e2e_t.append(dt)
     e2e_value = P * len(e2e_t) / sum(e2e_t)
     same = all(np.array_equal(out[n], bindings[n]) for n in out.dtype.names if n != 'pad_')
-    h2d = N * wire.NODE_DTYPE.itemsize + n_types * 168 + P * 12
+    h2d = N * wire.NODE_DTYPE.itemsize + n_types * 176 + P * 12
     d2h = P * wire.BINDING_DTYPE.itemsize
 
     if rank != 0:

@@ -140,6 +140,8 @@ struct PodType {
     uint8_t max_smt;                   /* largest single entry of cl_smt: some socket must offer that much */
     uint8_t max_nosmt;
     uint8_t has_bw;                    /* some group asks for NIC bandwidth (rx or tx > 0) */
+    uint8_t nic_groups;                /* bit g: group g has RX/TX cores, i.e. claims its NIC (Node.py:742-755) */
+    uint8_t pad2_[7];
 };
 
 NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
@@ -179,6 +181,10 @@ NHD_HD void make_pod_type(const nhd_pod& p, PodType& t)
     for (int g = 0; g < p.n_groups && g < NHD_MAX_GROUPS; g++)
         if (p.groups[g].rx_gbps > 0.0 || p.groups[g].tx_gbps > 0.0) bw = 1;
     t.max_smt = (uint8_t)ms; t.max_nosmt = (uint8_t)mn; t.has_bw = (uint8_t)bw;
+    t.nic_groups = 0;
+    for (int g = 0; g < p.n_groups && g < NHD_MAX_GROUPS; g++)
+        if (p.groups[g].flags & NHD_GRP_HAS_NIC_CORES) t.nic_groups |= (uint8_t)(1u << g);
+    for (int i = 0; i < 7; i++) t.pad2_[i] = 0;
 }
 
 /* ---------------------------------------------------------------- record validation */

@@ -371,18 +371,10 @@ __device__ __forceinline__ uint64_t memo_mix(uint64_t x)
     return x;
 }
 
-/* lane-0 only.  Returns -1 infeasible, else ps | ms << 8 */
-__device__ __noinline__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G, uint32_t balA, uint32_t balB, uint32_t balC)
+/* miss path of the mapping memo (lane 0): global LUT, else the CPython set emulation; out of line */
+__device__ __noinline__ int choose_mapping_slow(uint4* smemo, int ss, uint64_t* gmemo, int K, int G,
+                                                uint32_t balA, uint32_t balB, uint32_t balC, uint32_t tag)
 {
-    const uint32_t tag = 0x80000000u | ((uint32_t)K << 24) | ((uint32_t)G << 16);
-    uint32_t h32 = (balB * 0x9E3779B1u) ^ (balC * 0x85EBCA77u) ^ (balA * 0xC2B2AE3Du) ^ tag;
-    h32 ^= h32 >> 15;
-    const int ss = (int)(h32 & (uint32_t)smemo_mask);
-    const uint4 e = smemo[ss];
-    if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
-        const int v = (int)(e.w & 0xFFFF);
-        return v == 0xFFFF ? -1 : v;
-    }
     const uint64_t h = memo_mix(((uint64_t)balA << 32 | balB) ^ ((uint64_t)balC * 0x9E3779B97F4A7C15ULL) ^ tag);
     /* global memo: key = two words */
     const uint64_t k0 = (uint64_t)balA << 32 | balB, k1tag = ((uint64_t)tag << 32) | balC;
@@ -404,12 +396,27 @@ __device__ __noinline__ int choose_mapping_memo(uint4* smemo, int smemo_mask, ui
         }
         int ps, ms;
         val = choose_mapping(K, G, ma, mb, mc, &ps, &ms) ? (ps | (ms << 8)) : 0xFFFF;
-        if (free_slot >= 0) {
+        if (free_slot >= 0)
             reinterpret_cast<ulonglong2*>(gmemo)[free_slot] = make_ulonglong2(k0, k1tag | ((uint64_t)val << 32));
-        }
     }
     smemo[ss] = make_uint4(balA, balB, balC, tag | (uint32_t)val);
     return val == 0xFFFF ? -1 : val;
+}
+
+/* lane-0 only.  Returns -1 infeasible, else ps | ms << 8.  The shared-memory hit is inline. */
+__device__ __forceinline__ int choose_mapping_memo(uint4* smemo, int smemo_mask, uint64_t* gmemo, int K, int G,
+                                                   uint32_t balA, uint32_t balB, uint32_t balC)
+{
+    const uint32_t tag = 0x80000000u | ((uint32_t)K << 24) | ((uint32_t)G << 16);
+    uint32_t h32 = (balB * 0x9E3779B1u) ^ (balC * 0x85EBCA77u) ^ (balA * 0xC2B2AE3Du) ^ tag;
+    h32 ^= h32 >> 15;
+    const int ss = (int)(h32 & (uint32_t)smemo_mask);
+    const uint4 e = smemo[ss];
+    if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
+        const int v = (int)(e.w & 0xFFFF);
+        return v == 0xFFFF ? -1 : v;
+    }
+    return choose_mapping_slow(smemo, ss, gmemo, K, G, balA, balB, balC, tag);
 }
 
 /*
@@ -812,7 +819,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
         else { l = (li0 >> (8 * e0)) & 0xFF; x = (ix0 >> (8 * e0)) & 0xFF; e0++; }
         pm.li |= l << (8 * g);
         pm.idx |= x << (8 * g);
-        if (t.pod.groups[g].flags & NHD_GRP_HAS_NIC_CORES) { rec |= l << (8 * n_rec); n_rec++; }
+        if ((t.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
     }
     PROF2(4);   /* expand */
     pk.claimed = claimed_order_packed(rec, n_rec, pk.ncl);

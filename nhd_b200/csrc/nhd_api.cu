@@ -606,7 +606,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         memcpy(sa.cap, h->cap, sizeof(sa.cap));
         /* shared memory: memo front | pod types | cursors | (bitmaps when they fit) */
         size_t smem = (size_t)SMEMO_SLOTS * 16 + (size_t)DMEMO_SLOTS * 48 + (size_t)DCACHE_SLOTS * 36 + 16 +
-                      (size_t)CLSNIC_SLOTS * 32 + (size_t)SPMEMO_SLOTS * 16;
+                      (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16;
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
         const size_t with_bitmaps = smem + bm_bytes;

@@ -661,7 +661,14 @@ __device__ __forceinline__ uint32_t claimed_order_packed(uint32_t rec, int n_rec
 }
 
 /* static NIC layout of one hardware class, cached in shared memory (32 B) */
-struct ClsNic { uint32_t tag; uint32_t m0, m1, pad; unsigned long long sp0, sp1; };
+struct ClsNic {
+    uint32_t tag; uint32_t m0, m1;        /* NIC list-index masks of NUMA 0 / 1 */
+    uint32_t nk;                          /* n_0 | n_1 << 8, bit 31: some NUMA node has more than 8 NICs */
+    unsigned long long sp0, sp1;          /* speed-class nibbles by list index */
+    uint32_t spk0, spk1;                  /* speed-class nibbles of NUMA 0 / 1 in NUMA-local order (<= 8 NICs) */
+    uint32_t pad_[2];
+};
+static_assert(sizeof(ClsNic) == 48, "ClsNic is three 16-byte chunks");
 constexpr int CLSNIC_SLOTS = 64;
 
 /*
@@ -693,10 +700,10 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
 
     /* static NIC layout of the node's hardware class */
     ClsNic* ce = &cx.clsnic[du.d.hw_class & (CLSNIC_SLOTS - 1)];
-    uint32_t m0, m1;
+    uint32_t m0, m1, nk, spk0, spk1;
     unsigned long long sp0, sp1;
     if (ce->tag == (uint32_t)du.d.hw_class + 1u) {
-        m0 = ce->m0; m1 = ce->m1; sp0 = ce->sp0; sp1 = ce->sp1;
+        m0 = ce->m0; m1 = ce->m1; nk = ce->nk; sp0 = ce->sp0; sp1 = ce->sp1; spk0 = ce->spk0; spk1 = ce->spk1;
     } else {
         missed = true;
         const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
@@ -704,8 +711,15 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
         m0 = c5.x; m1 = c5.y;
         sp0 = (unsigned long long)c7.x | ((unsigned long long)c7.y << 32);
         sp1 = (unsigned long long)c7.z | ((unsigned long long)c7.w << 32);
+        const int n0 = popc32(m0), n1 = popc32(m1);
+        nk = (uint32_t)n0 | ((uint32_t)n1 << 8) | ((n0 > 8 || n1 > 8) ? 0x80000000u : 0u);
+        spk0 = spk1 = 0;
+        int j = 0;
+        for (uint32_t f = m0; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk0 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
+        j = 0;
+        for (uint32_t f = m1; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk1 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
         __syncwarp();
-        if (lane == 0) { ce->m0 = m0; ce->m1 = m1; ce->sp0 = sp0; ce->sp1 = sp1; ce->pad = 0; ce->tag = (uint32_t)du.d.hw_class + 1u; }
+        if (lane == 0) { ce->m0 = m0; ce->m1 = m1; ce->nk = nk; ce->sp0 = sp0; ce->sp1 = sp1; ce->spk0 = spk0; ce->spk1 = spk1; ce->pad_[0] = ce->pad_[1] = 0; ce->tag = (uint32_t)du.d.hw_class + 1u; }
         __syncwarp();
     }
 
@@ -717,15 +731,24 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     bool feas = false;
     uint32_t r_idx = 0, r_li = 0;                      /* one byte per member of S, in group order */
     if (S <= gmask) {
-      /* the sub-problem depends on (type, S, hardware class, k, which NICs of NUMA k are taken): memo */
-      const uint32_t skey = 0x80000000u | (uint32_t)ti | ((uint32_t)S << 12) | ((uint32_t)k << 16) | ((uint32_t)du.d.hw_class << 17);
-      const uint32_t inuse_k = inuse & mk;
-      uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u;
+      /* the sub-problem depends on (type, S) and on the NICs of this NUMA node only: their count,
+       * speeds and which are taken, in NUMA-local order — memo keyed by exactly that */
+      uint32_t inuse_k = 0;
+      {
+          int jl = 0;
+          for (uint32_t f = mk; f; f &= f - 1, jl++) inuse_k |= ((inuse >> ctz32(f)) & 1u) << jl;
+      }
+      const bool wide = (nk >> 31) != 0;
+      const uint32_t n_k = (k ? (nk >> 8) : nk) & 0xFF;
+      const uint32_t skey = 0x80000000u | (uint32_t)ti | ((uint32_t)S << 12) | (n_k << 16) |
+                            (wide ? (0x40000000u | ((uint32_t)k << 24)) : 0u);
+      const uint32_t skey2 = wide ? (uint32_t)du.d.hw_class : (k ? spk1 : spk0);
+      uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u ^ skey2 * 0xC2B2AE3Du;
       sh ^= sh >> 15;
       uint4* se = &cx.spmemo[sh & (SPMEMO_SLOTS - 1)];
       const uint4 sv = *se;
-      if (sv.x == skey && sv.y == inuse_k) {
-        feas = (sv.w >> 31) != 0; r_li = sv.z; r_idx = sv.w & 0x7FFFFFFFu;
+      if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) {
+        feas = (sv.w >> 31) != 0; r_idx = sv.w & 0x7FFFFFFFu;
       } else {
         /* members of S in group order, and their demands, in registers */
         const int n = popc32((uint32_t)S);
@@ -780,7 +803,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
                     r_idx |= (uint32_t)popc32(mk & ((1u << l) - 1)) << (8 * e);      /* NodeNic.idx = rank inside the NUMA node */
                 }
         }
-        *se = make_uint4(skey, inuse_k, r_li, r_idx | (feas ? 0x80000000u : 0u));
+        *se = make_uint4(skey, inuse_k, skey2, r_idx | (feas ? 0x80000000u : 0u));
       }
     }
     PROF2(1);   /* per-NUMA sub-problems */
@@ -808,15 +831,14 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     const int s1 = (int)(__brev((unsigned)ps) >> (32 - G));
     pm.pn = ((uint32_t)s1 & 1u) | (((uint32_t)s1 & 2u) << 7) | (((uint32_t)s1 & 4u) << 14) | (((uint32_t)s1 & 8u) << 21);   /* one byte per group */
     const int s0 = gmask & ~s1;
-    const uint32_t li0 = __shfl_sync(0xFFFFFFFFu, r_li, s0), li1 = __shfl_sync(0xFFFFFFFFu, r_li, 16 + s1);
     const uint32_t ix0 = __shfl_sync(0xFFFFFFFFu, r_idx, s0), ix1 = __shfl_sync(0xFFFFFFFFu, r_idx, 16 + s1);
     pm.idx = pm.li = 0;
     uint32_t rec = 0;
     int n_rec = 0, e0 = 0, e1 = 0;
     for (int g = 0; g < G; g++) {
         uint32_t l, x;
-        if ((s1 >> g) & 1) { l = (li1 >> (8 * e1)) & 0xFF; x = (ix1 >> (8 * e1)) & 0xFF; e1++; }
-        else { l = (li0 >> (8 * e0)) & 0xFF; x = (ix0 >> (8 * e0)) & 0xFF; e0++; }
+        if ((s1 >> g) & 1) { x = (ix1 >> (8 * e1)) & 0xFF; e1++; l = (uint32_t)nth_bit32(m1, (int)x); }
+        else { x = (ix0 >> (8 * e0)) & 0xFF; e0++; l = (uint32_t)nth_bit32(m0, (int)x); }     /* NodeNic.idx -> index in Node.nics */
         pm.li |= l << (8 * g);
         pm.idx |= x << (8 * g);
         if ((t.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
@@ -1030,7 +1052,7 @@ sweep_kernel(const SweepArgs a)
 
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < CLSNIC_SLOTS * 2 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) done[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;

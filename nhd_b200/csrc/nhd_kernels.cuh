@@ -334,11 +334,11 @@ filter_kernel(const FilterArgs a)
 #endif
 
 constexpr int SWEEP_THREADS = 256;
-constexpr int SMEMO_SLOTS = 2048;                 /* shared-memory front of the mapping memo (16 B)  */
+constexpr int SMEMO_SLOTS = 1024;                 /* shared-memory front of the mapping memo (16 B)  */
 constexpr int DMEMO_SLOTS = 128;                  /* decision memo (48 B entries), generic path only  */
 constexpr int SPMEMO_SLOTS = 1024;                /* NIC sub-problem memo (16 B entries)             */
 
-constexpr int DCACHE_SLOTS = 128;                 /* node-summary cache (32 B entries + tag)          */
+constexpr int DCACHE_SLOTS = 512;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
 
 struct SweepArgs {

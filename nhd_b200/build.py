@@ -29,7 +29,9 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, profile=False):
+def build(force=False, verbose=False, profile=False, checks=False):
+    if checks:
+        return _compile(os.path.join(HERE, 'libnhd_b200_chk.so'), verbose, ['-DNHD_CHECKS'])
     if profile:
         return _compile(os.path.join(HERE, 'libnhd_b200_prof.so'), verbose, ['-DNHD_PROFILE'])
     if not force and not is_stale():
@@ -51,4 +53,4 @@ def _compile(LIB, verbose, extra):
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose='-v' in sys.argv, profile='--profile' in sys.argv))
+    print(build(force=True, verbose='-v' in sys.argv, profile='--profile' in sys.argv, checks='--checks' in sys.argv))

@@ -220,7 +220,13 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_prof); cudaFree(h->d_pend); cudaFree(h->d_vresult); cudaFree(h->d_pod_groups);
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); 
+#ifdef NHD_CHECKS
+    cudaFreeHost(h->d_prof);
+#else
+    cudaFree(h->d_prof);
+#endif
+    cudaFree(h->d_pend); cudaFree(h->d_vresult); cudaFree(h->d_pod_groups);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_batch) cudaFreeHost(h->h_batch);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -259,8 +265,13 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     CK(cudaMalloc((void**)&h->d_memo, (size_t)MEMO_SLOTS * 16));
     CK(cudaMemsetAsync(h->d_memo, 0, (size_t)MEMO_SLOTS * 16, h->stream));
     CK(cudaMalloc((void**)&h->d_vresult, 16));
+#ifdef NHD_CHECKS
+    CK(cudaHostAlloc((void**)&h->d_prof, 64 * 8, cudaHostAllocMapped));      /* readable after a device fault */
+    memset(h->d_prof, 0, 64 * 8);
+#else
     CK(cudaMalloc((void**)&h->d_prof, 64 * 8));
     CK(cudaMemsetAsync(h->d_prof, 0, 64 * 8, h->stream));
+#endif
     CK(cudaMalloc((void**)&h->d_class_slots, (size_t)CLASS_SLOTS * sizeof(ClassSlot)));
     CK(cudaMemsetAsync(h->d_class_slots, 0, (size_t)CLASS_SLOTS * sizeof(ClassSlot), h->stream));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -521,7 +532,7 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
         h->d_pod_type = nullptr; h->d_now = nullptr; h->d_out = nullptr; h->pods_cap = 0;
         CK(cudaMalloc((void**)&h->d_pod_type, (size_t)n_pods * 4));
         CK(cudaMalloc((void**)&h->d_now, (size_t)n_pods * 8));
-        CK(cudaMalloc((void**)&h->d_out, (size_t)n_pods * sizeof(nhd_binding)));
+        CK(cudaMalloc((void**)&h->d_out, ((size_t)n_pods + 8) * sizeof(nhd_binding)));      /* + spare records for check builds */
         h->pods_cap = n_pods;
     }
     CK(grow_dev(h->d_bitmaps, h->bitmaps_cap, (size_t)(T + 2 + h->n_names) * h->words * 8));
@@ -599,7 +610,13 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.nodes = h->d_nodes; sa.types = h->d_types; sa.pod_type = h->d_pod_type; sa.now = h->d_now; sa.out = h->d_out;
         sa.n_pods = h->n_pods; sa.n_types = T; sa.n_nodes = h->n_nodes; sa.words = W;
         sa.n_names = h->n_names; sa.names_used = h->names_used; sa.pod_groups = h->d_pod_groups;
-        sa.dual = (h->const_clock && h->params.reserved_ != 1) ? 1 : 0;     /* reserved_ == 1 forces the single-warp sweep (tests) */
+        /* reserved_: 0 default (NHD_DEFAULT_CPU_WARPS speculating CPU-class warps + 1 GPU-class warp on a constant
+         * clock), 1 forces the single-warp sweep, 2..8 select 1..7 CPU-class warps (tests compare them byte for byte) */
+        sa.dual = (h->const_clock && (h->params.reserved_ & 0xFF) != 1) ? 1 : 0;
+        {
+            const int r = h->params.reserved_ & 0xFF, flags = h->params.reserved_ >> 8;
+            sa.n_cpu_warps = ((r >= 2 && r <= 8) ? r - 1 : NHD_DEFAULT_CPU_WARPS) | (flags << 8);
+        }
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
         sa.min_busy = h->params.min_busy_secs;
@@ -711,6 +728,12 @@ extern "C" int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* wor
 extern "C" int32_t nhd_debug_counters(nhd_handle* h, uint64_t* out32)
 {
     if (!h || !out32) return NHD_ERR_INVALID;
+#ifdef NHD_CHECKS
+    cudaStreamSynchronize(h->stream);
+    memcpy(out32, h->d_prof, 64 * 8);
+    memset(h->d_prof, 0, 64 * 8);
+    return NHD_OK;
+#endif
     CK(cudaSetDevice(h->params.device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out32, h->d_prof, 64 * 8, cudaMemcpyDeviceToHost));

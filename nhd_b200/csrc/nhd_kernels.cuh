@@ -333,6 +333,17 @@ filter_kernel(const FilterArgs a)
 #define PROF_FLUSH(buf)
 #endif
 
+#ifdef NHD_CHECKS
+/* debugging aid: first violated invariant of the multi-warp sweep -> prof[56..63] */
+#define CHK_FAIL(code, x0, x1, x2) do { if (lane == 0 && atomicCAS(&a.prof[56], 0ULL, (unsigned long long)(code)) == 0ULL) { \
+    a.prof[57] = (unsigned long long)(x0); a.prof[58] = (unsigned long long)(x1); a.prof[59] = (unsigned long long)(x2); a.prof[60] = (unsigned long long)wid; a.prof[61] = (unsigned long long)i; __threadfence_system(); } } while (0)
+#define CHK_SANE(du_, node_, where_) do { const int k_ = ((du_).d.info >> 2) & 7; \
+    if (k_ < 1 || k_ > 4 || (du_).d.n_nics > 32 || (du_).d.n_gpus > 16 || (node_) < 0 || (node_) >= a.n_nodes) CHK_FAIL(where_, node_, (du_).q[0].z, (du_).q[1].y); } while (0)
+#else
+#define CHK_FAIL(code, x0, x1, x2)
+#define CHK_SANE(du_, node_, where_)
+#endif
+
 constexpr int SWEEP_THREADS = 256;
 constexpr int SMEMO_SLOTS = 1024;                 /* shared-memory front of the mapping memo (16 B)  */
 constexpr int DMEMO_SLOTS = 128;                  /* decision memo (48 B entries), generic path only  */
@@ -340,6 +351,9 @@ constexpr int SPMEMO_SLOTS = 1024;                /* NIC sub-problem memo (16 B 
 
 constexpr int DCACHE_SLOTS = 512;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
+#ifndef NHD_DEFAULT_CPU_WARPS
+#define NHD_DEFAULT_CPU_WARPS 3              /* CPU-only pod class: warps that work ahead of the committing one */
+#endif
 
 struct SweepArgs {
     uint8_t* nodes;
@@ -348,7 +362,8 @@ struct SweepArgs {
     const double* now;
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
-    int dual;                    /* 1: constant clock -> GPU pods and CPU-only pods on two warps */
+    int dual;                    /* 1: constant clock -> GPU pods and CPU-only pods on separate warps */
+    int n_cpu_warps;             /* dual: warps walking the CPU-only class (speculate ahead, commit in pod order) */
     int n_names;                 /* > 0: per-pod node-group masks, one bitmap per name after BUSY */
     uint64_t names_used;
     const uint64_t* pod_groups;  /* [n_pods] when n_names > 0 */
@@ -605,8 +620,11 @@ struct SweepCtx {
     const PodType* types;
     bool types_in_smem;
     int lane;
-    int smemo_mask, dmemo_mask, dcache_mask;   /* table sizes - 1 (halved when two warps sweep) */
-    int32_t* peer_dtag;      /* summary-cache tags of the other sweeping warp (two-warp mode), else null */
+    int smemo_mask, dmemo_mask, dcache_mask, spmemo_mask, clsnic_mask;   /* slice sizes - 1 */
+    int32_t* peer_dtag;      /* summary-cache tags of the other pod class (multi-warp mode), else null */
+    int peer_mask;
+    const volatile int* evict_wait;   /* several committing warps share the cache: done[0], else null */
+    int evict_ticket;
     const uint16_t* s_needb; /* [T][2][32] per-tuple socket demand for 2-NUMA nodes: need0 | need1 << 8 */
     struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 32 B: static NIC layout per hardware class */
     uint4* spmemo;           /* SPMEMO_SLOTS x 16 B: first surviving NIC assignment of (type, groups S, NUMA k, NICs in use there) */
@@ -614,6 +632,25 @@ struct SweepCtx {
 
 union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
 
+/*
+ * Node summaries: HBM (later batches and commit_kernel read them) behind a direct-mapped shared-memory
+ * cache per pod class.  One warp per class commits at a time, in pod order; the other warps of the
+ * CPU-only class only read (they speculate ahead and are validated later, see sweep_kernel), so the
+ * rules are:
+ *   - a slot's tag is taken away before its data changes and put back after (shared-memory accesses of a
+ *     warp are performed in order), so a reader that sees the tag before and after its reads never mixes
+ *     two nodes;
+ *   - before a committing warp evicts another node from a slot it waits until every earlier committer of
+ *     its class has fenced its global stores (done[0]), so a node that is not cached is current in L2.
+ */
+__device__ __forceinline__ int ld_vol(const volatile int* p)
+{
+    const int v = *p;
+    asm volatile("" ::: "memory");
+    return v;
+}
+
+/* committing warp: exact */
 __device__ __forceinline__ void load_dyn(const SweepArgs& a, const SweepCtx& cx, int node, DynU& du)
 {
     const int cs = node & cx.dcache_mask;
@@ -621,17 +658,60 @@ __device__ __forceinline__ void load_dyn(const SweepArgs& a, const SweepCtx& cx,
     else { du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]); }   /* L2: the sweep also updates summaries with atomics */
 }
 
-/* HBM copy (later batches / commit_kernel read it) + shared-memory cache */
+/* speculating warp: false when the slot changed hands under the read; a summary of the right node that is
+ * stale or half-updated is fine (every field only moves one way inside a batch, and the result is compared
+ * with the committed summary before it is used) */
+__device__ __forceinline__ bool spec_load_dyn(const SweepArgs& a, const SweepCtx& cx, int node, DynU& du)
+{
+    const int cs = node & cx.dcache_mask;
+    /* the committing warp changes these words while we read: the whole warp must read them in the same
+     * instructions (converged), or its lanes could see different values and part ways */
+    __syncwarp();
+    bool ok = true;
+    if (ld_vol(cx.dtag + cs) == node) {
+        du.q[0] = cx.dcache[2 * cs]; du.q[1] = cx.dcache[2 * cs + 1];
+        asm volatile("" ::: "memory");
+        ok = ld_vol(cx.dtag + cs) == node;
+    } else {
+        du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]);
+    }
+    /* belt and braces: lane 0's copy for everybody */
+    du.q[0].x = __shfl_sync(0xFFFFFFFFu, du.q[0].x, 0); du.q[0].y = __shfl_sync(0xFFFFFFFFu, du.q[0].y, 0);
+    du.q[0].z = __shfl_sync(0xFFFFFFFFu, du.q[0].z, 0); du.q[0].w = __shfl_sync(0xFFFFFFFFu, du.q[0].w, 0);
+    du.q[1].x = __shfl_sync(0xFFFFFFFFu, du.q[1].x, 0); du.q[1].y = __shfl_sync(0xFFFFFFFFu, du.q[1].y, 0);
+    du.q[1].z = __shfl_sync(0xFFFFFFFFu, du.q[1].z, 0); du.q[1].w = __shfl_sync(0xFFFFFFFFu, du.q[1].w, 0);
+    return __shfl_sync(0xFFFFFFFFu, (int)ok, 0) != 0;
+}
+
+__device__ __forceinline__ bool same_dyn(const DynU& x, const DynU& y)
+{
+    return x.q[0].x == y.q[0].x && x.q[0].y == y.q[0].y && x.q[0].z == y.q[0].z && x.q[0].w == y.q[0].w &&
+           x.q[1].x == y.q[1].x && x.q[1].y == y.q[1].y && x.q[1].z == y.q[1].z && x.q[1].w == y.q[1].w;
+}
+
+/* committing warp: HBM copy + shared-memory cache */
 __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx, int node, const DynU& du)
 {
+    const int cs = node & cx.dcache_mask;
+    if (cx.evict_wait) {
+        if (cx.lane == 0) {
+            const int old = ld_vol(cx.dtag + cs);
+            if (old != node) {
+                if (old >= 0) while (ld_vol(cx.evict_wait) < cx.evict_ticket) { }
+                cx.dtag[cs] = -1;
+            }
+        }
+        __syncwarp();
+    }
     const uint4 half = cx.lane == 0 ? du.q[0] : du.q[1];      /* a select, not an index: keeps the summary in registers */
     if (cx.lane < 2) {
         a.dyn[(size_t)node * 2 + cx.lane] = half;
-        cx.dcache[2 * (node & cx.dcache_mask) + cx.lane] = half;
+        cx.dcache[2 * cs + cx.lane] = half;
     }
-    if (cx.lane == 2) cx.dtag[node & cx.dcache_mask] = node;
-    /* the other sweeping warp may hold an older copy of this node (spills, revisits) */
-    if (cx.lane == 3 && cx.peer_dtag && cx.peer_dtag[node & cx.dcache_mask] == node) cx.peer_dtag[node & cx.dcache_mask] = -1;
+    __syncwarp();
+    if (cx.lane == 2) cx.dtag[cs] = node;
+    /* the other pod class may hold an older copy of this node (spills, revisits) */
+    if (cx.lane == 3 && cx.peer_dtag && cx.peer_dtag[node & cx.peer_mask] == node) atomicCAS(&cx.peer_dtag[node & cx.peer_mask], node, -1);
 }
 
 /* claimed NIC order, list({x[0] for x in nic_list}) (NHDScheduler.py:302), registers only:
@@ -699,7 +779,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
 
     /* static NIC layout of the node's hardware class */
-    ClsNic* ce = &cx.clsnic[du.d.hw_class & (CLSNIC_SLOTS - 1)];
+    ClsNic* ce = &cx.clsnic[du.d.hw_class & cx.clsnic_mask];
     uint32_t m0, m1, nk, spk0, spk1;
     unsigned long long sp0, sp1;
     if (ce->tag == (uint32_t)du.d.hw_class + 1u) {
@@ -745,7 +825,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
       const uint32_t skey2 = wide ? (uint32_t)du.d.hw_class : (k ? spk1 : spk0);
       uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u ^ skey2 * 0xC2B2AE3Du;
       sh ^= sh >> 15;
-      uint4* se = &cx.spmemo[sh & (SPMEMO_SLOTS - 1)];
+      uint4* se = &cx.spmemo[sh & cx.spmemo_mask];
       const uint4 sv = *se;
       if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) {
         feas = (sv.w >> 31) != 0; r_idx = sv.w & 0x7FFFFFFFu;
@@ -1022,22 +1102,35 @@ sweep_kernel(const SweepArgs a)
     const int W = a.words, T = a.n_types;
     const int wid = tid >> 5;
     const int dual = a.dual;
-    const int half = (dual && wid == 1) ? 1 : 0;          /* the second sweeping warp owns the upper halves */
+    /* multi-warp mode: warps 0..ncw-1 walk the CPU-only pods, warp ncw the GPU pods; every sweeping warp owns
+     * a quarter of each memo table, the CPU class shares one summary cache, the GPU warp has its own */
+    const int ncw = dual ? (a.n_cpu_warps & 0xFF) : 0;
+    const int dbg = a.n_cpu_warps >> 8;       /* debug switches: 1 = never adopt, 2 = never speculate */
+    const int n_slices = !dual ? 1 : (ncw + 1 > 4 ? 8 : 4);
+    const int slice = dual ? wid & (n_slices - 1) : 0;
+    const int is_gpu_warp = dual && wid == ncw;
     SweepCtx cx;
     cx.lane = lane;
-    cx.smemo_mask = (dual ? SMEMO_SLOTS / 2 : SMEMO_SLOTS) - 1;
-    cx.dmemo_mask = (dual ? DMEMO_SLOTS / 2 : DMEMO_SLOTS) - 1;
+    cx.smemo_mask = SMEMO_SLOTS / n_slices - 1;
+    cx.dmemo_mask = DMEMO_SLOTS / n_slices - 1;
+    cx.spmemo_mask = SPMEMO_SLOTS / n_slices - 1;
+    cx.clsnic_mask = CLSNIC_SLOTS / n_slices - 1;
     cx.dcache_mask = (dual ? DCACHE_SLOTS / 2 : DCACHE_SLOTS) - 1;
-    cx.smemo = reinterpret_cast<uint4*>(smem) + half * (SMEMO_SLOTS / 2);                                  /* SMEMO_SLOTS x 16 B */
-    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + half * (DMEMO_SLOTS / 2) * 3;           /* DMEMO_SLOTS x 48 B */
-    cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + half * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
+    cx.peer_mask = cx.dcache_mask;
+    cx.smemo = reinterpret_cast<uint4*>(smem) + slice * (SMEMO_SLOTS / n_slices);                                 /* SMEMO_SLOTS x 16 B */
+    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + slice * (DMEMO_SLOTS / n_slices) * 3;          /* DMEMO_SLOTS x 48 B */
+    cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + is_gpu_warp * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
-    cx.dtag = dtag_all + half * (DCACHE_SLOTS / 2);
-    cx.peer_dtag = dual ? dtag_all + (1 - half) * (DCACHE_SLOTS / 2) : nullptr;
-    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods finished, [1] GPU pods finished */
-    cx.clsnic = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);              /* CLSNIC_SLOTS x 32 B */
-    cx.spmemo = reinterpret_cast<uint4*>(cx.clsnic + CLSNIC_SLOTS);                  /* SPMEMO_SLOTS x 16 B */
-    uint8_t* p0 = reinterpret_cast<uint8_t*>(cx.spmemo + SPMEMO_SLOTS);
+    cx.dtag = dtag_all + is_gpu_warp * (DCACHE_SLOTS / 2);
+    cx.peer_dtag = dual ? dtag_all + (1 - is_gpu_warp) * (DCACHE_SLOTS / 2) : nullptr;
+    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods committed and fenced, [1] GPU pods finished, [2] CPU-only pods committed (the turn) */
+    ClsNic* clsnic_all = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);     /* CLSNIC_SLOTS x 48 B */
+    uint4* spmemo_all = reinterpret_cast<uint4*>(clsnic_all + CLSNIC_SLOTS);         /* SPMEMO_SLOTS x 16 B */
+    cx.clsnic = clsnic_all + slice * (CLSNIC_SLOTS / n_slices);
+    cx.spmemo = spmemo_all + slice * (SPMEMO_SLOTS / n_slices);
+    cx.evict_wait = (dual && !is_gpu_warp && ncw > 1) ? (const volatile int*)&done[0] : nullptr;
+    cx.evict_ticket = 0;
+    uint8_t* p0 = reinterpret_cast<uint8_t*>(spmemo_all + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
     uint8_t* p1 = p0 + (cx.types_in_smem ? ((T * sizeof(PodType) + 15) & ~(size_t)15) : 0);
@@ -1052,7 +1145,7 @@ sweep_kernel(const SweepArgs a)
 
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(cx.clsnic)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(clsnic_all)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) done[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
@@ -1099,8 +1192,8 @@ sweep_kernel(const SweepArgs a)
     int32_t* cursors = SMEM_BITMAPS ? s_cursors : a.cursors;
     for (int i = tid; i < T * 3; i += SWEEP_THREADS) cursors[i] = 0;
     __syncthreads();
-    if (wid >= (dual ? 2 : 1)) return;
-    const int my_class = dual ? wid : -1;                 /* 0: CPU-only pods, 1: GPU pods, -1: everything */
+    if (wid >= (dual ? ncw + 1 : 1)) return;
+    const int my_class = dual ? is_gpu_warp : -1;         /* 0: CPU-only pods, 1: GPU pods, -1: everything */
 
     uint64_t* const BM = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
     uint64_t* const NOGPU = BM + (size_t)T * W;
@@ -1158,22 +1251,132 @@ sweep_kernel(const SweepArgs a)
       n_cls[1] += popc32(gpu_bits);
       for (uint32_t todo = !dual ? in_chunk : (my_class == 1 ? gpu_bits : (in_chunk & ~gpu_bits)); todo; todo &= todo - 1) {
         const int j = ctz32(todo);
+        const uint32_t below = (1u << j) - 1;
+        const int before_cpu = base_cpu + popc32(in_chunk & ~gpu_bits & below);   /* pods of each class ahead of this one */
+        const int before_gpu = base_gpu + popc32(gpu_bits & below);
+        if (dual && my_class == 0 && ncw > 1 && (before_cpu % ncw) != wid) continue;   /* another CPU warp's pod */
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
         nhd_binding* bout = &a.out[i];
-        const uint32_t below = (1u << j) - 1;
-        const int before_cpu = base_cpu + popc32(in_chunk & ~gpu_bits & below);   /* pods of each class ahead of this one */
-        const int before_gpu = base_gpu + popc32(gpu_bits & below);
         const int done_after = (t.needs_gpu ? before_gpu : before_cpu) + 1;
-        if (dual) {
+        uint64_t* F = BM + (size_t)ti * W;
+
+        /*
+         * ---- speculation (CPU-only class, several warps) ----
+         * While earlier CPU-only pods are still being committed by the other warps, this warp already works
+         * its pod out against the current state: first-fit target (first set bit of F[t] & NOGPU), decision,
+         * binding record, the summary after the pod and the types the node no longer fits.  All of that is a
+         * pure function of (type, node, summary).  When its turn comes the result is adopted iff the target
+         * bit is still set (bits are only ever cleared inside a batch, so a first set bit that is still set
+         * is still the first) and the node's summary is bit for bit the one that was evaluated; otherwise
+         * the pod takes the ordinary path below.  While waiting, a result that went stale is redone at once.
+         */
+        bool adopted = false;
+        if (dual && my_class == 0 && ncw > 1) {
+            int n_spec = -1;
+            bool gave_up = !t.valid_map || multi || (dbg & 2);
+            bool sp_eager = false, inv0 = false, inv1 = false;
+            DynU ds, da;
+            for (;;) {
+                const int trn = __shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0);
+                if (n_spec >= 0) {
+                    DynU dc;
+                    __syncwarp();
+                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[n_spec >> 6])[(n_spec >> 5) & 1], 0);   /* shared or L2, never L1 */
+                    bool ok = ((fw >> (n_spec & 31)) & 1) != 0;
+                    if (ok) ok = spec_load_dyn(a, cx, n_spec, dc) && same_dyn(dc, ds);
+                    if (!ok) { n_spec = -1; PROF_COUNT(14); }
+                }
+                if (trn >= before_cpu) break;            /* validated (or not) under the ticket: nobody else commits now */
+                if (n_spec >= 0 || gave_up) { if (trn + 1 < before_cpu) __nanosleep(100); continue; }
+                /* first candidate of pass 0 (every word another warp may change is read by lane 0 for all) */
+                __syncwarp();
+                int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + 0], 0);
+                const int c_in = c;
+                uint64_t raw = 0;
+                while (c < W) {
+                    raw = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
+                    raw = __shfl_sync(0xFFFFFFFFu, raw, 0);
+                    if (raw) break;
+                    int found = W;
+                    for (int base = c + 1; base < W; base += 32) {
+                        const int w = base + lane;
+                        const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) : 0;
+                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                        if (nz) { found = base + ctz32(nz); break; }
+                    }
+                    c = found;
+                }
+                if (c != c_in) cursors[ti * 3 + 0] = c;     /* a lower bound stays one: bits are only cleared */
+                if (c >= W) { gave_up = true; continue; }    /* will spill: ordinary path */
+                const int node = c * 64 + ctz64(raw);
+                if (!spec_load_dyn(a, cx, node, ds)) continue;
+                CHK_SANE(ds, node, 7);
+                PMap pms = {0, 0, 0, 0};
+                Picks pks;
+                pks.fail_status = 0;
+                bool ms;
+                const int st = __shfl_sync(0xFFFFFFFFu, resolve_decision(a, cx, ti, t, node, ds, pms, pks, ms), 0);
+                if (st < 2) { gave_up = true; continue; }    /* stale candidate: the committing pass clears it */
+                da.q[0] = ds.q[0]; da.q[1] = ds.q[1];
+                const bool sp_placed = apply_decision(cx, t, node, da.d, pms, pks, now, bout);
+                sp_eager = false; inv0 = inv1 = false;
+                if (eager && sp_placed) {
+                    const NodeDyn& nd = da.d;
+                    const int sum = nd.fc[0] + nd.fc[1] + nd.fc[2] + nd.fc[3];
+                    int mx = nd.fc[0] > nd.fc[1] ? nd.fc[0] : nd.fc[1];
+                    const int mx2 = nd.fc[2] > nd.fc[3] ? nd.fc[2] : nd.fc[3];
+                    mx = mx > mx2 ? mx : mx2;
+                    const uint32_t alln = nd.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << nd.n_nics) - 1);
+                    const bool roomy = sum >= all_need && mx >= all_big && nd.free_hugepages_gb >= all_hp && (nd.nic_inuse & alln) != alln;
+                    if (!roomy) {
+                        sp_eager = true;
+                        inv0 = lane < T && summary_infeasible(types[lane], da.d);
+                        inv1 = lane + 32 < T && summary_infeasible(types[lane + 32], da.d);
+                    }
+                }
+                __syncwarp();
+                n_spec = node;
+                PROF_COUNT(15);
+            }
+            cx.evict_ticket = before_cpu;
+            if (dbg & 1) n_spec = -1;
+#ifdef NHD_CHECKS
+            { int old_ = 0; if (lane == 0) old_ = atomicAdd((int*)&done[3], 1); old_ = __shfl_sync(0xFFFFFFFFu, old_, 0); if (old_ != 0) CHK_FAIL(1, old_, before_cpu, done[2]); }
+            if (n_spec >= 0) {
+                DynU dx; load_dyn(a, cx, n_spec, dx);
+                CHK_SANE(dx, n_spec, 2);
+                if (!same_dyn(dx, ds)) CHK_FAIL(3, n_spec, dx.q[0].x, ds.q[0].x);
+                PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
+                const int stx = resolve_decision(a, cx, ti, t, n_spec, dx, pmx, pkx, msx);
+                if (stx < 2) CHK_FAIL(4, n_spec, stx, 0);
+                else {
+                    nhd_binding* scratch = &a.out[a.n_pods + wid];      /* spare records behind the batch */
+                    apply_decision(cx, t, n_spec, dx.d, pmx, pkx, now, scratch);
+                    if (!same_dyn(dx, da)) CHK_FAIL(5, n_spec, dx.q[0].x, da.q[0].x);
+                }
+            }
+#endif
+            if (n_spec >= 0) {
+                /* commit what was worked out ahead (a GPU-less node: no touched / BUSY bookkeeping) */
+                store_dyn(a, cx, n_spec, da);
+                if (sp_eager) {
+                    if (inv0) bit_clear(BM + (size_t)lane * W, n_spec);
+                    if (inv1) bit_clear(BM + (size_t)(lane + 32) * W, n_spec);
+                }
+                adopted = true;
+                PROF_COUNT(13);
+            }
+        } else if (dual && my_class == 1) {
             /* a GPU pod must see every earlier CPU-only pod resolved: one of them may have spilled onto a GPU node */
-            if (my_class == 1) { while (done[0] < before_cpu) __nanosleep(40); __threadfence_block(); }
+            while (done[0] < before_cpu) __nanosleep(40);
+            __threadfence_block();
         }
         PROF_MARK(0);      /* pod header */
-        do {
+        if (!adopted) do {
 
         /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
         if (now != cur_now && !dual) {
@@ -1230,7 +1433,6 @@ sweep_kernel(const SweepArgs a)
         Picks pk;
         pk.fail_status = 0;
         const bool skip_busy = t.needs_gpu != 0;                         /* Matcher.py:107-111 */
-        uint64_t* F = BM + (size_t)ti * W;
         /* nodes whose groups intersect the pod's (NHDScheduler.py:241); all ones when the gate is in F */
         auto elig = [&](int w) -> uint64_t {
             if (!multi) return ~0ULL;
@@ -1246,7 +1448,7 @@ sweep_kernel(const SweepArgs a)
                 __threadfence_block();
             }
             /* (1) the cursor: first word with any candidate of this pass */
-            int c = cursors[ti * 3 + pass];
+            int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* warps working ahead advance it too: one read for all lanes */
             const int c_in = c;
             uint64_t raw = 0;
             while (c < W) {
@@ -1298,6 +1500,7 @@ sweep_kernel(const SweepArgs a)
                     break;
                 }
                 load_dyn(a, cx, node, du);
+                CHK_SANE(du, node, 6);
                 if (du.d.info & NHD_DYN_PENDING) {
                     /* the pod that took this node first is still unresolved: do it now, in order */
                     const int pj = a.pend_pod[node];
@@ -1376,7 +1579,20 @@ sweep_kernel(const SweepArgs a)
         }
         } while (0);
         __syncwarp();
-        if (dual) {                                        /* publish: this class is done up to and including pod i */
+        if (dual && my_class == 0 && ncw > 1) {
+            /* hand the turn on as soon as the shared-memory state is in (everything the CPU-only class shares
+             * lives there when the bitmaps do); done[0] follows once this warp's global stores are fenced */
+#ifdef NHD_CHECKS
+            if (lane == 0) atomicSub((int*)&done[3], 1);
+#endif
+            if (SMEM_BITMAPS && lane == 0) done[2] = done_after;
+            __threadfence_block();
+            if (lane == 0) {
+                while (done[0] < before_cpu) { }
+                done[0] = done_after;
+                if (!SMEM_BITMAPS) done[2] = done_after;
+            }
+        } else if (dual) {                                 /* publish: this class is done up to and including pod i */
             __threadfence_block();
             if (lane == 0) done[my_class] = done_after;
         }

@@ -8,6 +8,9 @@ from tests import helpers, ref_compare, scenarios
 
 pytestmark = pytest.mark.gpu
 
+# constant-clock batches run the multi-warp sweep: every number of CPU-class warps must agree with the rest
+ALL_CPU_WARPS = (1, 2, 3, 5, 7)
+
 
 @pytest.fixture(scope='module')
 def solver_mod():
@@ -15,21 +18,25 @@ def solver_mod():
     return solver
 
 
-def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0):
-    """Runs the batch with the default sweep (two warps when the clock is constant) and with the
-    forced one-warp sweep; both must agree byte for byte."""
+def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0, extra_cpu_warps=()):
+    """Runs the batch with the default sweep (speculating CPU-class warps + one GPU-class warp when the
+    clock is constant), with the forced one-warp sweep and with one / two CPU-class warps; all must agree
+    byte for byte."""
     outs = []
-    for single in (False, True):
-        s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single)
+    for single, cw in ((False, 0), (True, 0)) + tuple((False, c) for c in extra_cpu_warps):
+        s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single, cpu_warps=cw)
         try:
             s.load_nodes(recs)
             b = s.solve_batch(pods, now)
             final = s.read_nodes()
             outs.append((b, final, s.timing()))
+        except Exception as e:
+            raise AssertionError(f'sweep mode single_warp={single} cpu_warps={cw}: {e}') from e
         finally:
             s.close()
-    assert helpers.binding_bytes_equal(outs[0][0], outs[1][0]), helpers.first_binding_diff(outs[0][0], outs[1][0])
-    assert outs[0][1].tobytes() == outs[1][1].tobytes()
+    for k, o in enumerate(outs[1:]):
+        assert helpers.binding_bytes_equal(outs[0][0], o[0]), (k + 1, helpers.first_binding_diff(outs[0][0], o[0]))
+        assert outs[0][1].tobytes() == o[1].tobytes(), k + 1
     return outs[0]
 
 
@@ -76,7 +83,7 @@ def test_filter_kernel_matches_oracle_candidates(oracle_lib, solver_mod):
 def test_baseline_configs_match_oracle(oracle_lib, solver_mod, config, n_nodes, n_pods):
     recs, speed, pods, now = workload.make_workload(config, n_nodes, n_pods)
     ob, orecs = oracle_lib.solve(recs, speed, pods, now)
-    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now)
+    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now, extra_cpu_warps=ALL_CPU_WARPS)
     assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
     assert orecs.tobytes() == crecs.tobytes()
     assert timing['n_launches'] == 5      # filter, sweep, resolve, core ids, commit
@@ -124,7 +131,7 @@ def test_full_size_properties(oracle_lib, solver_mod):
     full, so (a) the first pods are compared with the oracle at full N, (b) size-independent
     invariants are checked on everything."""
     recs, speed, pods, now = workload.make_workload(4)
-    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now)
+    cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now, extra_cpu_warps=ALL_CPU_WARPS)
     n_check = 12
     ob, _ = oracle_lib.solve(recs, speed, pods[:n_check], now[:n_check])
     assert helpers.binding_bytes_equal(ob, cb[:n_check]), helpers.first_binding_diff(ob, cb[:n_check])
@@ -153,8 +160,9 @@ def test_full_size_properties(oracle_lib, solver_mod):
 
 
 def test_constant_clock_random_scenarios(oracle_lib, solver_mod):
-    """Constant clock => the two-warp sweep (GPU pods / CPU-only pods concurrently, spills
-    serialised); small clusters make CPU-only pods spill onto GPU nodes all the time."""
+    """Constant clock => the multi-warp sweep (GPU pods / CPU-only pods concurrently, CPU-only pods worked out
+    ahead of their turn, spills serialised); small clusters make consecutive pods hit the same node and make
+    CPU-only pods spill onto GPU nodes all the time."""
     spills = 0
     for seed in range(12):
         scn = scenarios.random_scenario(8000 + seed * 3, n_nodes=12, n_pods=64, flavor='mixed' if seed % 3 else 'big',
@@ -163,7 +171,8 @@ def test_constant_clock_random_scenarios(oracle_lib, solver_mod):
         for busy in (30.0, 0.0):
             now = np.full(len(pods), 5000.0)
             ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now, min_busy_secs=busy)
-            cb, crecs, _ = _run_cuda(solver_mod, recs, layout.speed_table(), pods, now, min_busy=busy)
+            cb, crecs, _ = _run_cuda(solver_mod, recs, layout.speed_table(), pods, now, min_busy=busy,
+                                     extra_cpu_warps=ALL_CPU_WARPS)
             assert helpers.binding_bytes_equal(ob, cb), (seed, busy, helpers.first_binding_diff(ob, cb))
             assert orecs.tobytes() == crecs.tobytes()
             placed = ob[ob['status'] == 0]

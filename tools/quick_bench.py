@@ -5,9 +5,10 @@ import numpy as np
 import workload
 from nhd_b200.solver import Solver
 
+CW = int(os.environ.get('NHD_CPU_WARPS', '0'))
 for cfg in [int(a) for a in sys.argv[1:]] or [2, 3, 4]:
     recs, speed, pods, now = workload.make_workload(cfg)
-    s = Solver(speed)
+    s = Solver(speed, cpu_warps=CW)
     s.load_nodes(recs)
     s.snapshot()
     best = None
@@ -19,7 +20,7 @@ for cfg in [int(a) for a in sys.argv[1:]] or [2, 3, 4]:
         t = s.timing()
         if best is None or t['total_ms'] < best['total_ms']:
             best = dict(t, wall_ms=wall)
-    print(f"cfg{cfg} N={len(recs)} P={len(pods)} placed={int((b['status']==0).sum())} types={best['n_types']} "
+    print(f"cw={CW} cfg{cfg} N={len(recs)} P={len(pods)} placed={int((b['status']==0).sum())} types={best['n_types']} "
           f"filter={best['filter_ms']:.3f}ms sweep={best['sweep_ms']:.3f}ms total={best['total_ms']:.3f}ms wall={best['wall_ms']:.3f}ms "
           f"-> {len(pods)/best['total_ms']*1e3:,.0f} dec/s (device) {len(pods)/best['wall_ms']*1e3:,.0f} dec/s (e2e wall)", flush=True)
     s.close()

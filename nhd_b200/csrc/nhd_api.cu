@@ -615,7 +615,10 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.dual = (h->const_clock && (h->params.reserved_ & 0xFF) != 1) ? 1 : 0;
         {
             const int r = h->params.reserved_ & 0xFF, flags = h->params.reserved_ >> 8;
-            sa.n_cpu_warps = ((r >= 2 && r <= 8) ? r - 1 : NHD_DEFAULT_CPU_WARPS) | (flags << 8);
+            /* working ahead needs the node-group gate folded into the pod types (one distinct group list in the
+             * batch); otherwise the CPU-only class stays on one warp */
+            const int dflt = h->n_names > 0 ? 1 : NHD_DEFAULT_CPU_WARPS;
+            sa.n_cpu_warps = ((r >= 2 && r <= 8) ? r - 1 : dflt) | (flags << 8);
         }
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;

@@ -623,10 +623,10 @@ struct SweepCtx {
     int smemo_mask, dmemo_mask, dcache_mask, spmemo_mask, clsnic_mask;   /* slice sizes - 1 */
     int32_t* peer_dtag;      /* summary-cache tags of the other pod class (multi-warp mode), else null */
     int peer_mask;
-    const volatile int* evict_wait;   /* several committing warps share the cache: done[0], else null */
-    int evict_ticket;
+    bool write_back;         /* several committing warps share the summary cache (see store_dyn) */
     const uint16_t* s_needb; /* [T][2][32] per-tuple socket demand for 2-NUMA nodes: need0 | need1 << 8 */
-    struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 32 B: static NIC layout per hardware class */
+    struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 48 B: static NIC layout per hardware class */
+    int* clsnic_lock;
     uint4* spmemo;           /* SPMEMO_SLOTS x 16 B: first surviving NIC assignment of (type, groups S, NUMA k, NICs in use there) */
 };
 
@@ -635,13 +635,11 @@ union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
 /*
  * Node summaries: HBM (later batches and commit_kernel read them) behind a direct-mapped shared-memory
  * cache per pod class.  One warp per class commits at a time, in pod order; the other warps of the
- * CPU-only class only read (they speculate ahead and are validated later, see sweep_kernel), so the
- * rules are:
+ * CPU-only class only read (they work ahead and are validated later, see sweep_kernel), so:
  *   - a slot's tag is taken away before its data changes and put back after (shared-memory accesses of a
  *     warp are performed in order), so a reader that sees the tag before and after its reads never mixes
  *     two nodes;
- *   - before a committing warp evicts another node from a slot it waits until every earlier committer of
- *     its class has fenced its global stores (done[0]), so a node that is not cached is current in L2.
+ *   - store_dyn keeps HBM current for every node that is not in the cache.
  */
 __device__ __forceinline__ int ld_vol(const volatile int* p)
 {
@@ -689,15 +687,30 @@ __device__ __forceinline__ bool same_dyn(const DynU& x, const DynU& y)
            x.q[1].x == y.q[1].x && x.q[1].y == y.q[1].y && x.q[1].z == y.q[1].z && x.q[1].w == y.q[1].w;
 }
 
-/* committing warp: HBM copy + shared-memory cache */
+/*
+ * Committing warp.  Ordinarily write-through (HBM copy + shared-memory cache).  When several warps share the
+ * cache (cx.write_back) the summary of a GPU-less node stays in the cache until its slot is needed — the
+ * evicting warp then writes it to HBM, fenced, before the tag goes — or until the end of the sweep; nobody
+ * else ever has a store to that node in flight, so a node that is not cached is always current in L2.
+ * Summaries of GPU nodes (CPU-only pods that spilled) are written through and fenced at once: the GPU-pod
+ * warp reads them from L2.
+ */
 __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx, int node, const DynU& du)
 {
     const int cs = node & cx.dcache_mask;
-    if (cx.evict_wait) {
+    const bool through = !cx.write_back || du.d.n_gpus != 0;
+    if (cx.write_back) {
         if (cx.lane == 0) {
             const int old = ld_vol(cx.dtag + cs);
             if (old != node) {
-                if (old >= 0) while (ld_vol(cx.evict_wait) < cx.evict_ticket) { }
+                if (old >= 0) {
+                    DynU ev;
+                    ev.q[0] = cx.dcache[2 * cs]; ev.q[1] = cx.dcache[2 * cs + 1];
+                    if (ev.d.n_gpus == 0) {
+                        a.dyn[(size_t)old * 2] = ev.q[0]; a.dyn[(size_t)old * 2 + 1] = ev.q[1];
+                        __threadfence_block();
+                    }
+                }
                 cx.dtag[cs] = -1;
             }
         }
@@ -705,9 +718,10 @@ __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx
     }
     const uint4 half = cx.lane == 0 ? du.q[0] : du.q[1];      /* a select, not an index: keeps the summary in registers */
     if (cx.lane < 2) {
-        a.dyn[(size_t)node * 2 + cx.lane] = half;
+        if (through) a.dyn[(size_t)node * 2 + cx.lane] = half;
         cx.dcache[2 * cs + cx.lane] = half;
     }
+    if (cx.write_back && through) __threadfence_block();
     __syncwarp();
     if (cx.lane == 2) cx.dtag[cs] = node;
     /* the other pod class may hold an older copy of this node (spills, revisits) */
@@ -779,12 +793,19 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
 
     /* static NIC layout of the node's hardware class */
+    /* the table is shared by the warps of the CPU-only class: one writer at a time (lock), tag cleared before
+     * the data changes and set after; a reader keeps what it read only if the tag held before and after */
     ClsNic* ce = &cx.clsnic[du.d.hw_class & cx.clsnic_mask];
     uint32_t m0, m1, nk, spk0, spk1;
     unsigned long long sp0, sp1;
-    if (ce->tag == (uint32_t)du.d.hw_class + 1u) {
-        m0 = ce->m0; m1 = ce->m1; nk = ce->nk; sp0 = ce->sp0; sp1 = ce->sp1; spk0 = ce->spk0; spk1 = ce->spk1;
-    } else {
+    __syncwarp();
+    const uint32_t want = (uint32_t)du.d.hw_class + 1u;
+    bool hit = (uint32_t)ld_vol(reinterpret_cast<const volatile int*>(&ce->tag)) == want;
+    m0 = ce->m0; m1 = ce->m1; nk = ce->nk; sp0 = ce->sp0; sp1 = ce->sp1; spk0 = ce->spk0; spk1 = ce->spk1;
+    asm volatile("" ::: "memory");
+    hit = hit && (uint32_t)ld_vol(reinterpret_cast<const volatile int*>(&ce->tag)) == want;
+    hit = __all_sync(0xFFFFFFFFu, hit);
+    if (!hit) {
         missed = true;
         const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
         const uint4 c7 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 7));
@@ -799,7 +820,13 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
         j = 0;
         for (uint32_t f = m1; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk1 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
         __syncwarp();
-        if (lane == 0) { ce->m0 = m0; ce->m1 = m1; ce->nk = nk; ce->sp0 = sp0; ce->sp1 = sp1; ce->spk0 = spk0; ce->spk1 = spk1; ce->pad_[0] = ce->pad_[1] = 0; ce->tag = (uint32_t)du.d.hw_class + 1u; }
+        if (lane == 0 && atomicCAS(cx.clsnic_lock, 0, 1) == 0) {
+            volatile ClsNic* vc = ce;
+            vc->tag = 0;
+            vc->m0 = m0; vc->m1 = m1; vc->nk = nk; vc->sp0 = sp0; vc->sp1 = sp1; vc->spk0 = spk0; vc->spk1 = spk1;
+            vc->tag = want;
+            *reinterpret_cast<volatile int*>(cx.clsnic_lock) = 0;
+        }
         __syncwarp();
     }
 
@@ -1111,13 +1138,15 @@ sweep_kernel(const SweepArgs a)
     const int is_gpu_warp = dual && wid == ncw;
     SweepCtx cx;
     cx.lane = lane;
-    cx.smemo_mask = SMEMO_SLOTS / n_slices - 1;
+    /* mapping memo and NIC sub-problem memo: 16-byte entries, written and read whole, values pure functions of
+     * the key -> shared by all warps; the multi-chunk tables (decision memo, class layouts) are sliced per warp */
+    cx.smemo_mask = SMEMO_SLOTS - 1;
     cx.dmemo_mask = DMEMO_SLOTS / n_slices - 1;
-    cx.spmemo_mask = SPMEMO_SLOTS / n_slices - 1;
-    cx.clsnic_mask = CLSNIC_SLOTS / n_slices - 1;
+    cx.spmemo_mask = SPMEMO_SLOTS - 1;
+    cx.clsnic_mask = CLSNIC_SLOTS - 1;
     cx.dcache_mask = (dual ? DCACHE_SLOTS / 2 : DCACHE_SLOTS) - 1;
     cx.peer_mask = cx.dcache_mask;
-    cx.smemo = reinterpret_cast<uint4*>(smem) + slice * (SMEMO_SLOTS / n_slices);                                 /* SMEMO_SLOTS x 16 B */
+    cx.smemo = reinterpret_cast<uint4*>(smem);                                 /* SMEMO_SLOTS x 16 B */
     cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + slice * (DMEMO_SLOTS / n_slices) * 3;          /* DMEMO_SLOTS x 48 B */
     cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + is_gpu_warp * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
@@ -1126,10 +1155,10 @@ sweep_kernel(const SweepArgs a)
     volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods committed and fenced, [1] GPU pods finished, [2] CPU-only pods committed (the turn) */
     ClsNic* clsnic_all = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);     /* CLSNIC_SLOTS x 48 B */
     uint4* spmemo_all = reinterpret_cast<uint4*>(clsnic_all + CLSNIC_SLOTS);         /* SPMEMO_SLOTS x 16 B */
-    cx.clsnic = clsnic_all + slice * (CLSNIC_SLOTS / n_slices);
-    cx.spmemo = spmemo_all + slice * (SPMEMO_SLOTS / n_slices);
-    cx.evict_wait = (dual && !is_gpu_warp && ncw > 1) ? (const volatile int*)&done[0] : nullptr;
-    cx.evict_ticket = 0;
+    cx.clsnic = clsnic_all;
+    cx.clsnic_lock = const_cast<int*>(reinterpret_cast<volatile int*>(&done[3]));
+    cx.spmemo = spmemo_all;
+    cx.write_back = dual && !is_gpu_warp && ncw > 1;
     uint8_t* p0 = reinterpret_cast<uint8_t*>(spmemo_all + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
@@ -1276,24 +1305,36 @@ sweep_kernel(const SweepArgs a)
          */
         bool adopted = false;
         if (dual && my_class == 0 && ncw > 1) {
-            int n_spec = -1;
+            int n_spec = -1;                       /* node the pod has been worked out for (ds -> da), else -1 */
             bool gave_up = !t.valid_map || multi || (dbg & 2);
             bool sp_eager = false, inv0 = false, inv1 = false;
             DynU ds, da;
+            bool wait = false;
+            int seen_trn = -1;
             for (;;) {
-                const int trn = __shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0);
-                if (n_spec >= 0) {
-                    DynU dc;
+                __syncwarp();
+                if (wait) {
+                    /* only a commit can change anything this warp looks at: sleep on the turn counter rather than
+                     * poll the state (idle polling would crowd the working warps out of the shared-memory pipe) */
+                    if (lane == 0) while (ld_vol((const volatile int*)&done[2]) == seen_trn) __nanosleep(20);
                     __syncwarp();
-                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[n_spec >> 6])[(n_spec >> 5) & 1], 0);   /* shared or L2, never L1 */
+                    wait = false;
+                }
+                const int trn = __shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0);
+                seen_trn = trn;
+                const bool my_turn = trn >= before_cpu;
+                if (n_spec >= 0) {
+                    /* still this pod's first fit, and still in the state it was worked out on?  (every word another
+                     * warp may change is read by lane 0 for all: lanes must not see different values and part ways) */
+                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[n_spec >> 6])[(n_spec >> 5) & 1], 0);
                     bool ok = ((fw >> (n_spec & 31)) & 1) != 0;
+                    DynU dc;
                     if (ok) ok = spec_load_dyn(a, cx, n_spec, dc) && same_dyn(dc, ds);
                     if (!ok) { n_spec = -1; PROF_COUNT(14); }
                 }
-                if (trn >= before_cpu) break;            /* validated (or not) under the ticket: nobody else commits now */
-                if (n_spec >= 0 || gave_up) { if (trn + 1 < before_cpu) __nanosleep(100); continue; }
-                /* first candidate of pass 0 (every word another warp may change is read by lane 0 for all) */
-                __syncwarp();
+                if (my_turn) break;                          /* validated (or not) under the ticket: nobody else commits now */
+                if (n_spec >= 0 || gave_up) { wait = true; continue; }
+                /* first candidate of pass 0 */
                 int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + 0], 0);
                 const int c_in = c;
                 uint64_t raw = 0;
@@ -1342,10 +1383,8 @@ sweep_kernel(const SweepArgs a)
                 n_spec = node;
                 PROF_COUNT(15);
             }
-            cx.evict_ticket = before_cpu;
             if (dbg & 1) n_spec = -1;
 #ifdef NHD_CHECKS
-            { int old_ = 0; if (lane == 0) old_ = atomicAdd((int*)&done[3], 1); old_ = __shfl_sync(0xFFFFFFFFu, old_, 0); if (old_ != 0) CHK_FAIL(1, old_, before_cpu, done[2]); }
             if (n_spec >= 0) {
                 DynU dx; load_dyn(a, cx, n_spec, dx);
                 CHK_SANE(dx, n_spec, 2);
@@ -1580,24 +1619,32 @@ sweep_kernel(const SweepArgs a)
         } while (0);
         __syncwarp();
         if (dual && my_class == 0 && ncw > 1) {
-            /* hand the turn on as soon as the shared-memory state is in (everything the CPU-only class shares
-             * lives there when the bitmaps do); done[0] follows once this warp's global stores are fenced */
-#ifdef NHD_CHECKS
-            if (lane == 0) atomicSub((int*)&done[3], 1);
-#endif
-            if (SMEM_BITMAPS && lane == 0) done[2] = done_after;
-            __threadfence_block();
-            if (lane == 0) {
-                while (done[0] < before_cpu) { }
-                done[0] = done_after;
-                if (!SMEM_BITMAPS) done[2] = done_after;
-            }
+            /* hand the turn on.  With the bitmaps in shared memory everything the next pod reads is already there or
+             * fenced (store_dyn); with global bitmaps the atomics on them have to be fenced first */
+            if (!SMEM_BITMAPS) __threadfence_block();
+            if (lane == 0) { done[0] = done_after; done[2] = done_after; }
         } else if (dual) {                                 /* publish: this class is done up to and including pod i */
             __threadfence_block();
             if (lane == 0) done[my_class] = done_after;
         }
         PROF_MARK(6);      /* write-back */
       }
+    }
+    if (cx.write_back) {
+        /* summaries of GPU-less nodes still held only by the cache: once every CPU-only pod is in, warp 0 writes
+         * them out (GPU nodes were written through; the GPU-pod warp may still be rewriting those) */
+        if (wid == 0) {
+            if (lane == 0) while (ld_vol((const volatile int*)&done[2]) < n_cls[0]) __nanosleep(40);
+            __syncwarp();
+            for (int sl = lane; sl <= cx.dcache_mask; sl += 32) {
+                const int tg = ld_vol(cx.dtag + sl);
+                if (tg >= 0) {
+                    DynU ev;
+                    ev.q[0] = cx.dcache[2 * sl]; ev.q[1] = cx.dcache[2 * sl + 1];
+                    if (ev.d.n_gpus == 0) { a.dyn[(size_t)tg * 2] = ev.q[0]; a.dyn[(size_t)tg * 2 + 1] = ev.q[1]; }
+                }
+            }
+        }
     }
     if (wid == 0) { PROF_FLUSH(a.prof); }
 }

@@ -6,7 +6,7 @@ import workload
 from nhd_b200.solver import Solver
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 recs, speed, pods, now = workload.make_workload(cfg)
-s = Solver(speed)
+s = Solver(speed, cpu_warps=int(os.environ.get('NHD_CPU_WARPS', '0')))
 s.load_nodes(recs); s.snapshot(); s.stage_batch(pods, now)
 for _ in range(3):
     s.restore(); s.solve_staged(); s.sync()
@@ -18,6 +18,8 @@ print(f'cfg{cfg}: sweep {t["sweep_ms"]:.3f} ms, {len(pods)} pods, total cycles {
 for i, n in enumerate(names):
     print(f'  {n:24s} cycles {int(c[i]):10d} ({100*int(c[i])/max(tot,1):5.1f}%)  count {int(c[32+i]):7d}  avg {int(c[i])/max(int(c[32+i]),1):8.1f}')
 print('  stale candidates', int(c[32 + 8]))
+# CPU-class warp 0 only: pods it worked out ahead / results that went stale while waiting / results adopted
+print('  warp 0: speculations', int(c[32 + 15]), 'invalidated', int(c[32 + 14]), 'adopted', int(c[32 + 13]))
 for i, n in enumerate(['cpu2: B mask + layout', 'cpu2: sub-problems', 'cpu2: combine', 'cpu2: mapping memo', 'cpu2: expand', 'cpu2: claim order']):
     print(f'  {n:24s} cycles {int(c[16+i]):10d}  per CPU pod {int(c[16+i])/2048:8.1f}')
 s.close()

@@ -6,7 +6,7 @@ from nhd_b200.solver import Solver
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 recs, speed, pods, now = workload.make_workload(cfg)
-s = Solver(speed)
+s = Solver(speed, cpu_warps=int(os.environ.get('NHD_CPU_WARPS', '0')))
 s.load_nodes(recs)
 s.snapshot()
 s.stage_batch(pods, now)

@@ -1129,25 +1129,28 @@ sweep_kernel(const SweepArgs a)
     const int W = a.words, T = a.n_types;
     const int wid = tid >> 5;
     const int dual = a.dual;
-    /* multi-warp mode: warps 0..ncw-1 walk the CPU-only pods, warp ncw the GPU pods; every sweeping warp owns
-     * a quarter of each memo table, the CPU class shares one summary cache, the GPU warp has its own */
+    /* multi-warp mode: warps 0..ncw-1 walk the CPU-only pods, warp ncw the GPU pods; the CPU class shares one
+     * summary cache, the GPU warp has its own */
     const int ncw = dual ? (a.n_cpu_warps & 0xFF) : 0;
     const int dbg = a.n_cpu_warps >> 8;       /* debug switches: 1 = never adopt, 2 = never speculate */
-    const int n_slices = !dual ? 1 : (ncw + 1 > 4 ? 8 : 4);
-    const int slice = dual ? wid & (n_slices - 1) : 0;
     const int is_gpu_warp = dual && wid == ncw;
+    /* decision memo (48-byte entries, generic path): half for the GPU-pod warp, which lives on it; the CPU-only
+     * warps (direct path, rarely here) share the other half in equal power-of-two slices */
+    const int cpu_slices = ncw <= 1 ? 1 : (ncw <= 2 ? 2 : (ncw <= 4 ? 4 : 8));
+    const int dm_slots = !dual ? DMEMO_SLOTS : (is_gpu_warp ? DMEMO_SLOTS / 2 : DMEMO_SLOTS / 2 / cpu_slices);
+    const int dm_first = !dual ? 0 : (is_gpu_warp ? DMEMO_SLOTS / 2 : wid * dm_slots);
     SweepCtx cx;
     cx.lane = lane;
     /* mapping memo and NIC sub-problem memo: 16-byte entries, written and read whole, values pure functions of
      * the key -> shared by all warps; the multi-chunk tables (decision memo, class layouts) are sliced per warp */
     cx.smemo_mask = SMEMO_SLOTS - 1;
-    cx.dmemo_mask = DMEMO_SLOTS / n_slices - 1;
+    cx.dmemo_mask = dm_slots - 1;
     cx.spmemo_mask = SPMEMO_SLOTS - 1;
     cx.clsnic_mask = CLSNIC_SLOTS - 1;
     cx.dcache_mask = (dual ? DCACHE_SLOTS / 2 : DCACHE_SLOTS) - 1;
     cx.peer_mask = cx.dcache_mask;
     cx.smemo = reinterpret_cast<uint4*>(smem);                                 /* SMEMO_SLOTS x 16 B */
-    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + slice * (DMEMO_SLOTS / n_slices) * 3;          /* DMEMO_SLOTS x 48 B */
+    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + dm_first * 3;          /* DMEMO_SLOTS x 48 B */
     cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + is_gpu_warp * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
     cx.dtag = dtag_all + is_gpu_warp * (DCACHE_SLOTS / 2);

@@ -169,7 +169,8 @@ typedef struct nhd_params {
     int32_t  device;                 /* CUDA device ordinal                                    */
     int32_t  rank;                   /* node-shard rank, 0 when single GPU                     */
     int32_t  world_size;             /* number of GPUs sharing the node set                    */
-    int32_t  reserved_;
+    int32_t  reserved_;              /* 0.  Test hook: low byte 1 = one-warp sweep, 2..8 = 1..7 CPU-only-class warps;
+                                      * all settings produce identical bindings (tests/test_gpu_parity.py)      */
     uint8_t  nccl_unique_id[128];    /* from nhd_nccl_unique_id() on rank 0; unused if world_size==1 */
 } nhd_params;
 

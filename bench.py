@@ -305,6 +305,7 @@ def main():
                       'wall_per_step_incl_restore_and_flush': 1e3 * wall_s / args.steps},
         'roofline': {'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'frac_of_nominal_8000': achieved / 8000.0,
                      'algorithmic_bytes_per_launch': int(alg_bytes),
                      'note': 'algorithmic = reference-equivalent bytes (every eligible node record read once per '
                              'decision, SURVEY 8d); the sweep itself is latency-bound and L2-resident'},

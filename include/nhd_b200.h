@@ -40,6 +40,7 @@ extern "C" {
 #define NHD_MAX_GROUP_GPUS     8    /* len(ProcGroup.group_gpus)                      */
 #define NHD_MAX_POD_GPUS       16   /* GPUs requested by one pod                      */
 #define NHD_MAX_POD_CORES      72   /* cores requested by one pod                     */
+#define NHD_MAX_GROUP_NAMES    64   /* distinct node-group names in the cluster       */
 
 /* ---- return codes ---------------------------------------------------------- */
 #define NHD_OK                  0
@@ -48,6 +49,7 @@ extern "C" {
 #define NHD_ERR_CUDA           -3   /* CUDA runtime failure (see nhd_last_error)      */
 #define NHD_ERR_NCCL           -4   /* NCCL failure / NCCL not loadable               */
 #define NHD_ERR_STATE          -5   /* call order (e.g. solve before load)            */
+#define NHD_ERR_LABELS         -6   /* Node.ParseLabels would return False (node ignored) */
 
 /* ---- per-pod outcome (nhd_binding.status) ---------------------------------- */
 #define NHD_PLACED              0   /* FindNode found a node and assignment succeeded (NHDScheduler.py:291-304) */
@@ -250,6 +252,37 @@ int32_t nhd_read_filter(nhd_handle* h, int32_t* n_types, int32_t* words_per_type
 /* Debug: 64 words of per-phase cycle accumulators / counters of the last sweep; only non-zero
  * in libraries built with -DNHD_PROFILE. */
 int32_t nhd_debug_counters(nhd_handle* h, uint64_t* out64);
+
+/* ---- node ingest (host side, no GPU): NFD label dictionary -> nhd_node_rec --------------------
+ * Replaces Node.ParseLabels (nhd/Node.py:468-487: InitGroups :312, InitMaintenance :324, InitCores :328,
+ * InitNics :378, InitGpus :428, InitMisc :440) + Node.SetHugepages (:489-493) for a node the scheduler has
+ * just discovered (nhd/NHDScheduler.py:122-140), and the packing of the resulting Node object.
+ * An nhd_ingest holds the two cluster-wide dictionaries the records refer to: node-group names -> bits of
+ * group_mask, NIC link speeds -> speed classes (= nhd_params.speed_gbps).  What the placement loop does not
+ * need (interface names, MACs, the gateway string) stays with the caller, addressed by label position. */
+typedef struct nhd_ingest nhd_ingest;
+
+typedef struct nhd_node_aux {
+    int32_t data_vlan;                     /* DATA_PLANE_VLAN                (Node.py:441-446)   */
+    int32_t res_hugepages_gb;              /* RES_HUGEPAGES_GB, 0 if absent  (Node.py:451-453)   */
+    int32_t n_reserved_cores;              /* len(Node.reserved_cores)       (Node.py:368-371)   */
+    int32_t gw_label;                      /* index of the DATA_DEFAULT_GW label                  */
+    int32_t gpu_device_id[NHD_MAX_GPUS];   /* Node.gpus[i].device_id, -1 beyond n_gpus            */
+    int32_t nic_label[NHD_MAX_NICS];       /* index of the label Node.nics[i] came from, -1 beyond n_nics */
+} nhd_node_aux;
+
+int32_t nhd_ingest_create(nhd_ingest** out);
+int32_t nhd_ingest_destroy(nhd_ingest* g);
+/* keys / values: the node's labels in dictionary order (NIC / GPU list order follows label order).
+ * NHD_ERR_LABELS: the reference's ParseLabels returns False; NHD_ERR_INVALID: it would raise;
+ * NHD_ERR_UNSUPPORTED: beyond NHD_MAX_*.  aux may be NULL. */
+int32_t nhd_ingest_node(nhd_ingest* g, int32_t n_labels, const char* const* keys, const char* const* values,
+                        int32_t active, int32_t hugepages_alloc_gb, int32_t hugepages_free_gb,
+                        nhd_node_rec* rec, nhd_node_aux* aux);
+/* '.'-joined group names (the NHD_GROUP label / pod group annotation) -> group_mask bits */
+int32_t nhd_ingest_group_mask(nhd_ingest* g, const char* dotted_names, int32_t create, uint64_t* mask);
+/* speed classes seen so far, for nhd_params.speed_gbps */
+int32_t nhd_ingest_speed_table(const nhd_ingest* g, double out[NHD_MAX_SPEED_CLASSES], int32_t* n_classes);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,9 @@ EXPORTS = ('nhd_default_params', 'nhd_nccl_unique_id', 'nhd_create', 'nhd_destro
            'nhd_validate_node', 'nhd_validate_pod', 'nhd_load_nodes', 'nhd_update_nodes', 'nhd_read_nodes',
            'nhd_snapshot', 'nhd_restore', 'nhd_solve_batch', 'nhd_stage_batch', 'nhd_solve_staged',
            'nhd_fetch_bindings', 'nhd_sync', 'nhd_run_filter_only', 'nhd_last_timing', 'nhd_read_filter',
-           'nhd_debug_counters', 'nhd_alloc_pinned', 'nhd_free_pinned')
+           'nhd_debug_counters', 'nhd_alloc_pinned', 'nhd_free_pinned',
+           'nhd_ingest_create', 'nhd_ingest_destroy', 'nhd_ingest_node', 'nhd_ingest_group_mask',
+           'nhd_ingest_speed_table')
 
 
 class Params(ctypes.Structure):
@@ -65,6 +67,11 @@ def load():
         'nhd_debug_counters': (i32, [vp, vp]),
         'nhd_alloc_pinned': (i32, [ctypes.c_uint64, ctypes.POINTER(vp)]),
         'nhd_free_pinned': (i32, [vp]),
+        'nhd_ingest_create': (i32, [ctypes.POINTER(vp)]),
+        'nhd_ingest_destroy': (i32, [vp]),
+        'nhd_ingest_node': (i32, [vp, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), i32, i32, i32, vp, vp]),
+        'nhd_ingest_group_mask': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(ctypes.c_uint64)]),
+        'nhd_ingest_speed_table': (i32, [vp, vp, ctypes.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnhd_b200.so')
-SOURCES = [os.path.join(CSRC, 'nhd_api.cu')]
+SOURCES = [os.path.join(CSRC, 'nhd_api.cu'), os.path.join(CSRC, 'nhd_ingest.cpp')]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('nhd_kernels.cuh', 'nhd_core.cuh')] + \
     [os.path.join(HERE, '..', 'include', 'nhd_b200.h')]
 

@@ -1,0 +1,93 @@
+"""Node ingest through the library: NFD label dictionaries -> packed ``nhd_node_rec`` records.
+
+The native counterpart of ``Node.ParseLabels`` + ``Node.SetHugepages`` (``nhd/Node.py:468-493``) followed
+by ``packing.pack_node``: a cluster can be uploaded (``Solver.load_nodes`` / ``update_nodes``) straight from
+the labels the K8s API returns, without building ``Node`` objects first.  The parsing lives in
+``csrc/nhd_ingest.cpp`` (C-ABI ``nhd_ingest_*``, ``include/nhd_b200.h``); this module only marshals.
+"""
+import ctypes
+from typing import Dict, Iterable, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from nhd_b200 import _lib, wire
+
+
+class LabelError(ValueError):
+    """``code`` is the library status: ``wire.ERR_LABELS`` where the reference's ``ParseLabels`` returns
+    False (the scheduler ignores the node), ``wire.ERR_INVALID`` where it would raise, ``wire.ERR_UNSUPPORTED``
+    beyond the packed layout's limits."""
+
+    def __init__(self, code: int, name: str = ''):
+        super().__init__(f'node {name!r}: label ingest failed with status {code}')
+        self.code = code
+
+
+class LabelIngest:
+    """Holds the cluster-wide dictionaries the packed records refer to (node-group names -> ``group_mask``
+    bits, NIC speeds -> speed classes), like ``packing.ClusterLayout`` does for objects."""
+
+    def __init__(self):
+        self._L = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._L.nhd_ingest_create(ctypes.byref(h))
+        if rc != wire.OK:
+            raise RuntimeError(f'nhd_ingest_create failed: {rc}')
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.nhd_ingest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def node(self, labels: Mapping[str, str], active: bool = True, hugepages_alloc_gb: int = 0,
+             hugepages_free_gb: int = 0, name: str = '', out=None) -> Tuple[np.ndarray, np.ndarray]:
+        """One node: ``(nhd_node_rec, nhd_node_aux)``.  ``labels`` in dictionary order; ``out``: a one-element
+        slice of a record array to fill in place."""
+        n = len(labels)
+        keys = (ctypes.c_char_p * n)(*[k.encode() for k in labels.keys()])
+        vals = (ctypes.c_char_p * n)(*[str(v).encode() for v in labels.values()])
+        rec = np.zeros((), dtype=wire.NODE_DTYPE) if out is None else out
+        aux = np.zeros((), dtype=wire.NODE_AUX_DTYPE)
+        rc = self._L.nhd_ingest_node(self._h, n, keys, vals, int(bool(active)), int(hugepages_alloc_gb),
+                                     int(hugepages_free_gb), rec.ctypes.data, aux.ctypes.data)
+        if rc != wire.OK:
+            raise LabelError(rc, name)
+        return rec, aux
+
+    def nodes(self, items: Sequence[Tuple[Mapping[str, str], bool, int, int]], skip_rejected: bool = False):
+        """Many nodes: ``items`` = ``(labels, active, hugepages_alloc_gb, hugepages_free_gb)``.  Returns the
+        records (and the positions kept when ``skip_rejected`` drops the nodes ``ParseLabels`` would refuse,
+        as ``NHDScheduler.BuildInitialNodeList`` does)."""
+        recs = np.zeros(len(items), dtype=wire.NODE_DTYPE)
+        kept = []
+        for i, (labels, active, alloc, free) in enumerate(items):
+            try:
+                self.node(labels, active, alloc, free, name=str(i), out=recs[len(kept):len(kept) + 1])
+            except LabelError as e:
+                if skip_rejected and e.code == wire.ERR_LABELS:
+                    continue
+                raise
+            kept.append(i)
+        return recs[:len(kept)], kept
+
+    def group_mask(self, names: Iterable[str], create: bool = False) -> int:
+        m = ctypes.c_uint64(0)
+        rc = self._L.nhd_ingest_group_mask(self._h, '.'.join(names).encode(), int(create), ctypes.byref(m))
+        if rc != wire.OK:
+            raise LabelError(rc)
+        return int(m.value)
+
+    def speed_table(self) -> np.ndarray:
+        t = np.zeros(wire.MAX_SPEED_CLASSES, dtype='<f8')
+        n = ctypes.c_int32(0)
+        rc = self._L.nhd_ingest_speed_table(self._h, t.ctypes.data, ctypes.byref(n))
+        if rc != wire.OK:
+            raise RuntimeError(f'nhd_ingest_speed_table failed: {rc}')
+        return t

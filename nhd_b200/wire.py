@@ -12,6 +12,10 @@ MAX_SPEED_CLASSES = 16
 MAX_GROUP_GPUS = 8
 MAX_POD_GPUS = 16
 MAX_POD_CORES = 72
+MAX_GROUP_NAMES = 64
+
+# error codes (include/nhd_b200.h)
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_LABELS = 0, -1, -2, -3, -4, -5, -6
 
 # nhd_binding.status
 PLACED, NO_CANDIDATE, ASSIGN_FAILED, REF_WOULD_CRASH, BAD_MAP_TYPE = 0, 1, 2, 3, 4
@@ -60,3 +64,10 @@ BINDING_DTYPE = np.dtype([
     ('cores', 'u1', (MAX_POD_CORES,)),
 ], align=False)
 assert BINDING_DTYPE.itemsize == 128
+
+# nhd_node_aux: what nhd_ingest_node reads from the labels besides the packed record
+NODE_AUX_DTYPE = np.dtype([
+    ('data_vlan', '<i4'), ('res_hugepages_gb', '<i4'), ('n_reserved_cores', '<i4'), ('gw_label', '<i4'),
+    ('gpu_device_id', '<i4', (MAX_GPUS,)), ('nic_label', '<i4', (MAX_NICS,)),
+])
+assert NODE_AUX_DTYPE.itemsize == 16 + 4 * MAX_GPUS + 4 * MAX_NICS

@@ -1,0 +1,144 @@
+"""Node ingest: the library's label parser (`nhd_ingest_node`, csrc/nhd_ingest.cpp) must give
+the records `packing.pack_node` makes of a Node that went through the reference's `Node.ParseLabels` +
+`SetHugepages` (nhd/Node.py:468-493), byte for byte, and fail where and how the reference fails."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from nhd_b200 import Node as mirror_node
+from nhd_b200 import packing, wire
+from nhd_b200.ingest import LabelError, LabelIngest
+from tests import conftest, scenarios
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ingest', 'cases.json')
+
+
+def _native(ing, case):
+    """-> ('ok', rec, aux) | ('false'|'raises'|'unsupported', None, None)"""
+    try:
+        rec, aux = ing.node(case['labels'], case['active'], case['hp_alloc'], case['hp_free'], name=case['name'])
+    except LabelError as e:
+        kind = {wire.ERR_LABELS: 'false', wire.ERR_INVALID: 'raises', wire.ERR_UNSUPPORTED: 'unsupported'}[e.code]
+        return kind, None, None
+    return 'ok', rec, aux
+
+
+def _object_path(node_mod, case, layout):
+    """the same through Node objects (reference's or the mirror's) and pack_node"""
+    n = node_mod.Node(case['name'], case['active'])
+    try:
+        ok = n.ParseLabels(case['labels'])
+    except Exception:                                            # noqa: BLE001
+        return 'raises', None, None
+    if not ok:
+        return 'false', None, None
+    n.SetHugepages(case['hp_alloc'], case['hp_free'])
+    try:
+        rec = packing.pack_node(n, layout)
+    except packing.UnsupportedError:
+        return 'unsupported', None, None
+    return 'ok', rec, n
+
+
+def _check_aux(case, rec, aux, n):
+    assert int(aux['data_vlan']) == n.data_vlan
+    assert int(aux['res_hugepages_gb']) == n.mem.res_hugepages_gb
+    assert int(aux['n_reserved_cores']) == len(n.reserved_cores)
+    assert aux['gpu_device_id'][:len(n.gpus)].tolist() == [g.device_id for g in n.gpus]
+    assert (aux['gpu_device_id'][len(n.gpus):] == -1).all()
+    keys = list(case['labels'].keys())
+    assert [keys[i].split('.')[4] for i in aux['nic_label'][:len(n.nics)]] == [x.ifname for x in n.nics]
+    assert keys[int(aux['gw_label'])] == 'DATA_DEFAULT_GW'
+
+
+def test_golden_cases_from_the_reference():
+    """Frozen outcomes of the unmodified reference (tests/golden/make_ingest_golden.py), one cluster dictionary
+    across all cases: group bits and speed classes must come out in the same order too."""
+    g = json.load(open(GOLDEN))
+    ing = LabelIngest()
+    seen = {'ok': 0, 'false': 0, 'raises': 0, 'unsupported': 0}
+    for case in g['cases']:
+        exp = case['expect']
+        want = exp['parse'] if exp['parse'] != 'ok' else ('unsupported' if exp['record'] == 'unsupported' else 'ok')
+        kind, rec, aux = _native(ing, case)
+        assert kind == want, (case['name'], kind, want)
+        seen[kind] += 1
+        if kind == 'ok':
+            assert rec.tobytes().hex() == exp['record'], case['name']
+            assert int(aux['data_vlan']) == exp['data_vlan']
+            assert int(aux['res_hugepages_gb']) == exp['res_hugepages_gb']
+            assert int(aux['n_reserved_cores']) == exp['n_reserved_cores']
+            assert aux['gpu_device_id'][:int(rec['n_gpus'])].tolist() == exp['gpu_device_id']
+            keys = list(case['labels'].keys())
+            assert [keys[i].split('.')[4] for i in aux['nic_label'][:int(rec['n_nics'])]] == exp['nic_ifname']
+    assert min(seen.values()) >= 10, seen
+    assert ing.speed_table().tolist() == g['speed_table']
+    for name, bit in g['group_bits'].items():
+        assert ing.group_mask([name]) == 1 << bit
+    ing.close()
+
+
+@pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
+def test_native_ingest_matches_mirror_objects(flavor):
+    ing, layout = LabelIngest(), packing.ClusterLayout()
+    n_ok = 0
+    for seed in range(12):
+        scn = scenarios.random_scenario(33000 + seed * 7 + len(flavor), n_nodes=9, n_pods=1, flavor=flavor)
+        for nd in scn['nodes']:
+            case = {'name': nd['name'], 'labels': nd['labels'], 'active': nd.get('active', True),
+                    'hp_alloc': nd['hp_alloc'], 'hp_free': nd['hp_free']}
+            kind, rec, aux = _native(ing, case)
+            okind, orec, n = _object_path(mirror_node, case, layout)
+            assert kind == okind, (seed, nd['name'])
+            if kind == 'ok':
+                assert rec.tobytes() == orec.tobytes(), (seed, nd['name'])
+                _check_aux(case, rec, aux, n)
+                n_ok += 1
+    assert n_ok > 80
+    assert ing.speed_table().tolist() == layout.speed_table().tolist()
+    assert all(ing.group_mask([g]) == 1 << b for g, b in layout.group_bits.items())
+
+
+def test_batch_ingest_feeds_the_record_validator():
+    """nodes(): rejected nodes are skipped like BuildInitialNodeList does, the rest pass nhd_validate_node."""
+    from nhd_b200 import _lib
+    L = _lib.load()
+    scn = scenarios.random_scenario(4242, n_nodes=20, n_pods=1, flavor='mixed')
+    items = [(nd['labels'], nd.get('active', True), nd['hp_alloc'], nd['hp_free']) for nd in scn['nodes']]
+    broken = dict(items[3][0])
+    del broken['DATA_PLANE_VLAN']
+    items[3] = (broken,) + items[3][1:]
+    ing = LabelIngest()
+    recs, kept = ing.nodes(items, skip_rejected=True)
+    assert kept == [i for i in range(20) if i != 3] and len(recs) == 19
+    for i in range(len(recs)):
+        assert L.nhd_validate_node(recs[i:i + 1].ctypes.data) == 0
+    with pytest.raises(LabelError):
+        ing.nodes(items, skip_rejected=False)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not conftest.has_reference(), reason='reference not present on this machine')
+def test_fuzzed_labels_against_the_live_reference():
+    """Seeded damage to valid label dictionaries: the native parser and the unmodified reference must agree on
+    accept / return False / raise / beyond-limits, and on every byte of the accepted records."""
+    from oracle import ref_loader
+    from tests.golden import make_ingest_golden as mk
+    ref = ref_loader.load()
+    rng = random.Random(5)
+    cases = mk.mutations(rng, 400)
+    ing, layout = LabelIngest(), packing.ClusterLayout()
+    kinds = {}
+    for case in cases:
+        kind, rec, aux = _native(ing, case)
+        okind, orec, n = _object_path(ref.node, case, layout)
+        assert kind == okind, (case['name'], kind, okind, case['labels'])
+        kinds[kind] = kinds.get(kind, 0) + 1
+        if kind == 'ok':
+            assert rec.tobytes() == orec.tobytes(), case['name']
+            _check_aux(case, rec, aux, n)
+    assert kinds.get('ok', 0) > 100 and kinds.get('raises', 0) > 10 and kinds.get('false', 0) > 5, kinds
+    assert ing.speed_table().tolist() == layout.speed_table().tolist()

@@ -284,6 +284,25 @@ int32_t nhd_ingest_group_mask(nhd_ingest* g, const char* dotted_names, int32_t c
 /* speed classes seen so far, for nhd_params.speed_gbps */
 int32_t nhd_ingest_speed_table(const nhd_ingest* g, double out[NHD_MAX_SPEED_CLASSES], int32_t* n_classes);
 
+/* ---- node statistics from packed records (host side) ------------------------------------------
+ * What NHDScheduler.GetBasicNodeStats (nhd/NHDScheduler.py:355-378) reads off a Node, for records that came
+ * back from the device mirror (nhd_read_nodes): the counters the packed state carries.  totalhuge_gb,
+ * totalpods and the per-NIC used speeds are not part of the placement state and stay with the caller. */
+typedef struct nhd_node_stats {
+    int32_t freegpu;                       /* Node.GetFreeGpuCount()      (Node.py:235-237) */
+    int32_t totalgpu;                      /* Node.GetTotalGPUs()         (Node.py:239-241) */
+    int32_t freecpu;                       /* Node.GetFreeCpuCoreCount(): logical cores, with SMT only those whose
+                                            * sibling is free too         (Node.py:225-233) */
+    int32_t totalcpu;                      /* Node.GetTotalCPUs() = len(Node.cores)         (Node.py:243-245) */
+    int32_t freehuge_gb;                   /* Node.GetFreeHugepages()     (Node.py:171-173) */
+    int32_t active;                        /* Node.GetNodeActive()        (Node.py:163-165) */
+    int32_t maintenance;
+    int32_t nics_in_use;                   /* NICs with pods_used > 0 */
+    int32_t free_cores_numa[NHD_MAX_NUMA]; /* Node.GetFreeCpuCores(): free physical cores per NUMA node (Node.py:250-264) */
+    int32_t free_gpus_numa[NHD_MAX_NUMA];  /* Node.GetFreeNumaGPUs()      (Node.py:456-462) */
+} nhd_node_stats;
+int32_t nhd_node_stats_from_records(int32_t n, const nhd_node_rec* recs, nhd_node_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

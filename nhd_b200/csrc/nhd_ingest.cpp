@@ -305,4 +305,41 @@ int32_t nhd_ingest_node(nhd_ingest* g, int32_t n_labels, const char* const* keys
     return NHD_OK;
 }
 
+/* ---- statistics off packed records (NHDScheduler.GetBasicNodeStats, nhd/NHDScheduler.py:355-378) ---- */
+int32_t nhd_node_stats_from_records(int32_t n, const nhd_node_rec* recs, nhd_node_stats* out)
+{
+    if (n < 0 || (n && (!recs || !out))) return NHD_ERR_INVALID;
+    for (int32_t i = 0; i < n; i++) {
+        const nhd_node_rec& r = recs[i];
+        nhd_node_stats s;
+        std::memset(&s, 0, sizeof s);
+        const bool smt = (r.flags & NHD_NODE_SMT) != 0;
+        const int phys = r.phys_cores, K = r.n_numa;
+        if (K < 1 || K > NHD_MAX_NUMA || phys <= 0 || phys % K || (smt ? 2 : 1) * phys > NHD_MAX_LCORES) return NHD_ERR_INVALID;
+        const int per = phys / K;
+        auto used = [&](int c) { return (r.used[c >> 6] >> (c & 63)) & 1ULL; };
+        for (int c = 0; c < phys; c++) {
+            /* Node.py:250-264: a physical core counts when it and (with SMT) its sibling are unused */
+            const bool free_pair = !used(c) && (!smt || !used(c + phys));
+            if (free_pair) s.free_cores_numa[c / per]++;
+            /* Node.py:225-233: every logical core whose own and sibling's flags are clear */
+            if (smt) { if (free_pair) s.freecpu += 2; }
+            else if (!used(c)) s.freecpu += 1;
+        }
+        s.totalcpu = smt ? 2 * phys : phys;
+        s.totalgpu = r.n_gpus;
+        for (int g = 0; g < r.n_gpus; g++)
+            if (!((r.gpu_used >> g) & 1)) {
+                s.freegpu++;
+                for (int k = 0; k < K; k++) if ((r.gpu_numa_mask[k] >> g) & 1) s.free_gpus_numa[k]++;
+            }
+        s.freehuge_gb = r.free_hugepages_gb;
+        s.active = (r.flags & NHD_NODE_ACTIVE) ? 1 : 0;
+        s.maintenance = (r.flags & NHD_NODE_MAINTENANCE) ? 1 : 0;
+        s.nics_in_use = __builtin_popcount(r.nic_inuse & (r.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << r.n_nics) - 1)));
+        out[i] = s;
+    }
+    return NHD_OK;
+}
+
 }  // extern "C"

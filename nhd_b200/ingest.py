@@ -91,3 +91,14 @@ class LabelIngest:
         if rc != wire.OK:
             raise RuntimeError(f'nhd_ingest_speed_table failed: {rc}')
         return t
+
+
+def node_stats(recs: np.ndarray) -> np.ndarray:
+    """``NHDScheduler.GetBasicNodeStats`` counters (``nhd/NHDScheduler.py:355-378``) of packed records, e.g. of
+    ``Solver.read_nodes()``: one ``wire.NODE_STATS_DTYPE`` row per record."""
+    recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE).reshape(-1)
+    out = np.zeros(len(recs), dtype=wire.NODE_STATS_DTYPE)
+    rc = _lib.load().nhd_node_stats_from_records(len(recs), recs.ctypes.data, out.ctypes.data)
+    if rc != wire.OK:
+        raise ValueError(f'nhd_node_stats_from_records failed: {rc}')
+    return out

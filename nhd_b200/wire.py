@@ -71,3 +71,11 @@ NODE_AUX_DTYPE = np.dtype([
     ('gpu_device_id', '<i4', (MAX_GPUS,)), ('nic_label', '<i4', (MAX_NICS,)),
 ])
 assert NODE_AUX_DTYPE.itemsize == 16 + 4 * MAX_GPUS + 4 * MAX_NICS
+
+# nhd_node_stats: GetBasicNodeStats counters of one packed record
+NODE_STATS_DTYPE = np.dtype([
+    ('freegpu', '<i4'), ('totalgpu', '<i4'), ('freecpu', '<i4'), ('totalcpu', '<i4'), ('freehuge_gb', '<i4'),
+    ('active', '<i4'), ('maintenance', '<i4'), ('nics_in_use', '<i4'),
+    ('free_cores_numa', '<i4', (MAX_NUMA,)), ('free_gpus_numa', '<i4', (MAX_NUMA,)),
+])
+assert NODE_STATS_DTYPE.itemsize == 64

@@ -142,3 +142,81 @@ def test_fuzzed_labels_against_the_live_reference():
             _check_aux(case, rec, aux, n)
     assert kinds.get('ok', 0) > 100 and kinds.get('raises', 0) > 10 and kinds.get('false', 0) > 5, kinds
     assert ing.speed_table().tolist() == layout.speed_table().tolist()
+
+
+# ---- node statistics off packed records (the part the packed state carries) -------------
+def _stats_of_objects(nodes):
+    rows = []
+    for n in nodes:
+        rows.append({'freegpu': n.GetFreeGpuCount(), 'totalgpu': n.GetTotalGPUs(), 'freecpu': n.GetFreeCpuCoreCount(),
+                     'totalcpu': n.GetTotalCPUs(), 'freehuge_gb': n.GetFreeHugepages(), 'active': int(bool(n.GetNodeActive())),
+                     # the per-NUMA counts are hot-path functions (a8 / a9): the reference has them, the mirror
+                     # leaves them to the device
+                     'free_cores_numa': list(n.GetFreeCpuCores()) if hasattr(n, 'GetFreeCpuCores') else None,
+                     'free_gpus_numa': list(n.GetFreeNumaGPUs()) if hasattr(n, 'GetFreeNumaGPUs') else None,
+                     'nics_in_use': sum(1 for x in n.nics if x.pods_used > 0)})
+    return rows
+
+
+def _check_stats(recs, rows):
+    from nhd_b200.ingest import node_stats
+    st = node_stats(recs)
+    assert len(st) == len(rows)
+    for s, r, rec in zip(st, rows, recs):
+        for k in ('freegpu', 'totalgpu', 'freecpu', 'totalcpu', 'freehuge_gb', 'active', 'nics_in_use'):
+            assert int(s[k]) == r[k], (k, int(s[k]), r[k])
+        if r['free_cores_numa'] is not None:
+            K = len(r['free_cores_numa'])
+            assert s['free_cores_numa'][:K].tolist() == r['free_cores_numa'] and (s['free_cores_numa'][K:] == 0).all()
+            assert s['free_gpus_numa'][:K].tolist() == r['free_gpus_numa']
+        else:
+            smt = int(rec['flags']) & wire.NODE_SMT
+            assert int(s['free_cores_numa'].sum()) * (2 if smt else 1) == r['freecpu']
+            assert int(s['free_gpus_numa'].sum()) == r['freegpu']
+
+
+@pytest.mark.parametrize('flavor', ['mixed', 'wild', 'vf', 'big'])
+def test_node_stats_match_mirror_getters_after_scheduling(oracle_lib, flavor):
+    """Schedule a scenario with the oracle, write the bindings into the mirror objects, then the counters of the
+    packed final records must be what the objects' getters report."""
+    from nhd_b200 import CfgTopology as mirror_cfg
+    from tests import ref_compare
+    for seed in range(6):
+        scn = scenarios.random_scenario(44000 + seed * 5 + len(flavor), n_nodes=8, n_pods=30, flavor=flavor)
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        bindings, final = oracle_lib.solve(recs, layout.speed_table(), pods, now)
+        nodes = scenarios.build_nodes(scn, mirror_node)
+        order = list(nodes.values())
+        for pod, b, t in zip(scn['pods'], bindings, now):
+            if int(b['node']) < 0:
+                continue
+            node = order[int(b['node'])]
+            node.busy_time = float(t)
+            if int(b['status']) == wire.PLACED:
+                top = scenarios.build_top(pod, mirror_cfg)
+                packing.apply_binding(node, top, b)
+                node.ClaimPodNICResources([int(x) for x in b['claimed_nics'][:int(b['n_claimed'])]])
+        assert packing.pack_nodes(order, layout).tobytes() == final.tobytes()
+        _check_stats(final, _stats_of_objects(order))
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not conftest.has_reference(), reason='reference not present on this machine')
+def test_node_stats_match_reference_getters_after_scheduling():
+    """Same against the unmodified reference: its own scheduler loop leaves Node objects behind whose getters
+    (what GetBasicNodeStats calls, nhd/NHDScheduler.py:355-378) must agree with the packed records' counters."""
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    import contextlib
+    import io
+    for seed, flavor in enumerate(['mixed', 'wild', 'vf', 'big', 'mixed', 'big']):
+        scn = scenarios.random_scenario(45000 + seed, n_nodes=8, n_pods=30, flavor=flavor)
+        nodes = scenarios.build_nodes(scn, ref.node)
+        matcher = ref.matcher.Matcher()
+        for pod, t in zip(scn['pods'], scn['now']):
+            top = scenarios.build_top(pod, ref.cfg)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref_loader.attempt_scheduling(ref, matcher, nodes, top, pod['groups'], t)
+        order = list(nodes.values())
+        recs = packing.pack_nodes(order, packing.ClusterLayout())
+        _check_stats(recs, _stats_of_objects(order))

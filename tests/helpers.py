@@ -44,3 +44,36 @@ def first_binding_diff(a, b):
             if n != 'pad_' and not np.array_equal(a[i][n], b[i][n]):
                 return f'pod {i} field {n}: {a[i][n]} != {b[i][n]}'
     return None
+
+
+class OracleSolver:
+    """Stand-in with ``nhd_b200.solver.Solver``'s interface whose batches are computed by the C oracle.
+    TEST INFRASTRUCTURE: lets the host-side scheduler logic (``nhd_b200.NHDScheduler``) run in the
+    ``-m "not gpu"`` suite, where no CUDA device exists; the GPU tests run the same scenarios through
+    the real ``Solver``.  Never used by the product."""
+
+    def __init__(self, speed_table, nic_bw_avail_percent=0.9, min_busy_secs=30.0, device=0):
+        from oracle import binding
+        self._oracle = binding
+        self._speed = np.ascontiguousarray(speed_table, dtype='<f8').copy()
+        self._bw, self._min_busy = nic_bw_avail_percent, min_busy_secs
+        self._recs = np.zeros(0, dtype=wire.NODE_DTYPE)
+        self.closed = False
+
+    def load_nodes(self, recs):
+        self._recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE).copy()
+
+    def update_nodes(self, idx, recs):
+        for i, r in zip(np.asarray(idx), np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE)):
+            self._recs[int(i)] = r
+
+    def read_nodes(self):
+        return self._recs.copy()
+
+    def solve_batch(self, pods, now):
+        out, final = self._oracle.solve(self._recs, self._speed, pods, now, self._bw, self._min_busy)
+        self._recs = final
+        return out
+
+    def close(self):
+        self.closed = True

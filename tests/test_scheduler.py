@@ -1,0 +1,147 @@
+"""SURVEY 8f row 1 — the scheduler loop around the hot path (``nhd_b200.NHDScheduler``): the pending
+set goes to the solver as one batch, and everything Kubernetes, ``pod_state`` and the ``Node``
+objects end up with must be what the UNMODIFIED reference ``nhd.NHDScheduler.run()`` leaves behind
+when it schedules the same pods one ``AttemptScheduling`` at a time.
+
+* live (build container, ``/root/reference`` present): random scripted sessions — pods appearing,
+  Kubernetes writes failing at every step the reference unwinds from, delete / create events,
+  cordon, maintenance, group changes, restarts, RPCs — played to both;
+* frozen: ``tests/golden/sched/*.json`` (made by ``tests/golden/make_sched_golden.py`` from the
+  reference), replayed here on CPU and, ``-m gpu``, through the CUDA solver on the B200 box.
+
+On CPU the solver behind ``DeviceCluster`` is ``tests.helpers.OracleSolver`` (the C oracle behind the
+``Solver`` interface, test infrastructure): these tests pin the *host* logic — batching, cutting a
+batch after an unwind, delta uploads; the placement arithmetic is pinned elsewhere.
+"""
+import glob
+import json
+import os
+
+import pytest
+
+from tests import helpers, sched_harness as H
+from tests.conftest import has_reference
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'sched', '*.json')))
+IDS = [os.path.basename(p)[:-5] for p in GOLDEN]
+
+
+def _load(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 8
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_scheduler_reproduces_reference_sessions(oracle_lib, path):
+    doc = _load(path)
+    stats = {}
+    got = H.run_mirror(doc['script'], solver_factory=helpers.OracleSolver, stats=stats)
+    assert H.first_difference(doc['expected'], got) is None
+    assert got == doc['expected']
+    assert stats['batches'] > 0 and stats['pods'] >= stats['batches']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_scheduler_cuda_reproduces_reference_sessions(path):
+    """The same sessions with the CUDA solver behind the scheduler (the product configuration)."""
+    doc = _load(path)
+    got = H.run_mirror(doc['script'])
+    assert H.first_difference(doc['expected'], got) is None
+    assert got == doc['expected']
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason='needs /root/reference (build container)')
+@pytest.mark.parametrize('flavor', ['mixed', 'vf', 'big'])
+def test_scheduler_matches_live_reference(oracle_lib, flavor):
+    checked = binds = 0
+    for seed in range(100, 112):
+        script = H.random_script(seed, flavor)
+        want = H.run_reference(script)
+        got = H.run_mirror(script, solver_factory=helpers.OracleSolver)
+        assert H.first_difference(want, got) is None, (seed, flavor)
+        checked += 1
+        binds += len(want['k8s']['binds'])
+    assert checked == 12 and binds > 100
+
+
+def test_pending_set_is_one_batch_and_unwinds_cut_it(oracle_lib):
+    """No failing write: the whole pending set is ONE solver call.  A write that fails before the
+    config annotation exists makes ``ReleasePodResources`` reset the cluster (``NHDScheduler.py:178-181``);
+    the batch is cut there and the rest solved again — and only then."""
+    from tests.golden.make_sched_golden import unwind_script
+    script = unwind_script()
+    clean = json.loads(json.dumps(script))
+    for st in clean['init']:
+        st['fail'] = []
+    clean['steps'] = []
+    stats = {}
+    doc = H.run_mirror(clean, solver_factory=helpers.OracleSolver, stats=stats)
+    assert stats['batches'] == 1 and stats['pods'] == len(clean['init']) and stats['full_loads'] == 1
+    assert len(doc['k8s']['binds']) > 8
+
+    script['steps'] = []
+    stats = {}
+    H.run_mirror(script, solver_factory=helpers.OracleSolver, stats=stats)
+    # cuts: nad, gpumap, annotate (each resets); bind leaks and podobj / cfg never reach the solver
+    assert stats['batches'] == 4, stats
+    assert stats['pods'] > 12
+
+
+def test_delta_uploads_only_touch_changed_nodes(oracle_lib):
+    """Between batches only the nodes the host changed are re-sent (``nhd_update_nodes``)."""
+    from nhd_b200.NHDScheduler import NHDScheduler
+    import nhd_b200.CfgTopology as cfg_mod
+    from tests import fake_k8s, scenarios
+    nodes = [scenarios.make_node(f'n{i}', 2, 16, True, 1, nics=[('eth0', 100000, 0, 0x10), ('eth1', 100000, 1, 0x20)])
+             for i in range(12)]
+    k8s = fake_k8s.FakeK8s(nodes)
+    clock = H.Clock(1000.0)
+    s = NHDScheduler(k8s, lambda t, c: fake_k8s.JsonCfgParser(c, cfg_mod), solver_factory=helpers.OracleSolver,
+                     clock=clock)
+    pod = scenarios.make_pod([scenarios.make_group(pairs=((10, 10),), workers=1)], misc=1, hugepages=1)
+    for i in range(5):
+        k8s.add_pod('a', f'p{i}', pod, uid=f'u{i}')
+    s.Startup()
+    assert (s.cluster.full_loads, s.cluster.delta_nodes, s.cluster.batches) == (1, 0, 1)
+    assert len(k8s.binds) == 5
+    s.HandleWatchItem({'type': 'NHD_WATCH_TYPE_NODE_CORDON', 'node': 'n0'})
+    s.HandleWatchItem({'type': 'NHD_WATCH_TYPE_NODE_CORDON', 'node': 'n0'})           # no change, no upload
+    s.HandleWatchItem({'type': 'NHD_WATCH_TYPE_TRIAD_POD_DELETE', 'pod': {'ns': 'a', 'name': 'p1', 'uid': 'u1'}})
+    k8s.add_pod('a', 'late', pod, uid='u9')
+    s.CheckPendingPods()
+    assert s.cluster.full_loads == 1 and s.cluster.batches == 2
+    assert 1 <= s.cluster.delta_nodes <= 2          # n0 (cordon) and the node p1 ran on (may be n0)
+    # the device copy equals the objects
+    from nhd_b200 import packing
+    want = packing.pack_nodes(list(s.nodes.values()), s.cluster.layout)
+    assert s.cluster.read_records().tobytes() == want.tobytes()
+    row = {r['name']: r for r in s.GetBasicNodeStats()}
+    assert row['n0']['active'] is False
+    s.close()
+
+
+def test_scheduler_has_no_cpu_placement_path():
+    """Without a CUDA device the default solver factory must raise, not fall back."""
+    from nhd_b200 import _lib
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip('a GPU is present')
+    except ImportError:
+        pass
+    from nhd_b200.NHDScheduler import NHDScheduler
+    from nhd_b200.solver import SolverError
+    import nhd_b200.CfgTopology as cfg_mod
+    from tests import fake_k8s, scenarios
+    _lib.load()
+    k8s = fake_k8s.FakeK8s([scenarios.make_node('n0', nics=[('eth0', 100000, 0, 0x10), ('eth1', 100000, 1, 0x20)])])
+    k8s.add_pod('a', 'p', scenarios.make_pod([scenarios.make_group()]))
+    s = NHDScheduler(k8s, lambda t, c: fake_k8s.JsonCfgParser(c, cfg_mod))
+    with pytest.raises(SolverError):
+        s.Startup()

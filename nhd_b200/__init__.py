@@ -4,6 +4,7 @@ Layout:
   csrc/            CUDA kernels (sm_100a) and the C-ABI library (include/nhd_b200.h)
   _lib, solver     ctypes binding and handle wrapper
   wire, packing    packed record formats and object <-> record conversion
-  CfgTopology, Node, Matcher   host-side mirrors of the reference interface
+  CfgTopology, Node, Matcher, NHDScheduler   host-side mirrors of the reference interface
+  ingest           native node-label ingest and node statistics
 """
-__all__ = ['CfgTopology', 'Node', 'Matcher', 'packing', 'wire', 'solver']
+__all__ = ['CfgTopology', 'Node', 'Matcher', 'NHDScheduler', 'packing', 'wire', 'solver', 'ingest']

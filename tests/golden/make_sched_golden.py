@@ -48,13 +48,14 @@ def unwind_script():
 def main():
     os.makedirs(OUT, exist_ok=True)
     cases = [('unwind_every_step', unwind_script())]
-    for seed, flavor in ((1, 'mixed'), (2, 'mixed'), (5, 'mixed'), (3, 'vf'), (7, 'vf'), (4, 'big'), (9, 'big')):
+    for seed, flavor in ((1, 'mixed'), (2, 'mixed'), (5, 'mixed'), (3, 'vf'), (7, 'vf'), (4, 'big'), (9, 'big'),
+                         (6, 'wild'), (11, 'wild')):
         cases.append((f'random{seed}_{flavor}', H.random_script(seed, flavor)))
     for name, script in cases:
         doc = {'generator': 'tests/golden/make_sched_golden.py', 'source': 'unmodified nhd.NHDScheduler.run()',
                'script': script, 'expected': H.run_reference(script)}
         with open(os.path.join(OUT, name + '.json'), 'w') as f:
-            json.dump(doc, f, separators=(',', ':'), sort_keys=True)
+            json.dump(doc, f, separators=(',', ':'))      # key order is data: NIC / GPU order follows label order
         print(name, 'binds', len(doc['expected']['k8s']['binds']),
               'failed_schedule_count', doc['expected']['failed_schedule_count'])
 

@@ -32,7 +32,7 @@ def _load(path):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 8
+    assert len(GOLDEN) >= 10
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=IDS)
@@ -57,7 +57,7 @@ def test_scheduler_cuda_reproduces_reference_sessions(path):
 
 @pytest.mark.reference
 @pytest.mark.skipif(not has_reference(), reason='needs /root/reference (build container)')
-@pytest.mark.parametrize('flavor', ['mixed', 'vf', 'big'])
+@pytest.mark.parametrize('flavor', ['mixed', 'vf', 'big', 'wild'])
 def test_scheduler_matches_live_reference(oracle_lib, flavor):
     checked = binds = 0
     for seed in range(100, 112):

@@ -100,6 +100,7 @@ class Matcher:
         nows = np.full(n, now, dtype='<f8') if np.isscalar(now) else np.asarray(now, dtype='<f8')
         bindings = solver.solve_batch(pods, nows)
         results = []
+        failed = set()
         for i, (top, b) in enumerate(zip(tops, bindings)):
             if int(b['node']) < 0:
                 results.append((None,))
@@ -113,4 +114,10 @@ class Matcher:
                 if int(b['status']) == wire.PLACED:
                     packing.apply_binding(node, top, b)                          # SetPhysicalIdsFromMapping
                     node.ClaimPodNICResources([int(x) for x in b['claimed_nics'][:int(b['n_claimed'])]])
+                else:
+                    failed.add(int(b['node']))
+        # a failed assignment gives cores and GPUs back but not the hugepages taken before the last step
+        # (Node.py:794-796 vs :825-837); the solver's records hold the nodes as the reference leaves them
+        for idx in failed:
+            nodes[idx].mem.free_hugepages_gb = int(solver.read_nodes(idx, 1)[0]['free_hugepages_gb'])
         return results

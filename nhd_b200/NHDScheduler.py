@@ -104,6 +104,8 @@ class DeviceCluster:
         self.full_loads = 0
         self.delta_nodes = 0
         self.batches = 0
+        self.rewinds = 0
+        self._last = None
 
     @property
     def layout(self):
@@ -173,10 +175,23 @@ class DeviceCluster:
         for i, top in enumerate(tops):
             packing.pack_pod(top, pod_groups[i], self._layout, out=pods[i])
         self.batches += 1
-        return self._solver.solve_batch(pods, np.full(len(tops), now, dtype='<f8'))
+        self._solver.snapshot()                       # so that rewind() can step back inside this batch
+        self._last = (pods, np.full(len(tops), now, dtype='<f8'))
+        return self._solver.solve_batch(*self._last)
+
+    def rewind(self, k: int):
+        """Put the device back to the state right after pod ``k`` of the last batch (restore the
+        snapshot taken before it, solve pods ``0..k`` again: the solver is deterministic)."""
+        pods, now = self._last
+        self._solver.restore()
+        self._solver.solve_batch(pods[:k + 1], now[:k + 1])
+        self.rewinds += 1
 
     def read_records(self):
         return self._solver.read_nodes()
+
+    def read_record(self, index: int):
+        return self._solver.read_nodes(index, 1)[0]
 
     def name_of(self, index: int) -> str:
         return self._names[index]
@@ -209,6 +224,7 @@ class NHDScheduler:
         self._dirty = set()
         self._log = logger
         self.pods_solved = 0
+        self.assign_failed_nodes = set()
 
     # ---- small helpers --------------------------------------------------------------------
     def _info(self, msg):
@@ -367,8 +383,15 @@ class NHDScheduler:
             packing.apply_binding(node, top, binding)                         # SetPhysicalIdsFromMapping (:292)
         except IndexError:
             self._error('Failed to map physical resources from topology config!')
-            if int(binding['status']) == wire.REF_WOULD_CRASH:
-                self._touch(nodename)       # the reference's thread would be dead; carry on from the host's state
+            # The reference's unwind (Node.py:825-837) gives cores and GPUs back but never the hugepages it
+            # took at :794-796 (a failure at the last step, the top-level misc cores); the solver's record
+            # holds the node as the reference leaves it.  Its NIC part indexes self.nics with a *speed* and
+            # stops at the first entry (IndexError again, or a TypeError that ends the reference's thread:
+            # status REF_WOULD_CRASH), leaving the Gb/s it had added in NodeNic.speed_used: that residue of a
+            # statistic is not reproduced, the node is remembered in assign_failed_nodes instead.
+            rec = self.cluster.read_record(int(binding['node']))
+            node.mem.free_hugepages_gb = int(rec['free_hugepages_gb'])
+            self.assign_failed_nodes.add(nodename)
             return False
         nidx = [int(x) for x in binding['claimed_nics'][:int(binding['n_claimed'])]]   # list({x[0] ...}) (:302)
         node.ClaimPodNICResources(nidx)
@@ -435,9 +458,16 @@ class NHDScheduler:
                 bindings = {e.pos: out[i] for i, e in enumerate(solvable)}
             cut = None
             for e in run:
-                results[e.key] = ok = self._finish(e, bindings.get(e.pos), now)
+                b = bindings.get(e.pos)
+                rewound = False
+                if b is not None and int(b['status']) in (wire.ASSIGN_FAILED, wire.REF_WOULD_CRASH):
+                    # what a failed assignment leaves on its node is read back from the solver (see _finish);
+                    # for that the device must stand right after this pod, not at the end of the batch
+                    self.cluster.rewind(solvable.index(e))
+                    rewound = True
+                results[e.key] = ok = self._finish(e, b, now)
                 self._record(e.key, ok)
-                if self._dirty:                       # the unwind changed nodes behind the solver's back
+                if self._dirty or rewound:            # nodes changed behind the solver's back / device rewound
                     cut = e
                     break
             if cut is None:

@@ -3,8 +3,9 @@
 TEST INFRASTRUCTURE ONLY (oracle), build container only — same rules as ref_loader.py.
 
 ``nhd.NHDScheduler`` imports ``kubernetes`` (through ``nhd.K8SMgr``), ``libconf`` and
-``magicattr`` (through ``nhd.TriadCfgParser``), none of which exist here.  They are
-only *imported* on the path we drive — ``CheckPendingPods`` / ``AttemptScheduling`` /
+``magicattr`` (through ``nhd.TriadCfgParser``), none of which exist here.  The last two
+are restated under ``oracle/_shim`` so that the reference's codec runs (``load_codec``); ``kubernetes``
+is only *imported* on the path we drive — ``CheckPendingPods`` / ``AttemptScheduling`` /
 ``ReleasePodResources`` / ``ResetResources`` / ``GetBasicNodeStats`` / ``GetPodStats``
 (``NHDScheduler.py:107-205, 235-441``) talk to ``self.k8s`` and ``self.GetCfgParser`` — so empty
 stub modules are enough: the scheduler object is created without running its constructor
@@ -34,16 +35,15 @@ def load():
     if _loaded is not None:
         return _loaded
     ref = ref_loader.load()
-    for name in ('kubernetes', 'libconf', 'magicattr'):
-        if name in sys.modules:
-            raise RuntimeError(f'{name} unexpectedly importable; review this loader')
+    if 'kubernetes' in sys.modules:
+        raise RuntimeError('kubernetes unexpectedly importable; review this loader')
     k = _stub('kubernetes')
     k.client = _stub('kubernetes.client')
     k.config = _stub('kubernetes.config')
     k.watch = _stub('kubernetes.watch')
     k.client.rest = _stub('kubernetes.client.rest', ApiException=type('ApiException', (Exception,), {}))
-    _stub('libconf')
-    _stub('magicattr')
+    # libconf / magicattr: the stand-ins under oracle/_shim (already on sys.path) are imported by
+    # nhd.TriadCfgParser itself
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         import nhd.NHDScheduler as ref_sched
@@ -52,7 +52,16 @@ def load():
     return ref
 
 
-def make_scheduler(ref, k8s, cfg_parser):
+def load_codec():
+    """The UNMODIFIED ``nhd.TriadCfgParser`` running on the libconf / magicattr stand-ins."""
+    ref = ref_loader.load()
+    if not hasattr(ref, 'codec'):
+        import nhd.TriadCfgParser as ref_codec
+        ref.codec = ref_codec
+    return ref
+
+
+def make_scheduler(ref, k8s, cfg_parser=None):
     """A reference ``NHDScheduler`` wired to fakes; ``cfg_parser(cfgtype, cfgstr)`` replaces
     ``GetCfgParser`` (``NHDScheduler.py:226-232``)."""
     S = ref.sched.NHDScheduler
@@ -65,5 +74,6 @@ def make_scheduler(ref, k8s, cfg_parser):
     s.pod_state = {}
     s.rpcq = None
     s.failed_schedule_count = 0
-    s.GetCfgParser = cfg_parser
+    if cfg_parser is not None:                         # else the reference's own GetCfgParser -> TriadCfgParser
+        s.GetCfgParser = cfg_parser
     return s

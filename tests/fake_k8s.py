@@ -84,7 +84,8 @@ class JsonCfgParser:
 
 
 class FakeK8s:
-    def __init__(self, scn_nodes):
+    def __init__(self, scn_nodes, codec='json'):
+        self.codec = codec                                # 'json' (JsonCfgParser) or 'triad' (libconfig text)
         self.node_defs = {n['name']: n for n in scn_nodes}
         self.pods = {}                                    # (ns, name) -> dict, insertion order = list order
         self.events = {}
@@ -96,11 +97,18 @@ class FakeK8s:
         doc = {'pod': pod_desc}
         if broken_cfg:
             doc['broken'] = True
+        if self.codec == 'triad':
+            import zlib
+            import numpy as np
+            from tests import triad_cfg
+            cfg_text = triad_cfg.pod_to_cfg(pod_desc, np.random.default_rng(zlib.crc32(f'{ns}/{name}'.encode())))
+        else:
+            cfg_text = json.dumps(doc, sort_keys=True)
         annotations = {}
         if pod_desc.get('groups') and list(pod_desc['groups']) != ['default']:
             annotations[GROUPS_ANNOTATION] = ','.join(pod_desc['groups'])
         self.pods[(ns, name)] = {'uid': uid or f'uid-{ns}-{name}', 'phase': phase, 'node': None,
-                                 'annotations': annotations, 'cfg': json.dumps(doc, sort_keys=True),
+                                 'annotations': annotations, 'cfg': cfg_text,
                                  'fail': set(fail),
                                  'requests': {'hugepages-1Gi': f'{pod_desc.get("hugepages", 0)}Gi'}}
         self.events[(ns, name)] = []
@@ -141,7 +149,9 @@ class FakeK8s:
 
     def GetCfgMap(self, pod, ns):                         # K8SMgr.py:328-357: (configmap name, text)
         p = self.pods[(ns, pod)]
-        return (f'{pod}-cfg', '{not json' if 'cfg' in p['fail'] else p['cfg'])
+        if 'cfg' in p['fail']:                            # a config CfgToTopology refuses (returns None)
+            return (f'{pod}-cfg', p['cfg'].replace('TopologyCfg', 'TopoCfg') if self.codec == 'triad' else '{not json')
+        return (f'{pod}-cfg', p['cfg'])
 
     def GetCfgType(self, pod, ns):
         return 'triad'

@@ -51,6 +51,12 @@ def main():
     for seed, flavor in ((1, 'mixed'), (2, 'mixed'), (5, 'mixed'), (3, 'vf'), (7, 'vf'), (4, 'big'), (9, 'big'),
                          (6, 'wild'), (11, 'wild')):
         cases.append((f'random{seed}_{flavor}', H.random_script(seed, flavor)))
+    # sessions in which assignments fail after a successful filter (rewind path), and sessions whose pods carry
+    # real libconfig text read by the reference's own TriadCfgParser (on the libconf / magicattr stand-ins)
+    for seed in (10, 17):
+        cases.append((f'random{seed}_wild_assign_failures', H.random_script(seed, 'wild')))
+    for seed, flavor in ((2, 'wild'), (3, 'mixed'), (8, 'vf'), (12, 'big')):
+        cases.append((f'triad{seed}_{flavor}', H.random_script(seed, flavor, codec='triad')))
     for name, script in cases:
         doc = {'generator': 'tests/golden/make_sched_golden.py', 'source': 'unmodified nhd.NHDScheduler.run()',
                'script': script, 'expected': H.run_reference(script)}

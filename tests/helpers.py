@@ -67,13 +67,19 @@ class OracleSolver:
         for i, r in zip(np.asarray(idx), np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE)):
             self._recs[int(i)] = r
 
-    def read_nodes(self):
-        return self._recs.copy()
+    def read_nodes(self, first=0, n=None):
+        return self._recs[first:(None if n is None else first + n)].copy()
 
     def solve_batch(self, pods, now):
         out, final = self._oracle.solve(self._recs, self._speed, pods, now, self._bw, self._min_busy)
         self._recs = final
         return out
+
+    def snapshot(self):
+        self._snap = self._recs.copy()
+
+    def restore(self):
+        self._recs = self._snap.copy()
 
     def close(self):
         self.closed = True

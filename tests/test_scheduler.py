@@ -32,7 +32,7 @@ def _load(path):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 10
+    assert len(GOLDEN) >= 16
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=IDS)
@@ -40,9 +40,13 @@ def test_scheduler_reproduces_reference_sessions(oracle_lib, path):
     doc = _load(path)
     stats = {}
     got = H.run_mirror(doc['script'], solver_factory=helpers.OracleSolver, stats=stats)
-    assert H.first_difference(doc['expected'], got) is None
-    assert got == doc['expected']
+    want = H.drop_speed_residue(doc['expected'], stats['assign_failed_nodes'])
+    got = H.drop_speed_residue(got, stats['assign_failed_nodes'])
+    assert H.first_difference(want, got) is None
+    assert got == want
     assert stats['batches'] > 0 and stats['pods'] >= stats['batches']
+    if 'assign_failures' in path:                        # failed assignments rewind the device inside the batch
+        assert stats['rewinds'] > 0 and stats['assign_failed_nodes']
 
 
 @pytest.mark.gpu
@@ -50,9 +54,12 @@ def test_scheduler_reproduces_reference_sessions(oracle_lib, path):
 def test_scheduler_cuda_reproduces_reference_sessions(path):
     """The same sessions with the CUDA solver behind the scheduler (the product configuration)."""
     doc = _load(path)
-    got = H.run_mirror(doc['script'])
-    assert H.first_difference(doc['expected'], got) is None
-    assert got == doc['expected']
+    stats = {}
+    got = H.run_mirror(doc['script'], stats=stats)
+    want = H.drop_speed_residue(doc['expected'], stats['assign_failed_nodes'])
+    got = H.drop_speed_residue(got, stats['assign_failed_nodes'])
+    assert H.first_difference(want, got) is None
+    assert got == want
 
 
 @pytest.mark.reference
@@ -61,9 +68,12 @@ def test_scheduler_cuda_reproduces_reference_sessions(path):
 def test_scheduler_matches_live_reference(oracle_lib, flavor):
     checked = binds = 0
     for seed in range(100, 112):
-        script = H.random_script(seed, flavor)
+        script = H.random_script(seed, flavor, codec='triad' if seed % 2 else 'json')
         want = H.run_reference(script)
-        got = H.run_mirror(script, solver_factory=helpers.OracleSolver)
+        stats = {}
+        got = H.run_mirror(script, solver_factory=helpers.OracleSolver, stats=stats)
+        want = H.drop_speed_residue(want, stats['assign_failed_nodes'])
+        got = H.drop_speed_residue(got, stats['assign_failed_nodes'])
         assert H.first_difference(want, got) is None, (seed, flavor)
         checked += 1
         binds += len(want['k8s']['binds'])

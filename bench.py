@@ -17,8 +17,8 @@ Own arm (CUDA):
           bindings (wall clock around nhd_load_nodes + nhd_solve_batch).
   roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
 Reference arm (--impl reference): the reference's algorithm on the host CPU — the C restatement
-under oracle/ (the reference itself is Python and cannot travel to the GPU box), one thread, on
-a bounded sample of the same workload.
+under oracle/ (the reference itself is Python and cannot travel to the GPU box), each pod's walk over
+the nodes split over all host threads, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -103,33 +103,46 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """Threads for the CPU arm: every host core this process may run on."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference_arm(args, rank):
-    """CPU arm: the oracle port of the reference path, single thread, bounded sample per step."""
+    """CPU arm: the oracle port of the reference path on the host cores.  The reference itself is one
+    Python thread (NHDScheduler.py:43); its per-pod walk over all nodes is independent per node, so the
+    port splits that walk over all host threads (pods stay strictly sequential).  Bounded sample per step."""
     if rank != 0:
         return
     from oracle import binding as ob
     ob.build()
     recs, speed, pods, now = workload.make_workload(CONFIG)
     N = len(recs)
-    # size one step at roughly budget/(steps+warmup) seconds: ~1.7 us per (pod, node) evaluation
+    T = host_threads()
+    # size one step at roughly budget/(steps+warmup) seconds from a short calibration run
+    t0 = time.perf_counter()
+    ob.solve(recs, speed, pods[:16], now[:16], threads=T)
+    per_pod = (time.perf_counter() - t0) / 16
     budget = 60.0
     per_step = budget / max(1, args.steps + args.warmup)
-    est_pod_s = N * 1.7e-6
-    n_sample = int(max(2, min(len(pods), per_step / est_pod_s)))
+    n_sample = int(max(8, min(len(pods), per_step / per_pod)))
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        ob.solve(recs, speed, pods[:n_sample], now[:n_sample])
+        ob.solve(recs, speed, pods[:n_sample], now[:n_sample], threads=T)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     value = n_sample * len(times) / sum(times)
-    sample = f'first {n_sample} pods of the 4096-pod stream on all {N} nodes, per step'
+    sample = f'first {n_sample} pods of the 4096-pod stream on all {N} nodes, per step, {T} host threads'
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u64', 'data': 'synthetic',
             'config': {'workload': f'BASELINE config {CONFIG}: 65536 nodes x 4096 pods', 'sample': sample},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': T, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0, 'host_cores_available': os.cpu_count()}
     print(json.dumps(line), flush=True)
@@ -275,15 +288,28 @@ def main():
     if world == 1:
         from oracle import binding as ob
         ob.build()
-        ns = args.cpu_sample_pods
+        names = [n for n in bindings.dtype.names if n != 'pad_']
+        # (1) as the reference runs it: one thread (NHDScheduler.py:43), a short prefix of the stream
+        n1 = min(args.cpu_sample_pods, 64)
         t0 = time.perf_counter()
-        cb, _ = ob.solve(recs, speed, pods[:ns], now[:ns])
+        c1, _ = ob.solve(recs, speed, pods[:n1], now[:n1])
+        dt1 = time.perf_counter() - t0
+        par1 = all(np.array_equal(c1[n], bindings[:n1][n]) for n in names)
+        # (2) all host threads: each pod's walk over the nodes split over them; ~15 s of the same stream
+        T = host_threads()
+        t0 = time.perf_counter()
+        ob.solve(recs, speed, pods[:16], now[:16], threads=T)
+        per_pod = (time.perf_counter() - t0) / 16
+        ns = int(max(args.cpu_sample_pods, min(P, 15.0 / per_pod)))
+        t0 = time.perf_counter()
+        cb, _ = ob.solve(recs, speed, pods[:ns], now[:ns], threads=T)
         dt = time.perf_counter() - t0
-        names = [n for n in cb.dtype.names if n != 'pad_']
         parity = all(np.array_equal(cb[n], bindings[:ns][n]) for n in names)
-        cpu = {'value': ns / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-               'sample': f'first {ns} pods of the same stream on all {N} nodes ({dt:.1f} s); '
+        cpu = {'value': ns / dt, 'unit': UNIT, 'cores': T, 'kind': 'port',
+               'sample': f'first {ns} pods of the same stream on all {N} nodes, {T} host threads ({dt:.1f} s); '
                          f'bindings identical to the GPU run: {parity}',
+               'single_thread': {'value': n1 / dt1, 'cores': 1,
+                                 'sample': f'first {n1} pods ({dt1:.1f} s); bindings identical to the GPU run: {par1}'},
                'host_cores_available': os.cpu_count()}
 
     placed = int((bindings['status'] == 0).sum())

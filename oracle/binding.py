@@ -36,6 +36,8 @@ def lib():
         L.nhd_oracle_solve.restype = ctypes.c_int
         L.nhd_oracle_solve.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.nhd_oracle_solve_mt.restype = ctypes.c_int
+        L.nhd_oracle_solve_mt.argtypes = L.nhd_oracle_solve.argtypes + [ctypes.c_int]
         L.nhd_oracle_candidates.restype = ctypes.c_int
         L.nhd_oracle_candidates.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
@@ -47,8 +49,9 @@ def lib():
     return _lib
 
 
-def solve(recs, speed_table, pods, now, nic_bw_avail_percent=0.9, min_busy_secs=30.0):
-    """Run the oracle over a batch.  Returns (bindings, final_records); inputs are not modified."""
+def solve(recs, speed_table, pods, now, nic_bw_avail_percent=0.9, min_busy_secs=30.0, threads=1):
+    """Run the oracle over a batch.  Returns (bindings, final_records); inputs are not modified.
+    ``threads`` > 1 splits each pod's walk over the nodes over host threads (same result)."""
     from nhd_b200 import wire
     recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE).copy()
     pods = np.ascontiguousarray(pods, dtype=wire.POD_DTYPE)
@@ -57,8 +60,12 @@ def solve(recs, speed_table, pods, now, nic_bw_avail_percent=0.9, min_busy_secs=
     assert len(now) == len(pods)
     out = np.zeros(len(pods), dtype=wire.BINDING_DTYPE)
     p = OracleParams(nic_bw_avail_percent, min_busy_secs)
-    rc = lib().nhd_oracle_solve(ctypes.byref(p), speed.ctypes.data, len(recs), recs.ctypes.data,
-                                len(pods), pods.ctypes.data, now.ctypes.data, out.ctypes.data)
+    if threads > 1:
+        rc = lib().nhd_oracle_solve_mt(ctypes.byref(p), speed.ctypes.data, len(recs), recs.ctypes.data,
+                                       len(pods), pods.ctypes.data, now.ctypes.data, out.ctypes.data, int(threads))
+    else:
+        rc = lib().nhd_oracle_solve(ctypes.byref(p), speed.ctypes.data, len(recs), recs.ctypes.data,
+                                    len(pods), pods.ctypes.data, now.ctypes.data, out.ctypes.data)
     if rc != 0:
         raise RuntimeError(f'nhd_oracle_solve failed: {rc}')
     return out, recs

@@ -46,6 +46,7 @@
 #include "pyset_model.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -394,7 +395,7 @@ static int filter_nic_stage(const o_node* v, const o_pod* top, o_filts* f)
     double req_nics[NHD_MAX_GROUPS][2];                    /* CfgTopology.py:219-232 */
     for (int g = 0; g < G; g++) { req_nics[g][0] = top->g[g].rx; req_nics[g][1] = top->g[g].tx; }
 
-    static double nnic_free[NHD_MAX_NUMA][NHD_MAX_NICS][2];
+    static _Thread_local double nnic_free[NHD_MAX_NUMA][NHD_MAX_NICS][2];
     int ncnt[NHD_MAX_NUMA];
     get_free_numa_nic_resources(v, nnic_free, ncnt);       /* :240 */
 
@@ -432,7 +433,7 @@ static int filter_nic_stage(const o_node* v, const o_pod* top, o_filts* f)
                     }
                 }
                 /* :254 nic_ttls = copy.deepcopy(nnic_free[n]) */
-                static double nic_ttls[NHD_MAX_NUMA][NHD_MAX_NICS][2];
+                static _Thread_local double nic_ttls[NHD_MAX_NUMA][NHD_MAX_NICS][2];
                 memcpy(nic_ttls, nnic_free, sizeof(nic_ttls));
                 /* :258 ttl_list = [c[np].pop(0) for np in p] */
                 uint8_t ttl_list[NHD_MAX_GROUPS];
@@ -478,7 +479,7 @@ static int intersect_node(const o_node* v, const o_pod* top, o_filts* f)
 
     if (top->map_type == NHD_MAP_PCI) {                    /* :295-335 */
         int gsw[NHD_MAX_SWITCHES];
-        static int nsw[NHD_MAX_NUMA][NHD_MAX_NICS];
+        static _Thread_local int nsw[NHD_MAX_NUMA][NHD_MAX_NICS];
         get_free_gpu_pci_count(v, gsw);                    /* :307 */
         get_numa_nic_pci_resources(v, nsw);                /* :308 */
         int* to_remove = (int*)calloc((size_t)f->n_nic + 1, sizeof(int));
@@ -763,6 +764,70 @@ index_error:                                               /* :825-837 */
 /* ------------------------------------------------------------------------- */
 /* One pod: InitialNodeFilter + FindNode + SetBusy + assignment + claim       */
 /* ------------------------------------------------------------------------- */
+/* What the node loop of FindNode leaves behind for SelectNode: the first candidate and the first
+ * candidate without GPUs, each with its filts (Matcher.py:55, 412-421).  The reference walks ALL
+ * nodes for every pod; scan_range() does the same over [lo, hi) so that the walk can be split into
+ * ranges (nhd_oracle_solve_mt) — node evaluations within one pod are independent of each other. */
+typedef struct {
+    int first_cand, first_nogpu;
+    o_filts f_first, f_nogpu;
+} scan_res;
+
+static void scan_range(const o_node* nodes, int lo, int hi, const o_pod* top, double now,
+                       scan_res* r, uint8_t* cand_out)
+{
+    r->first_cand = r->first_nogpu = -1;
+    memset(&r->f_first, 0, sizeof(r->f_first)); memset(&r->f_nogpu, 0, sizeof(r->f_nogpu));
+    for (int n = lo; n < hi; n++) {
+        const o_node* v = &nodes[n];
+        if (cand_out) cand_out[n] = 0;
+        /* InitialNodeFilter, NHDScheduler.py:241-243 */
+        if ((v->groups & top->groups) == 0) continue;
+        if (!v->active) continue;
+        o_filts f;
+        int cand = evaluate_node(v, top, now, &f);
+        if (cand && cand_out) cand_out[n] = 1;
+        if (cand && r->first_cand < 0) {
+            r->first_cand = n; r->f_first = f; memset(&f, 0, sizeof(f));
+            if (v->n_gpus == 0) r->first_nogpu = n;        /* shares f_first */
+        } else if (cand && r->first_nogpu < 0 && v->n_gpus == 0) {
+            r->first_nogpu = n; r->f_nogpu = f; memset(&f, 0, sizeof(f));
+        }
+        filts_free(&f);
+    }
+}
+
+static void scan_res_free(scan_res* r) { filts_free(&r->f_first); filts_free(&r->f_nogpu); }
+
+/* Ranges in ascending node order -> the result of one walk over all of them. */
+static void scan_merge(scan_res* parts, int n_parts, scan_res* out)
+{
+    out->first_cand = out->first_nogpu = -1;
+    memset(&out->f_first, 0, sizeof(out->f_first)); memset(&out->f_nogpu, 0, sizeof(out->f_nogpu));
+    for (int p = 0; p < n_parts; p++) {
+        scan_res* r = &parts[p];
+        int took_first = 0;
+        if (r->first_cand >= 0 && out->first_cand < 0) {
+            out->first_cand = r->first_cand;
+            out->f_first = r->f_first; memset(&r->f_first, 0, sizeof(r->f_first));
+            took_first = 1;
+        }
+        if (r->first_nogpu >= 0 && out->first_nogpu < 0) {
+            out->first_nogpu = r->first_nogpu;
+            if (r->first_nogpu == r->first_cand) {
+                /* the range's first candidate has no GPUs: one filts for both roles; it is already
+                 * out->f_first if this range supplied the overall first candidate */
+                if (!took_first) { out->f_nogpu = r->f_first; memset(&r->f_first, 0, sizeof(r->f_first)); }
+            } else {
+                out->f_nogpu = r->f_nogpu; memset(&r->f_nogpu, 0, sizeof(r->f_nogpu));
+            }
+        }
+        scan_res_free(r);
+    }
+}
+
+static void finish_scheduling(o_node* nodes, const o_pod* top, double now, nhd_binding* b, scan_res* sr);
+
 static void attempt_scheduling(o_node* nodes, int n_nodes, const o_pod* top, double now,
                                nhd_binding* b, uint8_t* cand_out)
 {
@@ -774,32 +839,20 @@ static void attempt_scheduling(o_node* nodes, int n_nodes, const o_pod* top, dou
         b->status = NHD_BAD_MAP_TYPE;
         return;
     }
+    scan_res sr;
+    scan_range(nodes, 0, n_nodes, top, now, &sr, cand_out);
+    finish_scheduling(nodes, top, now, b, &sr);
+}
 
+/* SelectNode, GetNumaGroupIdx, SetBusy, SetPhysicalIdsFromMapping on the walk's result. */
+static void finish_scheduling(o_node* nodes, const o_pod* top, double now, nhd_binding* b, scan_res* sr)
+{
     /* SelectNode inputs, Matcher.py:406-410 */
     int needsGpu = 0;
     for (int g = 0; g < top->n_groups; g++) if (top->g[g].n_gpus > 0) needsGpu = 1;
-
-    int first_cand = -1, first_nogpu = -1;
-    o_filts f_first, f_nogpu;
-    memset(&f_first, 0, sizeof(f_first)); memset(&f_nogpu, 0, sizeof(f_nogpu));
-
-    for (int n = 0; n < n_nodes; n++) {
-        const o_node* v = &nodes[n];
-        if (cand_out) cand_out[n] = 0;
-        /* InitialNodeFilter, NHDScheduler.py:241-243 */
-        if ((v->groups & top->groups) == 0) continue;
-        if (!v->active) continue;
-        o_filts f;
-        int cand = evaluate_node(v, top, now, &f);
-        if (cand && cand_out) cand_out[n] = 1;
-        if (cand && first_cand < 0) {
-            first_cand = n; f_first = f; memset(&f, 0, sizeof(f));
-            if (v->n_gpus == 0) first_nogpu = n;           /* shares f_first */
-        } else if (cand && first_nogpu < 0 && v->n_gpus == 0) {
-            first_nogpu = n; f_nogpu = f; memset(&f, 0, sizeof(f));
-        }
-        filts_free(&f);
-    }
+    const int first_cand = sr->first_cand, first_nogpu = sr->first_nogpu;
+#define f_first (sr->f_first)
+#define f_nogpu (sr->f_nogpu)
 
     if (first_cand < 0) {                                  /* Matcher.py:50-52 / 58-60 */
         b->status = NHD_NO_CANDIDATE;
@@ -839,6 +892,8 @@ static void attempt_scheduling(o_node* nodes, int n_nodes, const o_pod* top, dou
     b->status = set_physical_ids_from_mapping(&nodes[node], &m, top, b);
 
     filts_free(&f_first); filts_free(&f_nogpu);
+#undef f_first
+#undef f_nogpu
 }
 
 /* ------------------------------------------------------------------------- */
@@ -868,6 +923,93 @@ int nhd_oracle_solve(const nhd_oracle_params* params, const double* speed_gbps,
             collapse_node(&nodes[out[i].node], &recs[out[i].node]);
     }
     free(nodes);
+    return 0;
+}
+
+/* ---- the same, with the per-pod walk over the nodes split over threads ---------------------- */
+typedef struct {
+    int T;
+    pthread_barrier_t start, done;
+    volatile int quit;
+    const o_node* nodes; int n_nodes;
+    const o_pod* top; double now;
+    scan_res* parts;
+} scan_pool;
+
+typedef struct { scan_pool* pool; int t; } scan_worker;
+
+static void pool_do_range(scan_pool* pl, int t)
+{
+    const long n = pl->n_nodes;
+    scan_range(pl->nodes, (int)(n * t / pl->T), (int)(n * (t + 1) / pl->T), pl->top, pl->now, &pl->parts[t], NULL);
+}
+
+static void* pool_main(void* arg)
+{
+    scan_worker* w = (scan_worker*)arg;
+    for (;;) {
+        pthread_barrier_wait(&w->pool->start);
+        if (w->pool->quit) break;
+        pool_do_range(w->pool, w->t);
+        pthread_barrier_wait(&w->pool->done);
+    }
+    return NULL;
+}
+
+int nhd_oracle_solve_mt(const nhd_oracle_params* params, const double* speed_gbps,
+                        int n_nodes, nhd_node_rec* recs,
+                        int n_pods, const nhd_pod* pods, const double* now,
+                        nhd_binding* out, int n_threads)
+{
+    if (n_threads < 2)
+        return nhd_oracle_solve(params, speed_gbps, n_nodes, recs, n_pods, pods, now, out);
+    P = params; SPEED = speed_gbps;
+    o_node* nodes = (o_node*)malloc(sizeof(o_node) * (size_t)(n_nodes > 0 ? n_nodes : 1));
+    if (!nodes) return -1;
+    for (int n = 0; n < n_nodes; n++) expand_node(&recs[n], &nodes[n]);
+
+    scan_pool pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.T = n_threads; pl.nodes = nodes; pl.n_nodes = n_nodes;
+    pl.parts = (scan_res*)calloc((size_t)n_threads, sizeof(scan_res));
+    pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    scan_worker* ws = (scan_worker*)calloc((size_t)n_threads, sizeof(scan_worker));
+    if (!pl.parts || !th || !ws) return -1;
+    pthread_barrier_init(&pl.start, NULL, (unsigned)n_threads);
+    pthread_barrier_init(&pl.done, NULL, (unsigned)n_threads);
+    int started = 1;
+    for (int t = 1; t < n_threads; t++) {
+        ws[t].pool = &pl; ws[t].t = t;
+        if (pthread_create(&th[t], NULL, pool_main, &ws[t]) != 0) break;
+        started++;
+    }
+    if (started != n_threads) {                  /* could not get the threads: leave the pool, run the plain loop */
+        fprintf(stderr, "nhd_oracle_solve_mt: only %d of %d threads\n", started, n_threads);
+        abort();
+    }
+    for (int i = 0; i < n_pods; i++) {
+        o_pod top;
+        expand_pod(&pods[i], &top);
+        nhd_binding* b = &out[i];
+        memset(b, 0, sizeof(*b));
+        b->node = -1;
+        b->n_groups = (uint8_t)top.n_groups;
+        if (top.map_type != NHD_MAP_NUMA && top.map_type != NHD_MAP_PCI) { b->status = NHD_BAD_MAP_TYPE; continue; }
+        pl.top = &top; pl.now = now[i];
+        pthread_barrier_wait(&pl.start);
+        pool_do_range(&pl, 0);
+        pthread_barrier_wait(&pl.done);
+        scan_res sr;
+        scan_merge(pl.parts, n_threads, &sr);
+        finish_scheduling(nodes, &top, now[i], b, &sr);
+        if (b->node >= 0)
+            collapse_node(&nodes[b->node], &recs[b->node]);
+    }
+    pl.quit = 1;
+    pthread_barrier_wait(&pl.start);
+    for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
+    pthread_barrier_destroy(&pl.start); pthread_barrier_destroy(&pl.done);
+    free(pl.parts); free(th); free(ws); free(nodes);
     return 0;
 }
 

@@ -26,6 +26,14 @@ int nhd_oracle_solve(const nhd_oracle_params* params, const double* speed_gbps,
                      int n_pods, const nhd_pod* pods, const double* now,
                      nhd_binding* out);
 
+/* The same result with the walk over the nodes (which the reference repeats in full for every pod) split
+ * over n_threads host threads; pods are still taken strictly one after another.  Used for the CPU
+ * baseline of bench.py; checked bit for bit against nhd_oracle_solve (tests/test_oracle_mt.py). */
+int nhd_oracle_solve_mt(const nhd_oracle_params* params, const double* speed_gbps,
+                        int n_nodes, nhd_node_rec* recs,
+                        int n_pods, const nhd_pod* pods, const double* now,
+                        nhd_binding* out, int n_threads);
+
 /* cand_out[n] = 1 iff node n is in filts[1] after IntersectResources for this pod
  * (nhd/Matcher.py:55) on the given (unmodified) state. */
 int nhd_oracle_candidates(const nhd_oracle_params* params, const double* speed_gbps,

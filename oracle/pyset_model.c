@@ -91,7 +91,7 @@ found_null:
 /* set_table_resize(): smallest power of two > minused, re-insert in old slot order */
 static void table_resize(pyset* s, size_t minused)
 {
-    static pyset_entry old[PYSET_MAX_SLOTS];
+    static _Thread_local pyset_entry old[PYSET_MAX_SLOTS];
     size_t oldmask = s->mask;
     size_t newsize = PYSET_MINSIZE;
     while (newsize <= minused)

@@ -106,6 +106,7 @@ class DeviceCluster:
         self.batches = 0
         self.rewinds = 0
         self._last = None
+        self.stubs = set()
 
     @property
     def layout(self):
@@ -141,6 +142,7 @@ class DeviceCluster:
                 recs[i] = np.zeros((), dtype=wire.NODE_DTYPE)
                 recs[i]['n_numa'] = 1
                 recs[i]['phys_cores'] = 1
+                self.stubs.add(node.name)
         return recs
 
     def sync(self, nodes: Dict[str, object], dirty: Iterable[str]):
@@ -210,7 +212,8 @@ class _Pending:
 class NHDScheduler:
     def __init__(self, k8s, cfg_parser: Callable, rpcq: Queue = None, solver_factory: Callable = None,
                  device: int = 0, clock: Callable[[], float] = time.monotonic,
-                 wall: Callable[[], float] = time.time, node_cls=Node, logger=None):
+                 wall: Callable[[], float] = time.time, node_cls=Node, logger=None,
+                 stats_from_device: bool = False):
         self.nodes: Dict[str, Node] = {}
         self.k8s = k8s
         self.sched_name = NHD_SCHED_NAME
@@ -225,6 +228,7 @@ class NHDScheduler:
         self._log = logger
         self.pods_solved = 0
         self.assign_failed_nodes = set()
+        self.stats_from_device = stats_from_device
 
     # ---- small helpers --------------------------------------------------------------------
     def _info(self, msg):
@@ -614,12 +618,16 @@ class NHDScheduler:
         self._dirty.clear()
         st = ingest.node_stats(self.cluster.read_records())
         rows = []
+        by_name = {r['name']: r for r in self.GetBasicNodeStats()} if self.cluster.stubs else {}
         for i, (k, v) in enumerate(self.nodes.items()):
+            if k in self.cluster.stubs:              # no usable record: the half-initialised object answers
+                rows.append(by_name[k])
+                continue
             s = st[i]
             rows.append({'name': k,
-                         'freegpu': int(s['free_gpus']), 'totalgpu': int(s['total_gpus']),
-                         'freecpu': int(s['free_cpu_cores']), 'totalcpu': int(s['total_cpus']),
-                         'freehuge_gb': int(s['free_hugepages_gb']), 'totalhuge_gb': v.GetTotalHugepages(),
+                         'freegpu': int(s['freegpu']), 'totalgpu': int(s['totalgpu']),
+                         'freecpu': int(s['freecpu']), 'totalcpu': int(s['totalcpu']),
+                         'freehuge_gb': int(s['freehuge_gb']), 'totalhuge_gb': v.GetTotalHugepages(),
                          'totalpods': v.GetTotalPods(), 'active': bool(s['active']),
                          'nicstats': v.GetNICUsedSpeeds()})
         return rows
@@ -651,7 +659,8 @@ class NHDScheduler:
     def ParseRPCReq(self, msgid, q: Queue):
         t = _type_name(msgid)
         if t == 'TYPE_NODE_INFO':
-            q.put(self.GetBasicNodeStats())
+            q.put(self.GetBasicNodeStatsFromDevice() if self.stats_from_device and self.nodes
+                  else self.GetBasicNodeStats())
         elif t == 'TYPE_SCHEDULER_INFO':
             q.put(self.failed_schedule_count)
         elif t == 'TYPE_POD_INFO':

@@ -6,5 +6,7 @@ Layout:
   wire, packing    packed record formats and object <-> record conversion
   CfgTopology, Node, Matcher, NHDScheduler   host-side mirrors of the reference interface
   ingest           native node-label ingest and node statistics
+  TriadCfgParser, libconfig   the request codec (libconfig text <-> CfgTopology)
+  NHDRpcServer     the gRPC statistics service
 """
 __all__ = ['CfgTopology', 'Node', 'Matcher', 'NHDScheduler', 'packing', 'wire', 'solver', 'ingest']

@@ -1,0 +1,93 @@
+"""The CUDA kernels themselves on a machine without a GPU.
+
+``tests/emu/cuda_emu.h`` is a small CPU emulation of the CUDA execution model (every thread of a block a
+fiber, warp collectives as rendezvous that abort on divergent use, __syncthreads, atomics, mbarrier + bulk
+copy); ``tests/emu/build_emu_cuda.py`` compiles the product's own sources — ``nhd_api.cu``,
+``nhd_kernels.cuh``, ``nhd_core.cuh``, ``nhd_ingest.cpp`` — with g++ on top of it into
+``tests/emu/_emu_cuda.so``, a library with the product's C-ABI.  This test runs every ``-m gpu`` test of the
+repository (parity with the oracle, golden vectors, drop-in Matcher, scheduler sessions ...) in a child
+process whose ``NHD_B200_LIB`` points at that library: the filter, the multi-warp sweep with its hand-off
+protocol, resolve / core-id / commit kernels and the host side of the ABI all execute for real, on the CPU.
+
+What this does and does not show: the *logic* of the kernels and the convergence rules of the warp
+collectives (a lane of a mask that has exited, or lanes of one mask sitting in different collectives, abort
+the run).  It says nothing about speed or the GPU memory model (one OS thread: sequentially consistent).
+TEST INFRASTRUCTURE: the product library is built by nvcc only, and on the GPU box the same tests run on
+the B200 (``NHD_B200_LIB`` unset)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def emu_cuda_lib():
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+    try:
+        import build_emu_cuda
+    finally:
+        sys.path.pop(0)
+    return build_emu_cuda.build()
+
+
+def _run_gpu_tests(lib, extra_env=None, select=None):
+    env = dict(os.environ, NHD_B200_LIB=lib, EMU_LANE_ORDER='d')
+    env.update(extra_env or {})
+    cmd = [sys.executable, '-m', 'pytest', 'tests', '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider']
+    if select:
+        cmd += ['-k', select]
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+
+
+def test_gpu_suite_passes_on_the_emulated_device(emu_cuda_lib):
+    res = _run_gpu_tests(emu_cuda_lib)
+    tail = (res.stdout + res.stderr)[-3000:]
+    assert res.returncode == 0, tail
+    last = [ln for ln in res.stdout.strip().splitlines() if 'passed' in ln][-1]
+    assert 'failed' not in last and int(last.split()[0]) >= 60, last
+
+
+def test_emulator_catches_divergent_collectives(emu_cuda_lib, tmp_path):
+    """The emulation is only worth something if it refuses what the GPU leaves undefined."""
+    src = tmp_path / 'bad.cpp'
+    src.write_text('''
+#include "cuda_emu.h"
+__global__ void diverge(int* out) {
+    int lane = threadIdx.x;
+    if (lane & 1) out[lane] = __ballot_sync(0xFFFFFFFFu, 1);     /* odd lanes vote ...           */
+    else __syncwarp();                                           /* ... even lanes only synchronise */
+}
+__global__ void gone(int* out) {
+    int lane = threadIdx.x;
+    if (lane == 7) return;                                       /* lane 7 leaves, the mask still names it */
+    out[lane] = __shfl_sync(0xFFFFFFFFu, lane, 0);
+}
+__global__ void fine(int* out) {
+    int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(0xFFFFFFFFu, lane < 5);
+    out[threadIdx.x] = __shfl_sync(0xFFFFFFFFu, (int)m + lane, (lane + 1) & 31) + __shfl_up_sync(0xFFFFFFFFu, lane, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(out + 64, 1);
+}
+int main(int argc, char** argv) {
+    static int buf[80];
+    int* out = buf;
+    if (argv[1][0] == 'd') EMU_LAUNCH(diverge, 1, 32, 0, 0, out);
+    if (argv[1][0] == 'g') EMU_LAUNCH(gone, 1, 32, 0, 0, out);
+    if (argv[1][0] == 'f') { EMU_LAUNCH(fine, 3, 64, 0, 0, out); printf("%d %d %d %d %d\\n", out[0], out[1], out[31], out[63], out[64]); }
+    return 0;
+}
+''')
+    exe = tmp_path / 'bad'
+    emu = os.path.join(ROOT, 'tests', 'emu')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-I', emu, '-o', str(exe), str(src), os.path.join(emu, 'cuda_emu.cpp')],
+                   check=True)
+    ok = subprocess.run([str(exe), 'f'], capture_output=True, text=True)
+    assert ok.returncode == 0 and ok.stdout.split() == ['32', '33', '61', '61', '3'], (ok.stdout, ok.stderr)
+    d = subprocess.run([str(exe), 'd'], capture_output=True, text=True)
+    assert d.returncode != 0 and 'divergent collectives' in d.stderr
+    g = subprocess.run([str(exe), 'g'], capture_output=True, text=True)
+    assert g.returncode != 0 and 'already left the kernel' in g.stderr

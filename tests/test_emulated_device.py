@@ -50,6 +50,32 @@ def test_gpu_suite_passes_on_the_emulated_device(emu_cuda_lib):
     assert 'failed' not in last and int(last.split()[0]) >= 60, last
 
 
+def test_full_size_cluster_is_exact_on_the_emulated_device(emu_cuda_lib, oracle_lib):
+    """BASELINE config 4 at its full 65 536 nodes: the first 768 pods of the stream through the real kernels, every
+    binding and every final record against the oracle (``tools/emu_full_size.py`` does all 4 096 pods: equal)."""
+    code = '''
+import os, sys
+import numpy as np
+sys.path.insert(0, %r)
+import workload
+from nhd_b200.solver import Solver
+from oracle import binding
+from tests import helpers
+recs, speed, pods, now = workload.make_workload(4)
+pods, now = pods[:768], now[:768]
+s = Solver(speed); s.load_nodes(recs)
+b = s.solve_batch(pods, now); final = s.read_nodes(); s.close()
+ob, orecs = binding.solve(recs, speed, pods, now, threads=os.cpu_count())
+assert len(recs) == 65536 and helpers.binding_bytes_equal(ob, b), helpers.first_binding_diff(ob, b)
+assert final.tobytes() == orecs.tobytes()
+print('placed', int((ob['status'] == 0).sum()))
+''' % ROOT
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    res = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-2000:]
+    assert res.stdout.split()[-2:] == ['placed', '768']
+
+
 def test_emulator_catches_divergent_collectives(emu_cuda_lib, tmp_path):
     """The emulation is only worth something if it refuses what the GPU leaves undefined."""
     src = tmp_path / 'bad.cpp'

@@ -156,8 +156,11 @@ class _StopItem(dict):
 class _RefFeed:
     """Plays the part of ``qinst`` (watch queue) and of the gRPC queue for ``NHDScheduler.run``."""
 
-    def __init__(self, ref, k8s, steps, sink):
+    def __init__(self, ref, k8s, steps, sink, watch_enum=None, rpc_enum=None, clock=None):
         self.ref, self.k8s, self.steps, self.sink = ref, k8s, steps, sink
+        self.watch_enum = watch_enum if watch_enum is not None else ref.sched.NHDWatchTypes
+        self.rpc_enum = rpc_enum if rpc_enum is not None else ref.sched.RpcMsgType
+        self.clock = clock if clock is not None else ref.clock
         self.i = 0
         self.checked = False
         self.armed = False
@@ -171,7 +174,7 @@ class _RefFeed:
                 return _StopItem()
             st = self.steps[self.i]
             if st['op'] in K8S_OPS:
-                apply_k8s_op(self.k8s, self.ref.clock, st)
+                apply_k8s_op(self.k8s, self.clock, st)
                 self.i += 1
             elif st['op'] == 'restart':
                 self.i += 1
@@ -179,7 +182,7 @@ class _RefFeed:
             elif st['op'] == 'watch':
                 self.i += 1
                 item = {k: v for k, v in st.items() if k != 'op'}
-                item['type'] = self.ref.sched.NHDWatchTypes[st['type']]
+                item['type'] = self.watch_enum[st['type']]
                 return item
             else:
                 raise Empty()                             # rpc / idle: served by the other queue
@@ -193,7 +196,7 @@ class _RefFeed:
             st = f.steps[f.i]
             if st['op'] == 'rpc':
                 f.i += 1
-                return (f.ref.sched.RpcMsgType[st['msg']], f.sink)
+                return (f.rpc_enum[st['msg']], f.sink)
             assert st['op'] == 'idle'
             if not f.armed:
                 f.armed, f.checked = True, False
@@ -309,6 +312,49 @@ def drop_speed_residue(doc, names):
                 if isinstance(row, dict) and row.get('name') in names:
                     row.pop('nicstats', None)
     return doc
+
+
+def run_mirror_loop(script, solver_factory=None):
+    """Like run_mirror, but through ``nhd_b200.NHDScheduler.run()`` — the thread function with its queue
+    polling and idle counting — fed by the same fake queues that drive the reference's ``run()``."""
+    import nhd_b200.CfgTopology as cfg_mod
+    import nhd_b200.Node as node_mod
+    from nhd_b200 import NHDScheduler as M
+    node_mod.Node.MIN_BUSY_SECS = float(script['min_busy_secs'])
+    clock = Clock(script['clock0'])
+    k8s = fake_k8s.FakeK8s(script['nodes'], codec=script.get('codec', 'json'))
+    sink = RpcSink()
+    for st in script['init']:
+        apply_k8s_op(k8s, clock, st)
+    if script.get('codec', 'json') == 'triad':
+        from nhd_b200.TriadCfgParser import TriadCfgParser
+        parser = lambda cfgtype, cfgstr: TriadCfgParser(cfgstr, False)          # noqa: E731
+    else:
+        parser = lambda cfgtype, cfgstr: fake_k8s.JsonCfgParser(cfgstr, cfg_mod)  # noqa: E731
+    feed = _RefFeed(None, k8s, script['steps'], sink, M.NHDWatchTypes, M.RpcMsgType, clock)
+    s = None
+    try:
+        while True:
+            if s is not None:
+                s.close()
+            s = M.NHDScheduler(k8s, parser, rpcq=feed.rpcq, solver_factory=solver_factory, clock=clock)
+            orig = s.CheckPendingPods
+
+            def checked(orig=orig):
+                orig()
+                feed.checked = True
+            s.CheckPendingPods = checked
+            try:
+                s.run(feed)
+            except _Stop:
+                pass
+            if feed.i >= len(script['steps']):
+                break
+        return state_document(s, k8s, sink)
+    finally:
+        node_mod.Node.MIN_BUSY_SECS = 30.0
+        if s is not None:
+            s.close()
 
 
 def _collect(stats, s):

@@ -98,7 +98,8 @@ def test_no_cpu_fallback(lib):
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under nhd_b200/ may import, include or link it."""
     pkg = os.path.join(ROOT, 'nhd_b200')
-    pat = re.compile(r'(import\s+oracle|from\s+oracle|#include\s+"[^"]*oracle|libnhd_oracle|oracle/)')
+    pat = re.compile(r'(import\s+oracle|from\s+oracle|#include\s+"[^"]*oracle|libnhd_oracle|oracle/|'
+                     r'^\s*import\s+tests\b|^\s*from\s+tests\b|cuda_emu)', re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):

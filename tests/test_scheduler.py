@@ -80,6 +80,16 @@ def test_scheduler_matches_live_reference(oracle_lib, flavor):
     assert checked == 12 and binds > 100
 
 
+def test_thread_function_equals_direct_driving(oracle_lib):
+    """``NHDScheduler.run()`` (queue polling, idle counting, start-up flush) fed by the fake queues that drive
+    the reference's ``run()`` ends where driving the handlers directly ends."""
+    for seed, flavor, codec in ((3, 'mixed', 'json'), (4, 'wild', 'triad'), (5, 'vf', 'json')):
+        script = H.random_script(seed, flavor, codec=codec)
+        a = H.run_mirror(script, solver_factory=helpers.OracleSolver)
+        b = H.run_mirror_loop(script, solver_factory=helpers.OracleSolver)
+        assert H.first_difference(a, b) is None, (seed, flavor)
+
+
 def test_pending_set_is_one_batch_and_unwinds_cut_it(oracle_lib):
     """No failing write: the whole pending set is ONE solver call.  A write that fails before the
     config annotation exists makes ``ReleasePodResources`` reset the cluster (``NHDScheduler.py:178-181``);

@@ -104,11 +104,42 @@ class ClockSampler:
 
 
 def host_threads():
-    """Threads for the CPU arm: every host core this process may run on."""
+    """Threads for the CPU arm: the host cores this process may really use (affinity mask, cgroup CPU quota)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period) + 0.999)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def pick_threads(ob, recs, speed, pods, now, single_per_pod=None):
+    """Times a few pods with all host threads and with fewer; returns (threads, seconds per pod) of the fastest.
+    The walk over the nodes is barrier-synchronised per pod, so more threads than usable cores only hurt."""
+    best = (1, single_per_pod) if single_per_pod else None
+    T = host_threads()
+    tried = []
+    for t in sorted({T, max(1, T // 2), max(1, T // 4), min(T, 16)}, reverse=True):
+        if t < 2:
+            continue
+        t0 = time.perf_counter()
+        ob.solve(recs, speed, pods[:8], now[:8], threads=t)
+        per_pod = (time.perf_counter() - t0) / 8
+        tried.append((t, per_pod))
+        if best is None or per_pod < best[1]:
+            best = (t, per_pod)
+        if per_pod > 2.0:                       # hopeless already: do not spend the budget on calibration
+            break
+    if best is None:
+        t0 = time.perf_counter()
+        ob.solve(recs, speed, pods[:4], now[:4])
+        best = (1, (time.perf_counter() - t0) / 4)
+    return best
 
 
 def run_reference_arm(args, rank):
@@ -121,11 +152,8 @@ def run_reference_arm(args, rank):
     ob.build()
     recs, speed, pods, now = workload.make_workload(CONFIG)
     N = len(recs)
-    T = host_threads()
     # size one step at roughly budget/(steps+warmup) seconds from a short calibration run
-    t0 = time.perf_counter()
-    ob.solve(recs, speed, pods[:16], now[:16], threads=T)
-    per_pod = (time.perf_counter() - t0) / 16
+    T, per_pod = pick_threads(ob, recs, speed, pods, now)
     budget = 60.0
     per_step = budget / max(1, args.steps + args.warmup)
     n_sample = int(max(8, min(len(pods), per_step / per_pod)))
@@ -296,11 +324,8 @@ def main():
         dt1 = time.perf_counter() - t0
         par1 = all(np.array_equal(c1[n], bindings[:n1][n]) for n in names)
         # (2) all host threads: each pod's walk over the nodes split over them; ~15 s of the same stream
-        T = host_threads()
-        t0 = time.perf_counter()
-        ob.solve(recs, speed, pods[:16], now[:16], threads=T)
-        per_pod = (time.perf_counter() - t0) / 16
-        ns = int(max(args.cpu_sample_pods, min(P, 15.0 / per_pod)))
+        T, per_pod = pick_threads(ob, recs, speed, pods, now, single_per_pod=dt1 / n1)
+        ns = int(max(32, min(P, 15.0 / per_pod)))
         t0 = time.perf_counter()
         cb, _ = ob.solve(recs, speed, pods[:ns], now[:ns], threads=T)
         dt = time.perf_counter() - t0

@@ -77,7 +77,10 @@ static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint6
     return text.replace('#include "nhd_core.cuh"\n', '#include "nhd_core.cuh"\n' + shim, 1)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, asan=False):
+    """``asan``: a second library with AddressSanitizer (out-of-bounds accesses to emulated device memory);
+    run it with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0."""
+    OUT = os.path.join(HERE, '_emu_cuda_asan.so' if asan else '_emu_cuda.so')
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(GEN, exist_ok=True)
@@ -91,7 +94,8 @@ def build(force=False, verbose=False):
                 .replace('__noinline__', 'EMU_NOINLINE'))
     with open(os.path.join(GEN, 'nhd_ingest.cpp'), 'w') as f:
         f.write(open(os.path.join(CSRC, 'nhd_ingest.cpp')).read().replace('"../../include/nhd_b200.h"', '"%s"' % inc))
-    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-w',
+    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-w'] + \
+          (['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + [
            '-I', os.path.join(HERE, 'fake_cuda'), '-I', GEN, '-o', OUT,
            os.path.join(GEN, 'nhd_api.cpp'), os.path.join(GEN, 'nhd_ingest.cpp'), os.path.join(HERE, 'cuda_emu.cpp'), '-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -103,4 +107,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose=True))
+    print(build(force=True, verbose=True, asan='--asan' in sys.argv))

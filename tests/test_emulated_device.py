@@ -76,6 +76,67 @@ print('placed', int((ob['status'] == 0).sum()))
     assert res.stdout.split()[-2:] == ['placed', '768']
 
 
+RANK_CODE = '''
+import ctypes, os, sys, time
+import numpy as np
+sys.path.insert(0, %(root)r)
+ctypes.CDLL(%(nccl)r, mode=ctypes.RTLD_GLOBAL)            # soname libnccl.so.2: what the library resolves at run time
+import workload
+from nhd_b200.solver import Solver, nccl_unique_id
+rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+idf = os.path.join(tmp, 'nccl_id')
+if rank == 0:
+    nid = nccl_unique_id()
+    open(idf + '.tmp', 'wb').write(nid); os.rename(idf + '.tmp', idf)
+else:
+    t0 = time.time()
+    while not os.path.exists(idf):
+        time.sleep(0.02)
+        assert time.time() - t0 < 60
+    nid = open(idf, 'rb').read()
+recs, speed, pods, now = workload.make_workload(%(config)d, n_nodes=%(nodes)d, n_pods=%(pods)d)
+s = Solver(speed, rank=rank, world_size=world, nccl_id=nid)
+s.load_nodes(recs)
+b1 = s.solve_batch(pods[:len(pods) // 2], now[:len(pods) // 2])
+b2 = s.solve_batch(pods[len(pods) // 2:], now[len(pods) // 2:])
+np.save(os.path.join(tmp, 'bind%%d.npy' %% rank), np.concatenate([b1, b2]))
+np.save(os.path.join(tmp, 'final%%d.npy' %% rank), s.read_nodes())
+print('launches', s.timing()['n_launches'])
+s.close()
+'''
+
+
+@pytest.mark.parametrize('world,config', [(2, 3), (4, 5)])
+def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path, world, config):
+    """SURVEY 8e on the CPU: ``world`` processes, each with an emulated device and the full cluster, compute
+    their shard of the bitmaps, exchange them with one all-reduce (tests/emu/fake_nccl: shared memory instead
+    of NVLink) and run the identical sweep — every rank must return the oracle's bindings and records."""
+    import numpy as np
+    import workload
+    from tests import helpers
+    nccl_dir = os.path.join(ROOT, 'tests', 'emu', 'fake_nccl')
+    nccl = os.path.join(nccl_dir, 'libnccl.so.2')
+    src = os.path.join(nccl_dir, 'fake_nccl.c')
+    if not os.path.exists(nccl) or os.path.getmtime(nccl) < os.path.getmtime(src):
+        subprocess.run(['gcc', '-O2', '-fPIC', '-shared', '-w', '-Wl,-soname,libnccl.so.2', '-o', nccl, src, '-lrt'], check=True)
+    nodes, pods_n = 1800, 500                                       # 8 super-tiles of 256 nodes: uneven shards for 4 ranks
+    code = RANK_CODE % dict(root=ROOT, nccl=nccl, config=config, nodes=nodes, pods=pods_n)
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    procs = [subprocess.Popen([sys.executable, '-c', code, str(r), str(world), str(tmp_path)], cwd=ROOT, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, (o + e)[-2000:]
+    recs, speed, pods, now = workload.make_workload(config, n_nodes=nodes, n_pods=pods_n)
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now)
+    for r in range(world):
+        b = np.load(os.path.join(tmp_path, 'bind%d.npy' % r))
+        final = np.load(os.path.join(tmp_path, 'final%d.npy' % r))
+        assert helpers.binding_bytes_equal(ob, b), (r, helpers.first_binding_diff(ob, b))
+        assert final.tobytes() == orecs.tobytes(), r
+    assert (ob['status'] == 0).sum() > 100
+
+
 def test_emulator_catches_divergent_collectives(emu_cuda_lib, tmp_path):
     """The emulation is only worth something if it refuses what the GPU leaves undefined."""
     src = tmp_path / 'bad.cpp'

@@ -22,6 +22,8 @@ from tests import helpers, ref_compare, scenarios       # noqa: E402
 
 MODES = [dict(), dict(single_warp=True), dict(cpu_warps=1), dict(cpu_warps=2), dict(cpu_warps=3), dict(cpu_warps=5),
          dict(cpu_warps=7)]
+if os.environ.get('EMU_FUZZ_MODES'):                    # e.g. "1,2": only the one-warp sweep and one CPU-class warp
+    MODES = [MODES[int(i)] for i in os.environ['EMU_FUZZ_MODES'].split(',')]
 
 
 def one(recs, speed, pods, now, min_busy, mode, tag):

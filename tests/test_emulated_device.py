@@ -50,6 +50,14 @@ def test_gpu_suite_passes_on_the_emulated_device(emu_cuda_lib):
     assert 'failed' not in last and int(last.split()[0]) >= 60, last
 
 
+def test_driver_smoke_entry_point_on_the_emulated_device(emu_cuda_lib, oracle_lib):
+    """``__graft_entry__.smoke()`` — what the driver runs on the B200 before the bench — end to end."""
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    res = subprocess.run([sys.executable, '-c', 'import __graft_entry__ as g; g.smoke()'], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'smoke ok' in res.stdout, (res.stdout + res.stderr)[-2000:]
+
+
 def test_full_size_cluster_is_exact_on_the_emulated_device(emu_cuda_lib, oracle_lib):
     """BASELINE config 4 at its full 65 536 nodes: the first 768 pods of the stream through the real kernels, every
     binding and every final record against the oracle (``tools/emu_full_size.py`` does all 4 096 pods: equal)."""

@@ -124,12 +124,14 @@ def pick_threads(ob, recs, speed, pods, now, single_per_pod=None):
     best = (1, single_per_pod) if single_per_pod else None
     T = host_threads()
     tried = []
+    if T >= 2:
+        ob.solve(recs, speed, pods[:2], now[:2], threads=T)          # untimed: thread stacks, TLS, page faults
     for t in sorted({T, max(1, T // 2), max(1, T // 4), min(T, 16)}, reverse=True):
         if t < 2:
             continue
         t0 = time.perf_counter()
-        ob.solve(recs, speed, pods[:8], now[:8], threads=t)
-        per_pod = (time.perf_counter() - t0) / 8
+        ob.solve(recs, speed, pods[:12], now[:12], threads=t)
+        per_pod = (time.perf_counter() - t0) / 12
         tried.append((t, per_pod))
         if best is None or per_pod < best[1]:
             best = (t, per_pod)

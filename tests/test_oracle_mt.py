@@ -1,6 +1,5 @@
 """The multi-threaded CPU baseline (``nhd_oracle_solve_mt``: each pod's walk over the nodes split over
 host threads, pods still strictly in order) must give the plain oracle's result bit for bit."""
-import numpy as np
 import pytest
 
 from tests import helpers, ref_compare, scenarios

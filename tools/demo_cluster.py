@@ -25,7 +25,7 @@ import numpy as np                                       # noqa: E402
 from nhd_b200 import NHDRpcServer as R                   # noqa: E402
 from nhd_b200.NHDScheduler import NHDScheduler           # noqa: E402
 from nhd_b200.TriadCfgParser import TriadCfgParser       # noqa: E402
-from tests import fake_k8s, scenarios, triad_cfg         # noqa: E402
+from tests import fake_k8s, scenarios         # noqa: E402
 
 
 def main():

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
 import build_emu_cuda
 os.environ['NHD_B200_LIB']=build_emu_cuda.build(); os.environ['EMU_LANE_ORDER']='d'
-import numpy as np, workload
+import workload
 from nhd_b200.solver import Solver
 from oracle import binding
 from tests import helpers

@@ -137,6 +137,7 @@ namespace emu {
 void run_grid(const char* name, dim3 grid, dim3 block, size_t dyn_smem, std::function<void()> body)
 {
     if (g_blk) fail("nested kernel launch");
+    if ((block.x * block.y * block.z + 31) / 32 > 64) fail("blocks of more than 64 warps are not supported");
     if (dyn_smem > sizeof(nhd::smem)) fail("launch asks for %zu bytes of dynamic shared memory", dyn_smem);
     Block& b = g_block;
     const int n = (int)(block.x * block.y * block.z);
@@ -170,8 +171,22 @@ void run_grid(const char* name, dim3 grid, dim3 block, size_t dyn_smem, std::fun
              * that between two collectives the lanes of a warp always execute in that order — the closest a
              * run-to-the-next-collective emulation gets to a converged warp (see README in cuda_emu.h) */
             const int n_warps = (n + 31) / 32;
+            /* EMU_SCHED_SEED=<n>: the warps are visited in a pseudo-random order that changes every round, and a
+             * warp may be skipped for a round — other interleavings of the inter-warp protocols (turn counters,
+             * caches shared by several warps) than plain round-robin */
+            static const char* seed_env = getenv("EMU_SCHED_SEED");
+            static uint64_t rng = seed_env ? 0x9E3779B97F4A7C15ull * (uint64_t)(atoll(seed_env) + 1) : 0;
+            int order[64];
+            for (int i = 0; i < n_warps && i < 64; i++) order[i] = descending ? n_warps - 1 - i : i;
+            if (seed_env)
+                for (int i = n_warps - 1; i > 0; i--) {
+                    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                    const int j = (int)(rng % (uint64_t)(i + 1));
+                    const int tmp = order[i]; order[i] = order[j]; order[j] = tmp;
+                }
             for (int wk = 0; wk < n_warps && b.live > 0; wk++) {
-                const int wi = descending ? n_warps - 1 - wk : wk;
+                const int wi = order[wk];
+                if (seed_env) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; if ((rng & 3) == 0) { ran = true; continue; } }
                 const int lanes = (n - wi * 32) >= 32 ? 32 : n - wi * 32;
                 int restarts = 0;
                 for (int k = 0; k < lanes && b.live > 0; k++) {

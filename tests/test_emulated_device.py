@@ -50,6 +50,18 @@ def test_gpu_suite_passes_on_the_emulated_device(emu_cuda_lib):
     assert 'failed' not in last and int(last.split()[0]) >= 60, last
 
 
+@pytest.mark.parametrize('sched_seed', ['', '1', '2'], ids=['round_robin', 'shuffled1', 'shuffled2'])
+def test_every_sweep_mode_against_the_oracle_random(emu_cuda_lib, oracle_lib, sched_seed):
+    """tools/emu_fuzz.py: random clusters and pod streams, two batches per run, all seven sweep modes, with the
+    warps scheduled round-robin or in a shuffled order that changes every round."""
+    env = dict(os.environ, EMU_LANE_ORDER='d')
+    if sched_seed:
+        env['EMU_SCHED_SEED'] = sched_seed
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'emu_fuzz.py'), '7000', '42'], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and ' 0 mismatches' in res.stdout, (res.stdout + res.stderr)[-2000:]
+
+
 def test_driver_smoke_entry_point_on_the_emulated_device(emu_cuda_lib, oracle_lib):
     """``__graft_entry__.smoke()`` — what the driver runs on the B200 before the bench — end to end."""
     env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')

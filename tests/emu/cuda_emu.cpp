@@ -5,6 +5,9 @@
 
 dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+/* marks a library built on this emulation: nhd_b200/_lib.py refuses to load one unless the caller says so */
+extern "C" int nhd_emulated_device() { return 1; }
+
 namespace emu {
 
 Block* g_blk = nullptr;

@@ -105,3 +105,19 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), os.path.join(dirpath, f)
+
+
+def test_emulated_test_build_is_refused_by_the_loader():
+    """A CPU-emulated build of the library (tests/emu) must never stand in for the CUDA library by accident."""
+    import subprocess
+    import sys
+    emu = os.path.join(ROOT, 'tests', 'emu', '_emu_cuda.so')
+    if not os.path.exists(emu):
+        pytest.skip('emulated library not built yet (tests/test_emulated_device.py builds it)')
+    code = ('from nhd_b200 import _lib\n'
+            'try:\n    _lib.load(); print("LOADED")\n'
+            'except RuntimeError as e:\n    print("REFUSED" if "CPU-emulated" in str(e) else "OTHER")\n')
+    env = dict(os.environ, NHD_B200_LIB=emu)
+    env.pop('NHD_B200_ALLOW_EMULATED', None)
+    out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True).stdout
+    assert out.strip() == 'REFUSED'

@@ -34,7 +34,7 @@ def emu_cuda_lib():
 
 
 def _run_gpu_tests(lib, extra_env=None, select=None):
-    env = dict(os.environ, NHD_B200_LIB=lib, EMU_LANE_ORDER='d')
+    env = dict(os.environ, NHD_B200_LIB=lib, NHD_B200_ALLOW_EMULATED='1', EMU_LANE_ORDER='d')
     env.update(extra_env or {})
     cmd = [sys.executable, '-m', 'pytest', 'tests', '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider']
     if select:
@@ -64,7 +64,7 @@ def test_every_sweep_mode_against_the_oracle_random(emu_cuda_lib, oracle_lib, sc
 
 def test_driver_smoke_entry_point_on_the_emulated_device(emu_cuda_lib, oracle_lib):
     """``__graft_entry__.smoke()`` — what the driver runs on the B200 before the bench — end to end."""
-    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, NHD_B200_ALLOW_EMULATED='1', EMU_LANE_ORDER='d')
     res = subprocess.run([sys.executable, '-c', 'import __graft_entry__ as g; g.smoke()'], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and 'smoke ok' in res.stdout, (res.stdout + res.stderr)[-2000:]
@@ -90,7 +90,7 @@ assert len(recs) == 65536 and helpers.binding_bytes_equal(ob, b), helpers.first_
 assert final.tobytes() == orecs.tobytes()
 print('placed', int((ob['status'] == 0).sum()))
 ''' % ROOT
-    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, NHD_B200_ALLOW_EMULATED='1', EMU_LANE_ORDER='d')
     res = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, (res.stdout + res.stderr)[-2000:]
     assert res.stdout.split()[-2:] == ['placed', '768']
@@ -141,7 +141,7 @@ def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path,
         subprocess.run(['gcc', '-O2', '-fPIC', '-shared', '-w', '-Wl,-soname,libnccl.so.2', '-o', nccl, src, '-lrt'], check=True)
     nodes, pods_n = 1800, 500                                       # 8 super-tiles of 256 nodes: uneven shards for 4 ranks
     code = RANK_CODE % dict(root=ROOT, nccl=nccl, config=config, nodes=nodes, pods=pods_n)
-    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, EMU_LANE_ORDER='d')
+    env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, NHD_B200_ALLOW_EMULATED='1', EMU_LANE_ORDER='d')
     procs = [subprocess.Popen([sys.executable, '-c', code, str(r), str(world), str(tmp_path)], cwd=ROOT, env=env,
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
     outs = [p.communicate(timeout=600) for p in procs]

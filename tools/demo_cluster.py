@@ -17,6 +17,7 @@ if '--emulated' in sys.argv:
     sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
     import build_emu_cuda
     os.environ['NHD_B200_LIB'] = build_emu_cuda.build()
+    os.environ['NHD_B200_ALLOW_EMULATED'] = '1'
     os.environ.setdefault('EMU_LANE_ORDER', 'd')
 
 import grpc                                              # noqa: E402

@@ -7,7 +7,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
 import build_emu_cuda
-os.environ['NHD_B200_LIB']=build_emu_cuda.build(); os.environ['EMU_LANE_ORDER']='d'
+os.environ['NHD_B200_LIB']=build_emu_cuda.build()
+os.environ['NHD_B200_ALLOW_EMULATED'] = '1'; os.environ['EMU_LANE_ORDER']='d'
 import workload
 from nhd_b200.solver import Solver
 from oracle import binding

@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
 import build_emu_cuda                                   # noqa: E402
 os.environ['NHD_B200_LIB'] = build_emu_cuda.build()
+os.environ['NHD_B200_ALLOW_EMULATED'] = '1'
 os.environ.setdefault('EMU_LANE_ORDER', 'd')
 
 import numpy as np                                      # noqa: E402

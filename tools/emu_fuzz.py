@@ -2,6 +2,10 @@
 random clusters and pod streams, every sweep mode.  Developer tool; needs no GPU.
 
     python tools/emu_fuzz.py [first_seed] [n_seeds]
+
+Environment: EMU_SCHED_SEED=<n> shuffles the warp schedule, EMU_FUZZ_MODES="0,3,5" picks sweep modes, EMU_LIB_OVERRIDE=<.so>
+runs another emulated build (e.g. the sources compiled with -DNHD_CHECKS, which re-derives every result the sweep adopted
+ahead of its turn and traps on a difference: clean under shuffled schedules).
 """
 import os
 import sys
@@ -11,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
 import build_emu_cuda                                   # noqa: E402
-os.environ['NHD_B200_LIB'] = build_emu_cuda.build()
+os.environ['NHD_B200_LIB'] = os.environ.get('EMU_LIB_OVERRIDE') or build_emu_cuda.build()
 os.environ['NHD_B200_ALLOW_EMULATED'] = '1'
 os.environ.setdefault('EMU_LANE_ORDER', 'd')
 

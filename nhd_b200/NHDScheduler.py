@@ -107,6 +107,7 @@ class DeviceCluster:
         self.rewinds = 0
         self._last = None
         self.stubs = set()
+        self.unsupported_nodes: Dict[str, str] = {}
 
     @property
     def layout(self):
@@ -134,11 +135,14 @@ class DeviceCluster:
         for i, node in enumerate(nodes):
             try:
                 packing.pack_node(node, self._layout, out=recs[i])
-            except packing.UnsupportedError:
+            except packing.UnsupportedError as err:
                 # a node whose labels were refused stays in NHDScheduler.nodes, deactivated and half
-                # initialised (NHDScheduler.py:88-100); it holds its place in the order as an inactive stub
+                # initialised (NHDScheduler.py:88-100); it holds its place in the order as an inactive stub.
+                # An ACTIVE node beyond the packed limits (> 256 logical cores, > 16 GPUs, ...) cannot be
+                # described to the solver either: it is kept out of placement (never approximated) and named in
+                # unsupported_nodes for the operator.
                 if node.active:
-                    raise
+                    self.unsupported_nodes[node.name] = str(err)
                 recs[i] = np.zeros((), dtype=wire.NODE_DTYPE)
                 recs[i]['n_numa'] = 1
                 recs[i]['phys_cores'] = 1
@@ -201,11 +205,11 @@ class DeviceCluster:
 
 class _Pending:
     """One pending pod between the Kubernetes reads and the Kubernetes writes."""
-    __slots__ = ('pos', 'key', 'pobj', 'tcfg', 'top', 'groups', 'ready')
+    __slots__ = ('pos', 'key', 'pobj', 'tcfg', 'top', 'groups', 'ready', 'unsupported')
 
     def __init__(self, pos, key):
         self.pos, self.key = pos, key
-        self.pobj = self.tcfg = self.top = self.groups = None
+        self.pobj = self.tcfg = self.top = self.groups = self.unsupported = None
         self.ready = False
 
 
@@ -228,6 +232,7 @@ class NHDScheduler:
         self._log = logger
         self.pods_solved = 0
         self.assign_failed_nodes = set()
+        self.unsupported_pods = []                   # (ns, pod, why): requests beyond the packed layout's limits
         self.stats_from_device = stats_from_device
 
     # ---- small helpers --------------------------------------------------------------------
@@ -366,6 +371,10 @@ class NHDScheduler:
                                       f'Error while processing config for pod {podname}')
             return
         e.groups = self.k8s.GetPodNodeGroups(podname, ns)
+        try:                                         # a request beyond the packed layout (include/nhd_b200.h, NHD_MAX_*)
+            packing.pack_pod(e.top, e.groups, self.cluster.layout)
+        except packing.UnsupportedError as err:      # cannot be solved here and is never approximated: the pod fails,
+            e.unsupported = str(err)                 # loudly, instead of taking the scheduler thread down
 
     def _finish(self, e: _Pending, binding, now: float) -> bool:
         """``AttemptScheduling`` from the result of ``FindNode`` on (``:278-353``)."""
@@ -373,6 +382,13 @@ class NHDScheduler:
         if e.pobj is None or e.top is None:
             return False
         k8s, pobj, top, tcfg = self.k8s, e.pobj, e.top, e.tcfg
+        if e.unsupported is not None:
+            self._error(f'Pod {ns}.{podname} is outside the solver\'s limits: {e.unsupported}')
+            k8s.GeneratePodEvent(pobj, podname, ns, 'FailedScheduling', K8SEventType.EVENT_TYPE_WARNING,
+                                 f'Pod {podname} cannot be placed by the B200 solver: {e.unsupported}')
+            self.failed_schedule_count += 1
+            self.unsupported_pods.append((ns, podname, e.unsupported))
+            return False
         if binding is None or int(binding['node']) < 0:
             k8s.GeneratePodEvent(pobj, podname, ns, 'FailedScheduling', K8SEventType.EVENT_TYPE_WARNING,
                                  f'No valid candidate nodes found for scheduling pod {podname}')
@@ -452,7 +468,7 @@ class NHDScheduler:
                 if not e.ready:
                     self._prepare(e)
             now = float(self._clock())
-            solvable = [e for e in run if e.top is not None]
+            solvable = [e for e in run if e.top is not None and e.unsupported is None]
             bindings = {}
             if solvable and self.nodes:
                 self.cluster.sync(self.nodes, self._dirty)

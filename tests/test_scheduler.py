@@ -165,3 +165,29 @@ def test_scheduler_has_no_cpu_placement_path():
     s = NHDScheduler(k8s, lambda t, c: fake_k8s.JsonCfgParser(c, cfg_mod))
     with pytest.raises(SolverError):
         s.Startup()
+
+
+def test_requests_and_nodes_beyond_the_packed_limits_fail_loudly_not_fatally(oracle_lib):
+    """A pod asking for more than the packed layout can describe gets a FailedScheduling event and is listed; an
+    active node beyond the limits is kept out of placement and listed; everything else is scheduled as usual."""
+    from nhd_b200.NHDScheduler import NHDScheduler
+    import nhd_b200.CfgTopology as cfg_mod
+    from tests import fake_k8s, scenarios
+    nics = [('eth0', 100000, 0, 0x10), ('eth1', 100000, 1, 0x20)]
+    nodes = [scenarios.make_node('huge', 2, 192, True, 2, nics=nics),          # 384 logical cores > NHD_MAX_LCORES
+             scenarios.make_node('n1', 2, 32, True, 2, nics=nics), scenarios.make_node('n2', 2, 32, True, 2, nics=nics)]
+    k8s = fake_k8s.FakeK8s(nodes)
+    ok_pod = scenarios.make_pod([scenarios.make_group(pairs=((10, 10),), workers=2)], misc=1)
+    k8s.add_pod('a', 'fits', ok_pod, uid='u1')
+    k8s.add_pod('a', 'monster', scenarios.make_pod([scenarios.make_group(workers=80)]), uid='u2')   # > 72 cores per pod
+    k8s.add_pod('a', 'fits2', ok_pod, uid='u3')
+    s = NHDScheduler(k8s, lambda t, c: fake_k8s.JsonCfgParser(c, cfg_mod), solver_factory=helpers.OracleSolver,
+                     clock=H.Clock(1000.0))
+    s.Startup()
+    assert [b[1] for b in k8s.binds] == ['fits', 'fits2'] and all(b[2] in ('n1', 'n2') for b in k8s.binds)
+    assert 'huge' in s.cluster.unsupported_nodes and s.nodes['huge'].active
+    assert [p[1] for p in s.unsupported_pods] == ['monster'] and s.failed_schedule_count == 1
+    assert k8s.events[('a', 'monster')][-1][0] == 'FailedScheduling'
+    assert s.pod_state[('a', 'monster')]['state'].name == 'POD_STATUS_FAILED'
+    assert s.cluster.batches == 1
+    s.close()

@@ -33,6 +33,7 @@ any object with ``K8SMgr``'s method surface, ``cfg_parser(cfgtype, cfgstr)`` ret
 ``CfgToTopology / TopologyToCfg / TopologyToGpuMap`` (``TriadCfgParser``).  There is no CPU
 placement path: without the CUDA library ``DeviceCluster`` raises.
 """
+import re
 import time
 from enum import Enum
 from queue import Queue
@@ -473,7 +474,18 @@ class NHDScheduler:
             if solvable and self.nodes:
                 self.cluster.sync(self.nodes, self._dirty)
                 self._dirty.clear()
-                out = self.cluster.solve([e.top for e in solvable], [e.groups for e in solvable], now)
+                out = []
+                while solvable:
+                    try:
+                        out = self.cluster.solve([e.top for e in solvable], [e.groups for e in solvable], now)
+                        break
+                    except Exception as err:
+                        # a limit that depends on the cluster as well (numa^(groups+1) tuples, include/nhd_b200.h):
+                        # the library refuses the whole batch and names the pod; that pod fails loudly, the rest goes on
+                        m = re.search(r'pod (\d+)', str(err)) if getattr(err, 'code', None) == wire.ERR_UNSUPPORTED else None
+                        if m is None or int(m.group(1)) >= len(solvable):
+                            raise
+                        solvable.pop(int(m.group(1))).unsupported = str(err)
                 self.pods_solved += len(solvable)
                 bindings = {e.pos: out[i] for i, e in enumerate(solvable)}
             cut = None

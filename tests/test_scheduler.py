@@ -191,3 +191,29 @@ def test_requests_and_nodes_beyond_the_packed_limits_fail_loudly_not_fatally(ora
     assert s.pod_state[('a', 'monster')]['state'].name == 'POD_STATUS_FAILED'
     assert s.cluster.batches == 1
     s.close()
+
+
+@pytest.mark.gpu
+def test_cluster_dependent_limit_fails_one_pod_not_the_batch():
+    """4 processing groups on a cluster with a 4-NUMA node exceed the solver's tuple enumeration (4^5 > 256,
+    include/nhd_b200.h): the library refuses the batch naming the pod; the scheduler fails that pod and schedules
+    the others."""
+    from nhd_b200.NHDScheduler import NHDScheduler
+    import nhd_b200.CfgTopology as cfg_mod
+    from tests import fake_k8s, scenarios
+    nics4 = [(f'eth{k}', 100000, k, 0x10 * (k + 1)) for k in range(4)]
+    nodes = [scenarios.make_node('quad', 4, 64, True, 1, nics=nics4),
+             scenarios.make_node('n1', 2, 32, True, 2, nics=nics4[:2]), scenarios.make_node('n2', 2, 32, True, 2, nics=nics4[:2])]
+    k8s = fake_k8s.FakeK8s(nodes)
+    small = scenarios.make_pod([scenarios.make_group(pairs=((10, 10),), workers=1)], misc=1)
+    four = scenarios.make_pod([scenarios.make_group(pairs=((5, 5),), workers=1) for _ in range(4)], misc=1)
+    for i, pod in enumerate([small, four, small, four, small]):
+        k8s.add_pod('a', f'p{i}', pod, uid=f'u{i}')
+    s = NHDScheduler(k8s, lambda t, c: fake_k8s.JsonCfgParser(c, cfg_mod), clock=H.Clock(1000.0))
+    try:
+        s.Startup()
+        assert [b[1] for b in k8s.binds] == ['p0', 'p2', 'p4']
+        assert [p[1] for p in s.unsupported_pods] == ['p1', 'p3'] and s.failed_schedule_count == 2
+        assert 'tuple' in s.unsupported_pods[0][2]
+    finally:
+        s.close()

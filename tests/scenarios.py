@@ -245,3 +245,46 @@ def random_scenario(seed, n_nodes=8, n_pods=24, flavor='mixed', min_busy_secs=30
         t += 0.0 if r < 0.5 else (float(rng.integers(1, 20)) if r < 0.9 else 31.0)
         now.append(t)
     return {'nodes': nodes, 'pods': pods, 'now': now, 'min_busy_secs': min_busy_secs}
+
+
+# ----------------------------------------------------------------------------------
+# objects near the packed layout's limits (include/nhd_b200.h: 256 logical cores, 16 GPUs, 32 NICs per
+# node; 72 cores per pod; numa^(groups+1) <= 256 tuples)
+# ----------------------------------------------------------------------------------
+def huge_node(rng, name):
+    sockets = int(rng.choice([1, 2, 4]))
+    phys = int(rng.choice([64, 96, 128]))
+    smt = bool(rng.random() < 0.7)
+    n_gpu = int(rng.choice([0, 8, 16]))
+    gpus = [(d, d * sockets // max(1, n_gpu), 0x10 * (d * sockets // max(1, n_gpu) + 1) + (d % 4)) for d in range(n_gpu)]
+    n_nic = int(rng.choice([2, 8, 16, 32]))
+    nics = [(f'vf{i}', int(rng.choice([25000, 100000, 40000])), i % sockets, 0x10 * ((i % sockets) + 1) + (i % 4))
+            for i in range(n_nic)]
+    return make_node(name, sockets, phys, smt, int(rng.integers(0, 3)), gpus, nics, (), None, hp_alloc=128)
+
+
+def huge_pod(rng):
+    G = int(rng.integers(1, 4))                      # 4 groups on a 4-NUMA node would exceed the tuple limit
+    gpu = rng.random() < 0.5
+    pci = gpu and rng.random() < 0.5
+    groups, budget = [], 72 - 3
+    for g in range(G):
+        pairs = [(int(rng.choice([0, 5, 10, 20])), int(rng.choice([0, 5, 10]))) for _ in range(int(rng.integers(0, 3)))]
+        feeders = [int(rng.integers(0, 3)) for _ in range((1 if pci else int(rng.integers(0, 3))) if gpu else 0)]
+        w, h = int(rng.integers(0, 8)), int(rng.integers(0, 4))
+        need = 2 * len(pairs) + w + h + sum(feeders)
+        if need > budget // (G - g):
+            w = max(0, w - (need - budget // (G - g)))
+            need = 2 * len(pairs) + w + h + sum(feeders)
+        budget -= need
+        groups.append(make_group(pairs, w, feeders, h, bool(rng.random() < 0.5), bool(rng.random() < 0.5)))
+    return make_pod(groups, int(rng.integers(0, 4)), bool(rng.random() < 0.5), 'PCI' if pci else 'NUMA',
+                    int(rng.choice([0, 2, 8])))
+
+
+def huge_scenario(seed, min_busy_secs=30.0):
+    rng = np.random.default_rng(seed)
+    n_pods = int(rng.integers(20, 120))
+    now = [1000.0] * n_pods if seed % 2 else [float(x) for x in 1000.0 + np.cumsum(rng.integers(0, 12, n_pods))]
+    return {'nodes': [huge_node(rng, f'n{i}') for i in range(int(rng.integers(3, 20)))],
+            'pods': [huge_pod(rng) for _ in range(n_pods)], 'now': now, 'min_busy_secs': min_busy_secs}

@@ -55,6 +55,22 @@ def test_random_scenarios_match_oracle(oracle_lib, solver_mod, flavor):
     assert placed > 100
 
 
+def test_objects_near_the_packed_limits_match_oracle(oracle_lib, solver_mod):
+    """Nodes with up to 256 logical cores, 16 GPUs, 32 NICs and 1 / 2 / 4 NUMA nodes; pods with up to 3 groups and
+    72 cores (include/nhd_b200.h NHD_MAX_*), constant and moving clocks, every sweep mode."""
+    placed = 0
+    for seed in range(24):
+        scn = scenarios.huge_scenario(81000 + seed, min_busy_secs=30.0 if seed % 3 else 0.0)
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        ob, orecs = oracle_lib.solve(recs, layout.speed_table(), pods, now, min_busy_secs=scn['min_busy_secs'])
+        cb, crecs, _ = _run_cuda(solver_mod, recs, layout.speed_table(), pods, now, min_busy=scn['min_busy_secs'],
+                                 extra_cpu_warps=(2, 5) if seed % 2 else ())
+        assert helpers.binding_bytes_equal(ob, cb), (seed, helpers.first_binding_diff(ob, cb))
+        assert orecs.tobytes() == crecs.tobytes(), (seed, ref_compare.diff_records(orecs, crecs)[:3])
+        placed += int((ob['status'] == 0).sum())
+    assert placed > 500
+
+
 def test_filter_kernel_matches_oracle_candidates(oracle_lib, solver_mod):
     """F[type][node] from filter_kernel == filts[1] membership after IntersectResources
     (busy window aside), on partially filled clusters, plus the NOGPU / BUSY bitmaps."""

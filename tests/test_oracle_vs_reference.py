@@ -49,3 +49,23 @@ def test_mirror_node_ingest_matches_reference_labels(oracle_lib):
                     x.sockets, x.numa_nodes, x.smt_enabled, x.cores_per_proc) == \
                 (y.groups, y.maintenance, y.data_vlan, y.gwip, y.mem.free_hugepages_gb, y.reserved_cores,
                  y.sockets, y.numa_nodes, y.smt_enabled, y.cores_per_proc)
+
+
+def test_oracle_matches_live_reference_near_the_limits(oracle_lib):
+    """Nodes with up to 256 logical cores / 16 GPUs / 32 NICs / 4 NUMA nodes and pods with up to 72 cores: the
+    reference itself is slow here (seconds per pod), so a few short streams."""
+    attempts = placed = 0
+    for seed in range(3):
+        scn = scenarios.huge_scenario(81000 + seed, min_busy_secs=30.0 if seed % 3 else 0.0)
+        scn['nodes'], scn['pods'], scn['now'] = scn['nodes'][:5], scn['pods'][:14], scn['now'][:14]
+        outs, init, final, layout, names = ref_compare.run_reference(scn)
+        recs, pods, now, layout2 = ref_compare.pack_scenario(scn)
+        assert ref_compare.records_equal(recs, init)
+        b, orecs = oracle_lib.solve(recs, layout2.speed_table(), pods, now, min_busy_secs=scn['min_busy_secs'])
+        for i, (o, bb) in enumerate(zip(outs, b)):
+            errs = ref_compare.diff_outcome(o, bb)
+            assert not errs, (seed, i, errs)
+            attempts += 1
+            placed += o['status'] == 'placed'
+        assert not ref_compare.diff_records(orecs, final), seed
+    assert attempts == 42 and placed > 20

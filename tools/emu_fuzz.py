@@ -60,7 +60,10 @@ def main():
         scn = scenarios.random_scenario(90000 + seed, n_nodes=int(rng.integers(3, 70)), n_pods=int(rng.integers(10, 160)),
                                         flavor=flavor, max_groups=4 if flavor != 'wild' else 3,
                                         min_busy_secs=float(rng.choice([30.0, 0.0])))
-        if seed % 3:
+        if seed % 6 == 1:                                     # objects near the packed layout's limits
+            scn = scenarios.huge_scenario(70000 + seed, float(rng.choice([30.0, 0.0])))
+            flavor = 'huge'
+        elif seed % 3:
             scn['now'] = [1000.0] * len(scn['now'])           # constant clock: the multi-warp sweep
         recs, pods, now, layout = ref_compare.pack_scenario(scn)
         mode = MODES[seed % len(MODES)]

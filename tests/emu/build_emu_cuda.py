@@ -77,10 +77,12 @@ static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint6
     return text.replace('#include "nhd_core.cuh"\n', '#include "nhd_core.cuh"\n' + shim, 1)
 
 
-def build(force=False, verbose=False, asan=False):
+def build(force=False, verbose=False, asan=False, ubsan=False):
     """``asan``: a second library with AddressSanitizer (out-of-bounds accesses to emulated device memory);
-    run it with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0."""
-    OUT = os.path.join(HERE, '_emu_cuda_asan.so' if asan else '_emu_cuda.so')
+    run it with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0.
+    ``ubsan``: a library that aborts on misaligned accesses (a uint4 load from an address that is not a multiple of 16
+    is a fault on the GPU and silent on x86) and on out-of-range indices into fixed-size arrays."""
+    OUT = os.path.join(HERE, '_emu_cuda_asan.so' if asan else '_emu_cuda_ubsan.so' if ubsan else '_emu_cuda.so')
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(GEN, exist_ok=True)
@@ -95,7 +97,8 @@ def build(force=False, verbose=False, asan=False):
     with open(os.path.join(GEN, 'nhd_ingest.cpp'), 'w') as f:
         f.write(open(os.path.join(CSRC, 'nhd_ingest.cpp')).read().replace('"../../include/nhd_b200.h"', '"%s"' % inc))
     cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-w'] + \
-          (['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + [
+          (['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + \
+          (['-fsanitize=alignment,bounds', '-fno-sanitize-recover=all'] if ubsan else []) + [
            '-I', os.path.join(HERE, 'fake_cuda'), '-I', GEN, '-o', OUT,
            os.path.join(GEN, 'nhd_api.cpp'), os.path.join(GEN, 'nhd_ingest.cpp'), os.path.join(HERE, 'cuda_emu.cpp'), '-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -107,4 +110,4 @@ def build(force=False, verbose=False, asan=False):
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose=True, asan='--asan' in sys.argv))
+    print(build(force=True, verbose=True, asan='--asan' in sys.argv, ubsan='--ubsan' in sys.argv))

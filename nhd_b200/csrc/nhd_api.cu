@@ -629,6 +629,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
                       (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16;
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
+        if (T <= SWEEP_TYPES_SMEM_MAX) smem += (size_t)T * sizeof(TSlot);
         const size_t with_bitmaps = smem + bm_bytes;
         if (with_bitmaps <= (size_t)h->smem_optin) {
             sweep_kernel<true><<<1, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);

@@ -352,7 +352,7 @@ constexpr int SPMEMO_SLOTS = 1024;                /* NIC sub-problem memo (16 B 
 constexpr int DCACHE_SLOTS = 512;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
 #ifndef NHD_DEFAULT_CPU_WARPS
-#define NHD_DEFAULT_CPU_WARPS 3              /* CPU-only pod class: warps that work ahead of the committing one */
+#define NHD_DEFAULT_CPU_WARPS 7              /* CPU-only pod class: the committing warp + 6 workers (standing decisions per type) */
 #endif
 
 struct SweepArgs {
@@ -1039,7 +1039,7 @@ __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepC
  * binding header (the core ids follow in assign_cores_kernel).  Returns true when placed.
  */
 __device__ __forceinline__ bool apply_decision(const SweepCtx& cx, const PodType& t, int node, NodeDyn& d, const PMap& pm,
-                                               const Picks& pk, double now, nhd_binding* bout)
+                                               const Picks& pk, double now, nhd_binding* bout, int chunks = 8)
 {
     const int G = t.G;
     const bool smt_node = (d.info & NHD_DYN_SMT) != 0;
@@ -1086,7 +1086,7 @@ __device__ __forceinline__ bool apply_decision(const SweepCtx& cx, const PodType
     else if (cx.lane == 1) v = make_uint4(w4, w5, w6, w7);
     else if (cx.lane == 2) v = make_uint4(w8, w9, (uint32_t)pk.gi_lo, (uint32_t)(pk.gi_lo >> 32));
     else if (cx.lane == 3) v = make_uint4((uint32_t)pk.gi_hi, (uint32_t)(pk.gi_hi >> 32), w14, 0);
-    if (cx.lane < 8) reinterpret_cast<uint4*>(bout)[cx.lane] = v;
+    if (cx.lane < chunks) reinterpret_cast<uint4*>(bout)[cx.lane] = v;      /* chunks 4..7 are zero until the core ids */
     return !fail;
 }
 
@@ -1103,6 +1103,107 @@ __device__ __noinline__ void resolve_pending(const SweepArgs& a, const SweepCtx&
     apply_decision(cx, tjy, node, du.d, pmj, pkj, du.d.busy_time, bout);
     store_dyn(a, cx, node, du);
     __syncwarp();
+}
+
+/*
+ * Standing decision of one CPU-only pod type (multi-warp sweep).  A worker warp that owns the type keeps this
+ * slot current: the type's first-fit node on the GPU-less pass (first set bit of F[t] & NOGPU), the node's
+ * summary it evaluated, the summary after a pod of the type has been placed there, and the binding header.
+ * All of that is a pure function of (type, node, summary).  The committing warp — the only one that walks
+ * the CPU-only pods, in pod order — adopts the slot iff the node's summary is bit for bit `before` (bits of
+ * F[t] are only ever cleared inside a batch, so a first set bit that is still set is still the first);
+ * otherwise it kicks the worker and waits for a fresh one.  The slot is a seqlock (odd = being rewritten).
+ */
+struct TSlot {
+    int seq;                 /* even: stable, odd: the worker is rewriting the slot                     */
+    int node;                /* first-fit node the decision was worked out for                          */
+    int kind;                /* 0 nothing yet, 1 decision available, 2 GPU-less pass exhausted (final)  */
+    int wake;                /* set by the committing warp: the node changed, work the type out again   */
+    uint4 before[2];         /* NodeDyn the decision was evaluated on                                   */
+    uint4 after[2];          /* NodeDyn once the pod is placed                                          */
+    uint4 bind[4];           /* first 64 bytes of the nhd_binding (the rest is zero until the core ids) */
+};
+static_assert(sizeof(TSlot) == 144, "TSlot is nine 16-byte chunks");
+
+__device__ __forceinline__ void vol_store(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+
+/*
+ * Worker warp: bring the standing decision of CPU-only type ti up to date against the current state.
+ * Nodes that do not fit lose their bit for good (resources only shrink inside a batch, and a summary read
+ * while it was being updated is never below the current one in any resource); a node that fits is published
+ * together with the summary it was evaluated on, which the committing warp compares with the node's actual
+ * summary before it uses the result.
+ */
+template <bool SMEM_BITMAPS>
+__device__ __forceinline__ void worker_refresh(const SweepArgs& a, const SweepCtx& cx, TSlot* sl, int ti, const PodType& t,
+                                               uint64_t* F, const uint64_t* NOGPU, int W, int32_t* cursor, double now)
+{
+    const int lane = cx.lane;
+    int seq = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);          /* only this warp ever writes it */
+    for (;;) {
+        __syncwarp();
+        /* first candidate of the GPU-less pass (Matcher.py:412-416) */
+        int c = __shfl_sync(0xFFFFFFFFu, ld_vol(cursor), 0);
+        const int c_in = c;
+        uint64_t raw = 0;
+        while (c < W) {
+            raw = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
+            raw = __shfl_sync(0xFFFFFFFFu, raw, 0);
+            if (raw) break;
+            int found = W;
+            for (int base = c + 1; base < W; base += 32) {
+                const int w = base + lane;
+                const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) : 0;
+                const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                if (nz) { found = base + ctz32(nz); break; }
+            }
+            c = found;
+        }
+        if (c != c_in && lane == 0) vol_store(cursor, c);          /* a lower bound stays one: bits are only cleared */
+        if (c >= W) {
+            /* nothing left on GPU-less nodes: pods of this type spill (ordinary path of the committing warp) */
+            if (lane == 0) vol_store(&sl->seq, seq + 1);
+            __threadfence_block();
+            if (lane == 0) { vol_store(&sl->node, -1); vol_store(&sl->kind, 2); }
+            __threadfence_block();
+            if (lane == 0) vol_store(&sl->seq, seq + 2);
+            __syncwarp();
+            return;
+        }
+        const int node = c * 64 + ctz64(raw);
+        DynU ds;
+        if (!spec_load_dyn(a, cx, node, ds)) continue;
+        PMap pms = {0, 0, 0, 0};
+        Picks pks;
+        pks.fail_status = 0;
+        bool ms;
+        const int st = __shfl_sync(0xFFFFFFFFu, resolve_decision(a, cx, ti, t, node, ds, pms, pks, ms), 0);
+        if (st < 2) {
+            if (lane == 0) bit_clear(F, node);
+            continue;
+        }
+        /* publish */
+        __syncwarp();
+        if (lane == 0) vol_store(&sl->seq, seq + 1);
+        __threadfence_block();
+        __syncwarp();
+        DynU da;
+        da.q[0] = ds.q[0]; da.q[1] = ds.q[1];
+        apply_decision(cx, t, node, da.d, pms, pks, now, reinterpret_cast<nhd_binding*>(sl->bind), 4);
+        {
+            const uint4 hb = lane == 0 ? ds.q[0] : ds.q[1], ha = lane == 0 ? da.q[0] : da.q[1];
+            if (lane < 2) { sl->before[lane] = hb; sl->after[lane] = ha; }
+        }
+        if (lane == 0) { vol_store(&sl->node, node); vol_store(&sl->kind, 1); }
+        __threadfence_block();
+        __syncwarp();
+        seq += 2;
+        if (lane == 0) vol_store(&sl->seq, seq);
+        __syncwarp();
+        /* the node may have been committed to while it was being worked out: look once more */
+        DynU dc;
+        if (spec_load_dyn(a, cx, node, dc) && same_dyn(dc, ds)) return;
+    }
 }
 
 /*
@@ -1129,11 +1230,13 @@ sweep_kernel(const SweepArgs a)
     const int W = a.words, T = a.n_types;
     const int wid = tid >> 5;
     const int dual = a.dual;
-    /* multi-warp mode: warps 0..ncw-1 walk the CPU-only pods, warp ncw the GPU pods; the CPU class shares one
-     * summary cache, the GPU warp has its own */
+    /* multi-warp mode: warp 0 walks (commits) the CPU-only pods, warps 1..ncw-1 keep one standing decision per
+     * CPU-only pod type current (TSlot), warp ncw walks the GPU pods; the CPU class shares one summary cache,
+     * the GPU warp has its own */
     const int ncw = dual ? (a.n_cpu_warps & 0xFF) : 0;
-    const int dbg = a.n_cpu_warps >> 8;       /* debug switches: 1 = never adopt, 2 = never speculate */
+    const int dbg = a.n_cpu_warps >> 8;       /* debug switches: 1 = never adopt, 2 = no worker warps */
     const int is_gpu_warp = dual && wid == ncw;
+    const bool is_worker = dual && wid >= 1 && wid < ncw;
     /* decision memo (48-byte entries, generic path): half for the GPU-pod warp, which lives on it; the CPU-only
      * warps (direct path, rarely here) share the other half in equal power-of-two slices */
     const int cpu_slices = ncw <= 1 ? 1 : (ncw <= 2 ? 2 : (ncw <= 4 ? 4 : 8));
@@ -1155,13 +1258,13 @@ sweep_kernel(const SweepArgs a)
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
     cx.dtag = dtag_all + is_gpu_warp * (DCACHE_SLOTS / 2);
     cx.peer_dtag = dual ? dtag_all + (1 - is_gpu_warp) * (DCACHE_SLOTS / 2) : nullptr;
-    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods committed and fenced, [1] GPU pods finished, [2] CPU-only pods committed (the turn) */
+    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods committed and fenced, [1] GPU pods finished, [2] set once every CPU-only pod is in (the worker warps leave) */
     ClsNic* clsnic_all = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);     /* CLSNIC_SLOTS x 48 B */
     uint4* spmemo_all = reinterpret_cast<uint4*>(clsnic_all + CLSNIC_SLOTS);         /* SPMEMO_SLOTS x 16 B */
     cx.clsnic = clsnic_all;
     cx.clsnic_lock = const_cast<int*>(reinterpret_cast<volatile int*>(&done[3]));
     cx.spmemo = spmemo_all;
-    cx.write_back = dual && !is_gpu_warp && ncw > 1;
+    cx.write_back = dual && !is_gpu_warp && ncw > 1;      /* the workers read the summary cache while warp 0 updates it */
     uint8_t* p0 = reinterpret_cast<uint8_t*>(spmemo_all + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
@@ -1172,7 +1275,9 @@ sweep_kernel(const SweepArgs a)
     cx.s_needb = cx.types_in_smem ? s_needb : nullptr;
     uint8_t* p2 = reinterpret_cast<uint8_t*>(s_needb) + (cx.types_in_smem ? (size_t)T * 128 : 0);
     int32_t* s_cursors = reinterpret_cast<int32_t*>(p2);                        /* [T][3] */
-    uint64_t* s_touched = reinterpret_cast<uint64_t*>(p2 + (((size_t)T * 3 * 4 + 15) & ~(size_t)15));   /* [W] */
+    uint8_t* p3 = p2 + (((size_t)T * 3 * 4 + 15) & ~(size_t)15);
+    TSlot* slots = reinterpret_cast<TSlot*>(p3);                                /* [T] standing decisions (types in shared memory only) */
+    uint64_t* s_touched = reinterpret_cast<uint64_t*>(p3 + (cx.types_in_smem ? (size_t)T * sizeof(TSlot) : 0));   /* [W] */
     uint64_t* s_bitmaps = s_touched + W;
 
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
@@ -1181,6 +1286,9 @@ sweep_kernel(const SweepArgs a)
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) done[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
+    if (cx.types_in_smem)
+        for (int i = tid; i < T * (int)(sizeof(TSlot) / 16); i += SWEEP_THREADS)     /* seq 0, node -1, kind 0, wake 1 */
+            reinterpret_cast<uint4*>(slots)[i] = (i % (int)(sizeof(TSlot) / 16)) == 0 ? make_uint4(0, 0xFFFFFFFFu, 0, 1) : make_uint4(0, 0, 0, 0);
     if (cx.types_in_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.types);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_types);
@@ -1247,6 +1355,40 @@ sweep_kernel(const SweepArgs a)
         all_gpus = ty.total_gpus > all_gpus ? ty.total_gpus : all_gpus;
     }
 
+    /* standing decisions need the types in shared memory and the node-group gate folded into them */
+    const bool use_workers = dual && ncw > 1 && !multi && cx.types_in_smem && !(dbg & 2);
+    if (is_worker) {
+        if (!use_workers) return;
+        /* the CPU-only types this warp owns: every (ncw-1)-th of them */
+        unsigned long long mine = 0;
+        {
+            int rank = 0;
+            for (int tt = 0; tt < T; tt++) {
+                if (types[tt].needs_gpu || !types[tt].valid_map) continue;
+                if ((rank++ % (ncw - 1)) == wid - 1) mine |= 1ULL << tt;
+            }
+        }
+        const double now0 = a.now[0];
+        while (mine) {
+            __syncwarp();
+            if (__shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0)) break;     /* every CPU-only pod is in */
+            bool any = false;
+            for (unsigned long long m = mine; m; m &= m - 1) {
+                const int tt = ctz64(m);
+                TSlot* sl = &slots[tt];
+                if (!__shfl_sync(0xFFFFFFFFu, ld_vol(&sl->wake), 0)) continue;
+                /* the flag goes down before the state is read: a commit after this point raises it again */
+                if (lane == 0) vol_store(&sl->wake, 0);
+                __threadfence_block();
+                __syncwarp();
+                worker_refresh<SMEM_BITMAPS>(a, cx, sl, tt, types[tt], BM + (size_t)tt * W, NOGPU, W, &cursors[tt * 3 + 0], now0);
+                any = true;
+            }
+            if (!any && lane == 0) __nanosleep(20);
+        }
+        return;
+    }
+
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
     int n_busy = 0;
     for (int w0 = 0; w0 < W && !dual; w0 += 32) {      /* (two-warp mode runs on a constant clock: no list needed) */
@@ -1286,7 +1428,6 @@ sweep_kernel(const SweepArgs a)
         const uint32_t below = (1u << j) - 1;
         const int before_cpu = base_cpu + popc32(in_chunk & ~gpu_bits & below);   /* pods of each class ahead of this one */
         const int before_gpu = base_gpu + popc32(gpu_bits & below);
-        if (dual && my_class == 0 && ncw > 1 && (before_cpu % ncw) != wid) continue;   /* another CPU warp's pod */
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
@@ -1297,118 +1438,86 @@ sweep_kernel(const SweepArgs a)
         uint64_t* F = BM + (size_t)ti * W;
 
         /*
-         * ---- speculation (CPU-only class, several warps) ----
-         * While earlier CPU-only pods are still being committed by the other warps, this warp already works
-         * its pod out against the current state: first-fit target (first set bit of F[t] & NOGPU), decision,
-         * binding record, the summary after the pod and the types the node no longer fits.  All of that is a
-         * pure function of (type, node, summary).  When its turn comes the result is adopted iff the target
-         * bit is still set (bits are only ever cleared inside a batch, so a first set bit that is still set
-         * is still the first) and the node's summary is bit for bit the one that was evaluated; otherwise
-         * the pod takes the ordinary path below.  While waiting, a result that went stale is redone at once.
+         * ---- adoption (CPU-only pod whose type has a standing decision) ----
+         * The worker warps keep, per CPU-only type, the type's first-fit node on the GPU-less pass, the summary
+         * it was evaluated on, the summary after the pod and the binding header (TSlot).  The slot is used iff
+         * the node's summary is still bit for bit the evaluated one (and the bit is still set: bits are only ever
+         * cleared inside a batch, so a first set bit that is still set is still the first); otherwise the worker
+         * is kicked and this warp waits for the fresh result.  Pods are committed strictly in pod order, here.
          */
-        bool adopted = false;
-        if (dual && my_class == 0 && ncw > 1) {
-            int n_spec = -1;                       /* node the pod has been worked out for (ds -> da), else -1 */
-            bool gave_up = !t.valid_map || multi || (dbg & 2);
-            bool sp_eager = false, inv0 = false, inv1 = false;
-            DynU ds, da;
-            bool wait = false;
-            int seen_trn = -1;
+        bool adopted = false, n_touched = false;
+        int n_adopt = -1;
+        if (use_workers && my_class == 0 && t.valid_map && !(dbg & 1)) {
+            TSlot* sl = &slots[ti];
+            DynU db, da;
+            uint4 vbind = make_uint4(0, 0, 0, 0);
             for (;;) {
                 __syncwarp();
-                if (wait) {
-                    /* only a commit can change anything this warp looks at: sleep on the turn counter rather than
-                     * poll the state (idle polling would crowd the working warps out of the shared-memory pipe) */
-                    if (lane == 0) while (ld_vol((const volatile int*)&done[2]) == seen_trn) __nanosleep(20);
-                    __syncwarp();
-                    wait = false;
+                const int s1 = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);
+                if (s1 & 1) { if (lane == 0) __nanosleep(20); continue; }
+                const int kind = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->kind), 0);
+                const int node = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->node), 0);
+                db.q[0] = sl->before[0]; db.q[1] = sl->before[1];
+                da.q[0] = sl->after[0]; da.q[1] = sl->after[1];
+                if (lane < 4) vbind = sl->bind[lane];
+                __threadfence_block();
+                const int s2 = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);
+                if (s2 != s1) continue;
+                if (kind == 2) break;                                    /* GPU-less pass exhausted: ordinary path (spill) */
+                bool ok = kind == 1;
+                if (ok) {
+                    /* lane 0's view decides (other warps clear bits of these words) */
+                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[node >> 6])[(node >> 5) & 1], 0);
+                    ok = ((fw >> (node & 31)) & 1) != 0;
                 }
-                const int trn = __shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0);
-                seen_trn = trn;
-                const bool my_turn = trn >= before_cpu;
-                if (n_spec >= 0) {
-                    /* still this pod's first fit, and still in the state it was worked out on?  (every word another
-                     * warp may change is read by lane 0 for all: lanes must not see different values and part ways) */
-                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[n_spec >> 6])[(n_spec >> 5) & 1], 0);
-                    bool ok = ((fw >> (n_spec & 31)) & 1) != 0;
-                    DynU dc;
-                    if (ok) ok = spec_load_dyn(a, cx, n_spec, dc) && same_dyn(dc, ds);
-                    if (!ok) { n_spec = -1; PROF_COUNT(14); }
-                }
-                if (my_turn) break;                          /* validated (or not) under the ticket: nobody else commits now */
-                if (n_spec >= 0 || gave_up) { wait = true; continue; }
-                /* first candidate of pass 0 */
-                int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + 0], 0);
-                const int c_in = c;
-                uint64_t raw = 0;
-                while (c < W) {
-                    raw = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
-                    raw = __shfl_sync(0xFFFFFFFFu, raw, 0);
-                    if (raw) break;
-                    int found = W;
-                    for (int base = c + 1; base < W; base += 32) {
-                        const int w = base + lane;
-                        const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) : 0;
-                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
-                        if (nz) { found = base + ctz32(nz); break; }
+                if (ok) {
+                    /* the node's summary now: the cache (this warp is its only writer), else the snapshot if no pod of
+                     * the batch was bound there, else HBM (evicted) */
+                    const int cs = node & cx.dcache_mask;
+                    n_touched = ((s_touched[node >> 6] >> (node & 63)) & 1) != 0;
+                    if (cx.dtag[cs] == node) {
+                        DynU dc;
+                        dc.q[0] = cx.dcache[2 * cs]; dc.q[1] = cx.dcache[2 * cs + 1];
+                        ok = same_dyn(dc, db);
+                    } else if (n_touched) {
+                        DynU dc;
+                        dc.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); dc.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]);
+                        ok = same_dyn(dc, db);
                     }
-                    c = found;
+                    ok = __shfl_sync(0xFFFFFFFFu, (int)ok, 0) != 0;
                 }
-                if (c != c_in) cursors[ti * 3 + 0] = c;     /* a lower bound stays one: bits are only cleared */
-                if (c >= W) { gave_up = true; continue; }    /* will spill: ordinary path */
-                const int node = c * 64 + ctz64(raw);
-                if (!spec_load_dyn(a, cx, node, ds)) continue;
-                CHK_SANE(ds, node, 7);
-                PMap pms = {0, 0, 0, 0};
-                Picks pks;
-                pks.fail_status = 0;
-                bool ms;
-                const int st = __shfl_sync(0xFFFFFFFFu, resolve_decision(a, cx, ti, t, node, ds, pms, pks, ms), 0);
-                if (st < 2) { gave_up = true; continue; }    /* stale candidate: the committing pass clears it */
-                da.q[0] = ds.q[0]; da.q[1] = ds.q[1];
-                const bool sp_placed = apply_decision(cx, t, node, da.d, pms, pks, now, bout);
-                sp_eager = false; inv0 = inv1 = false;
-                if (eager && sp_placed) {
-                    const NodeDyn& nd = da.d;
-                    const int sum = nd.fc[0] + nd.fc[1] + nd.fc[2] + nd.fc[3];
-                    int mx = nd.fc[0] > nd.fc[1] ? nd.fc[0] : nd.fc[1];
-                    const int mx2 = nd.fc[2] > nd.fc[3] ? nd.fc[2] : nd.fc[3];
-                    mx = mx > mx2 ? mx : mx2;
-                    const uint32_t alln = nd.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << nd.n_nics) - 1);
-                    const bool roomy = sum >= all_need && mx >= all_big && nd.free_hugepages_gb >= all_hp && (nd.nic_inuse & alln) != alln;
-                    if (!roomy) {
-                        sp_eager = true;
-                        inv0 = lane < T && summary_infeasible(types[lane], da.d);
-                        inv1 = lane + 32 < T && summary_infeasible(types[lane + 32], da.d);
-                    }
+                if (ok) { n_adopt = node; break; }
+                /* nothing yet, or worked out on a summary that has changed since: have it redone */
+                PROF_COUNT(14);
+                if (lane == 0) {
+                    vol_store(&sl->wake, 1);
+                    while (ld_vol(&sl->seq) == s1) __nanosleep(20);
                 }
-                __syncwarp();
-                n_spec = node;
-                PROF_COUNT(15);
             }
-            if (dbg & 1) n_spec = -1;
 #ifdef NHD_CHECKS
-            if (n_spec >= 0) {
-                DynU dx; load_dyn(a, cx, n_spec, dx);
-                CHK_SANE(dx, n_spec, 2);
-                if (!same_dyn(dx, ds)) CHK_FAIL(3, n_spec, dx.q[0].x, ds.q[0].x);
+            if (n_adopt >= 0) {
+                DynU dx; load_dyn(a, cx, n_adopt, dx);
+                CHK_SANE(dx, n_adopt, 2);
+                if (!same_dyn(dx, db)) CHK_FAIL(3, n_adopt, dx.q[0].x, db.q[0].x);
                 PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
-                const int stx = resolve_decision(a, cx, ti, t, n_spec, dx, pmx, pkx, msx);
-                if (stx < 2) CHK_FAIL(4, n_spec, stx, 0);
+                const int stx = resolve_decision(a, cx, ti, t, n_adopt, dx, pmx, pkx, msx);
+                if (stx < 2) CHK_FAIL(4, n_adopt, stx, 0);
                 else {
                     nhd_binding* scratch = &a.out[a.n_pods + wid];      /* spare records behind the batch */
-                    apply_decision(cx, t, n_spec, dx.d, pmx, pkx, now, scratch);
-                    if (!same_dyn(dx, da)) CHK_FAIL(5, n_spec, dx.q[0].x, da.q[0].x);
+                    apply_decision(cx, t, n_adopt, dx.d, pmx, pkx, now, scratch);
+                    if (!same_dyn(dx, da)) CHK_FAIL(5, n_adopt, dx.q[0].x, da.q[0].x);
                 }
+                /* and it is the first fit of the GPU-less pass */
+                for (int w = lane; w < (n_adopt >> 6); w += 32)
+                    if (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) CHK_FAIL(6, n_adopt, w, 0);
+                if ((ldw<SMEM_BITMAPS>(&F[n_adopt >> 6]) & ldw<SMEM_BITMAPS>(&NOGPU[n_adopt >> 6])) & ((1ULL << (n_adopt & 63)) - 1)) CHK_FAIL(7, n_adopt, 0, 0);
             }
 #endif
-            if (n_spec >= 0) {
-                /* commit what was worked out ahead (a GPU-less node: no touched / BUSY bookkeeping) */
-                store_dyn(a, cx, n_spec, da);
-                if (sp_eager) {
-                    if (inv0) bit_clear(BM + (size_t)lane * W, n_spec);
-                    if (inv1) bit_clear(BM + (size_t)(lane + 32) * W, n_spec);
-                }
+            if (n_adopt >= 0) {
+                /* commit (a GPU-less node: no BUSY bookkeeping) */
+                store_dyn(a, cx, n_adopt, da);
+                if (lane == 0 && !n_touched) bit_set(s_touched, n_adopt);
+                if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = vbind;
                 adopted = true;
                 PROF_COUNT(13);
             }
@@ -1418,6 +1527,7 @@ sweep_kernel(const SweepArgs a)
             __threadfence_block();
         }
         PROF_MARK(0);      /* pod header */
+        int commit_node = n_adopt;             /* CPU class: node whose summary this pod changed */
         if (!adopted) do {
 
         /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
@@ -1584,8 +1694,10 @@ sweep_kernel(const SweepArgs a)
         } else {
             placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
             store_dyn(a, cx, chosen, du);
-            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
-            if (lane == 0 && du.d.n_gpus) bit_set(s_touched, chosen);
+            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node;
+             * with standing decisions the touched bit also says "the summary is no longer the snapshot's" */
+            if (lane == 0 && (du.d.n_gpus || use_workers)) bit_set(s_touched, chosen);
+            commit_node = chosen;
         }
         PROF_MARK(5);      /* assignment */
         if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
@@ -1621,13 +1733,14 @@ sweep_kernel(const SweepArgs a)
         }
         } while (0);
         __syncwarp();
-        if (dual && my_class == 0 && ncw > 1) {
-            /* hand the turn on.  With the bitmaps in shared memory everything the next pod reads is already there or
-             * fenced (store_dyn); with global bitmaps the atomics on them have to be fenced first */
-            if (!SMEM_BITMAPS) __threadfence_block();
-            if (lane == 0) { done[0] = done_after; done[2] = done_after; }
-        } else if (dual) {                                 /* publish: this class is done up to and including pod i */
+        if (dual) {                                        /* publish: this class is done up to and including pod i */
             __threadfence_block();
+            if (use_workers && my_class == 0 && commit_node >= 0) {
+                /* every standing decision made for this node is out of date: wake the owners (after the summary
+                 * is in place; a worker lowers its flag before it reads the state) */
+                for (int tt = lane; tt < T; tt += 32)
+                    if (ld_vol(&slots[tt].node) == commit_node) vol_store(&slots[tt].wake, 1);
+            }
             if (lane == 0) done[my_class] = done_after;
         }
         PROF_MARK(6);      /* write-back */
@@ -1637,7 +1750,7 @@ sweep_kernel(const SweepArgs a)
         /* summaries of GPU-less nodes still held only by the cache: once every CPU-only pod is in, warp 0 writes
          * them out (GPU nodes were written through; the GPU-pod warp may still be rewriting those) */
         if (wid == 0) {
-            if (lane == 0) while (ld_vol((const volatile int*)&done[2]) < n_cls[0]) __nanosleep(40);
+            if (lane == 0) done[2] = 1;                     /* every CPU-only pod is in: the workers leave */
             __syncwarp();
             for (int sl = lane; sl <= cx.dcache_mask; sl += 32) {
                 const int tg = ld_vol(cx.dtag + sl);

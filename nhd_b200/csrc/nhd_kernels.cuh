@@ -699,6 +699,7 @@ __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx
 {
     const int cs = node & cx.dcache_mask;
     const bool through = !cx.write_back || du.d.n_gpus != 0;
+    __syncwarp();                                        /* every lane has finished reading the cache */
     if (cx.write_back) {
         if (cx.lane == 0) {
             const int old = ld_vol(cx.dtag + cs);
@@ -752,6 +753,75 @@ __device__ __forceinline__ uint32_t claimed_order_packed(uint32_t rec, int n_rec
         if (sl) { out |= (sl - 1) << (8 * ncl); ncl++; }
     }
     return out;
+}
+
+/*
+ * NIC stage of Matcher.py:242-268 restricted to one NUMA node: the first surviving assignment of the groups
+ * S (bit g = group g, taken in group order, first group most significant in the reference's product order) to
+ * the NICs `mk` (list-index mask, ascending = NodeNic.idx order) of that NUMA node, with the reference's fp64
+ * subtraction order.  Returns feasible << 31 | one byte per member of S: its NodeNic.idx.  Cold path (memoised).
+ */
+__device__ __noinline__ uint32_t nic_sub_solve(const double* cap, const PodType& t, int S, uint32_t mk, uint32_t inuse,
+                                               unsigned long long sp0, unsigned long long sp1)
+{
+    bool feas = false;
+    uint32_t r_idx = 0, r_li = 0;
+    {
+        /* members of S in group order, and their demands, in registers */
+        const int n = popc32((uint32_t)S);
+        int sr = S;
+        const int g0 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g1 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g2 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
+        const int g3 = sr ? ctz32((uint32_t)sr) : 0;
+        const double rx[NHD_MAX_GROUPS] = {t.pod.groups[g0].rx_gbps, t.pod.groups[g1].rx_gbps, t.pod.groups[g2].rx_gbps, t.pod.groups[g3].rx_gbps};
+        const double tx[NHD_MAX_GROUPS] = {t.pod.groups[g0].tx_gbps, t.pod.groups[g1].tx_gbps, t.pod.groups[g2].tx_gbps, t.pod.groups[g3].tx_gbps};
+        auto capof = [&](int l) -> double {
+            if ((inuse >> l) & 1) return 0.0;
+            const int sc = (int)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF);
+            return cap[sc];
+        };
+        if (n == 0) feas = true;
+        else if (mk != 0) {
+            for (uint32_t f0 = mk; f0 && !feas; f0 &= f0 - 1) {
+                const int l0 = ctz32(f0);
+                const double c0 = capof(l0);
+                const double r0 = c0 - rx[0], t0 = c0 - tx[0];
+                if (r0 < 0 || t0 < 0) continue;
+                if (n == 1) { feas = true; r_li = l0; break; }
+                for (uint32_t f1 = mk; f1 && !feas; f1 &= f1 - 1) {
+                    const int l1 = ctz32(f1);
+                    const double c1 = capof(l1);
+                    const double r1 = (l1 == l0 ? r0 : c1) - rx[1], t1 = (l1 == l0 ? t0 : c1) - tx[1];
+                    if (r1 < 0 || t1 < 0) continue;
+                    if (n == 2) { feas = true; r_li = l0 | (l1 << 8); break; }
+                    for (uint32_t f2 = mk; f2 && !feas; f2 &= f2 - 1) {
+                        const int l2 = ctz32(f2);
+                        const double c2 = capof(l2);
+                        const double b2r = l2 == l1 ? r1 : (l2 == l0 ? r0 : c2), b2t = l2 == l1 ? t1 : (l2 == l0 ? t0 : c2);
+                        const double r2 = b2r - rx[2], t2 = b2t - tx[2];
+                        if (r2 < 0 || t2 < 0) continue;
+                        if (n == 3) { feas = true; r_li = l0 | (l1 << 8) | (l2 << 16); break; }
+                        for (uint32_t f3 = mk; f3; f3 &= f3 - 1) {
+                            const int l3 = ctz32(f3);
+                            const double c3 = capof(l3);
+                            const double b3r = l3 == l2 ? r2 : (l3 == l1 ? r1 : (l3 == l0 ? r0 : c3));
+                            const double b3t = l3 == l2 ? t2 : (l3 == l1 ? t1 : (l3 == l0 ? t0 : c3));
+                            if (b3r - rx[3] < 0 || b3t - tx[3] < 0) continue;
+                            feas = true; r_li = l0 | (l1 << 8) | (l2 << 16) | ((uint32_t)l3 << 24);
+                            break;
+                        }
+                    }
+                }
+            }
+            if (feas)
+                for (int e = 0; e < n; e++) {
+                    const int l = (r_li >> (8 * e)) & 0xFF;
+                    r_idx |= (uint32_t)popc32(mk & ((1u << l) - 1)) << (8 * e);      /* NodeNic.idx = rank inside the NUMA node */
+                }
+        }
+    }
+    return r_idx | (feas ? 0x80000000u : 0u);
 }
 
 /* static NIC layout of one hardware class, cached in shared memory (32 B) */
@@ -857,59 +927,8 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
       if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) {
         feas = (sv.w >> 31) != 0; r_idx = sv.w & 0x7FFFFFFFu;
       } else {
-        /* members of S in group order, and their demands, in registers */
-        const int n = popc32((uint32_t)S);
-        int sr = S;
-        const int g0 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
-        const int g1 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
-        const int g2 = sr ? ctz32((uint32_t)sr) : 0; sr &= sr - 1;
-        const int g3 = sr ? ctz32((uint32_t)sr) : 0;
-        const double rx[NHD_MAX_GROUPS] = {t.pod.groups[g0].rx_gbps, t.pod.groups[g1].rx_gbps, t.pod.groups[g2].rx_gbps, t.pod.groups[g3].rx_gbps};
-        const double tx[NHD_MAX_GROUPS] = {t.pod.groups[g0].tx_gbps, t.pod.groups[g1].tx_gbps, t.pod.groups[g2].tx_gbps, t.pod.groups[g3].tx_gbps};
-        auto capof = [&](int l) -> double {
-            if ((inuse >> l) & 1) return 0.0;
-            const int sc = (int)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF);
-            return a.cap[sc];
-        };
-        if (n == 0) feas = true;
-        else if (mk != 0) {
-            for (uint32_t f0 = mk; f0 && !feas; f0 &= f0 - 1) {
-                const int l0 = ctz32(f0);
-                const double c0 = capof(l0);
-                const double r0 = c0 - rx[0], t0 = c0 - tx[0];
-                if (r0 < 0 || t0 < 0) continue;
-                if (n == 1) { feas = true; r_li = l0; break; }
-                for (uint32_t f1 = mk; f1 && !feas; f1 &= f1 - 1) {
-                    const int l1 = ctz32(f1);
-                    const double c1 = capof(l1);
-                    const double r1 = (l1 == l0 ? r0 : c1) - rx[1], t1 = (l1 == l0 ? t0 : c1) - tx[1];
-                    if (r1 < 0 || t1 < 0) continue;
-                    if (n == 2) { feas = true; r_li = l0 | (l1 << 8); break; }
-                    for (uint32_t f2 = mk; f2 && !feas; f2 &= f2 - 1) {
-                        const int l2 = ctz32(f2);
-                        const double c2 = capof(l2);
-                        const double b2r = l2 == l1 ? r1 : (l2 == l0 ? r0 : c2), b2t = l2 == l1 ? t1 : (l2 == l0 ? t0 : c2);
-                        const double r2 = b2r - rx[2], t2 = b2t - tx[2];
-                        if (r2 < 0 || t2 < 0) continue;
-                        if (n == 3) { feas = true; r_li = l0 | (l1 << 8) | (l2 << 16); break; }
-                        for (uint32_t f3 = mk; f3; f3 &= f3 - 1) {
-                            const int l3 = ctz32(f3);
-                            const double c3 = capof(l3);
-                            const double b3r = l3 == l2 ? r2 : (l3 == l1 ? r1 : (l3 == l0 ? r0 : c3));
-                            const double b3t = l3 == l2 ? t2 : (l3 == l1 ? t1 : (l3 == l0 ? t0 : c3));
-                            if (b3r - rx[3] < 0 || b3t - tx[3] < 0) continue;
-                            feas = true; r_li = l0 | (l1 << 8) | (l2 << 16) | ((uint32_t)l3 << 24);
-                            break;
-                        }
-                    }
-                }
-            }
-            if (feas)
-                for (int e = 0; e < n; e++) {
-                    const int l = (r_li >> (8 * e)) & 0xFF;
-                    r_idx |= (uint32_t)popc32(mk & ((1u << l) - 1)) << (8 * e);      /* NodeNic.idx = rank inside the NUMA node */
-                }
-        }
+        const uint32_t rr = nic_sub_solve(a.cap, t, S, mk, inuse, sp0, sp1);
+        feas = (rr >> 31) != 0; r_idx = rr & 0x7FFFFFFFu;
         *se = make_uint4(skey, inuse_k, skey2, r_idx | (feas ? 0x80000000u : 0u));
       }
     }
@@ -1106,104 +1125,355 @@ __device__ __noinline__ void resolve_pending(const SweepArgs& a, const SweepCtx&
 }
 
 /*
- * Standing decision of one CPU-only pod type (multi-warp sweep).  A worker warp that owns the type keeps this
- * slot current: the type's first-fit node on the GPU-less pass (first set bit of F[t] & NOGPU), the node's
- * summary it evaluated, the summary after a pod of the type has been placed there, and the binding header.
- * All of that is a pure function of (type, node, summary).  The committing warp — the only one that walks
- * the CPU-only pods, in pod order — adopts the slot iff the node's summary is bit for bit `before` (bits of
- * F[t] are only ever cleared inside a batch, so a first set bit that is still set is still the first);
- * otherwise it kicks the worker and waits for a fresh one.  The slot is a seqlock (odd = being rewritten).
+ * ---------------------------------------------------------------- standing decisions (constant-clock batches)
+ *
+ * On a constant clock (the batch case) the sweep keeps, for every pod type, what the next pod of that type
+ * will do — a pure function of (type, first-fit node, that node's summary):
+ *   CPU-only types  the first-fit node of the GPU-less pass (first set bit of F[t] & NOGPU, Matcher.py:412-416),
+ *                   the mapping, the node's summary after the pod and the binding header (NHD_SLOT_FAST);
+ *   GPU types       the first candidate that is not busy (Matcher.py:107-111); if no pod of this batch was bound
+ *                   there its snapshot bit is exact and the pod only stamps the node (NHD_SLOT_DEFER).
+ * A pod then commits its type's slot in a handful of instructions, and the slots made for the node it changed
+ * are worked out again at once — all of them in one pass, 32 / LP types side by side, LP = 2^G lanes per type
+ * (one NUMA tuple of the groups per lane; G <= 2 in the reference's deployments, so eight types per pass).
+ * Anything else (spills onto GPU nodes, GPU pods on nodes already bound to, nodes with more than two NUMA
+ * nodes or without a hardware class, PCI-mode CPU pods, more groups than lanes) is NHD_SLOT_SLOW: the pod
+ * takes the ordinary path below.  One warp does all of this in pod order: no inter-warp hand-off exists.
  */
-struct TSlot {
-    int seq;                 /* even: stable, odd: the worker is rewriting the slot                     */
-    int node;                /* first-fit node the decision was worked out for                          */
-    int kind;                /* 0 nothing yet, 1 decision available, 2 GPU-less pass exhausted (final)  */
-    int wake;                /* set by the committing warp: the node changed, work the type out again   */
-    uint4 before[2];         /* NodeDyn the decision was evaluated on                                   */
-    uint4 after[2];          /* NodeDyn once the pod is placed                                          */
-    uint4 bind[4];           /* first 64 bytes of the nhd_binding (the rest is zero until the core ids) */
-};
-static_assert(sizeof(TSlot) == 144, "TSlot is nine 16-byte chunks");
+#define NHD_SLOT_SLOW   0
+#define NHD_SLOT_FAST   1
+#define NHD_SLOT_DEFER  2
+#define NHD_SLOT_NONE   3
 
-__device__ __forceinline__ void vol_store(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+struct TSlot {
+    int node;                /* node the slot was made for (-1: none)                                   */
+    int kind;                /* NHD_SLOT_*                                                              */
+    int pad_[2];
+    uint4 after[2];          /* FAST: NodeDyn once the pod is placed                                    */
+    uint4 bind[4];           /* FAST: first 64 bytes of the nhd_binding (the rest is zero until the core ids) */
+};
+static_assert(sizeof(TSlot) == 112, "TSlot is seven 16-byte chunks");
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x)       /* bit i -> bit 2i */
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+struct FastOut {
+    int state;                       /* 0 idle lane, 1 the node does not take the pod, 2 placed */
+    uint32_t pn, idx, li, ms;        /* the mapping, one byte per group (PMap) */
+    uint32_t claimed;
+    int ncl;
+};
 
 /*
- * Worker warp: bring the standing decision of CPU-only type ti up to date against the current state.
- * Nodes that do not fit lose their bit for good (resources only shrink inside a batch, and a summary read
- * while it was being updated is never below the current one in any resource); a node that fits is published
- * together with the summary it was evaluated on, which the committing warp compares with the node's actual
- * summary before it uses the result.
+ * resolve_cpu2 for 32 / LP problems at once: lanes [j*LP, (j+1)*LP) work on problem j = (type ti, node with
+ * summary du); lane p of a group owns the NUMA tuple p of the groups (digit g = bit G-1-g) and both positions
+ * of the misc cores.  Same tables and the same results as resolve_cpu2:
+ *   CPU stage (Matcher.py:203-212)  two compares per lane against the type's per-tuple socket demands;
+ *   NIC stage (Matcher.py:242-268)  factorised per NUMA node: lane p looks up "groups on NUMA 0" and "groups on
+ *                                   NUMA 1" of its tuple in the sub-problem memo (nic_sub_solve on a miss);
+ *   mapping   (Matcher.py:423-452)  the mapping memo on the three masks, gathered with three ballots;
+ *   claim order (NHDScheduler.py:302) of the chosen tuple's NICs.
+ * Preconditions (checked by the caller, `have` false otherwise): CPU-only type, NUMA mode, 2^G <= LP, 2-NUMA
+ * node with a hardware class.  All 32 lanes must call.
+ */
+__device__ __forceinline__ void fast_eval(const SweepArgs& a, const SweepCtx& cx, int LP, bool have, int ti, int node,
+                                          const DynU& du, FastOut& o)
+{
+    const int lane = cx.lane, p = lane & (LP - 1), base = lane - p;
+    const uint32_t lpm = LP >= 32 ? 0xFFFFFFFFu : ((1u << LP) - 1);
+    if (!have) ti = 0;
+    const PodType& t = cx.types[ti];
+    const int G = t.G, gmask = (1 << G) - 1, nq = 1 << (G + 1);
+    const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
+    const bool tup = have && p <= gmask;
+    o.state = 0; o.pn = o.idx = o.li = o.ms = o.claimed = 0; o.ncl = 0;
+
+    /* ---- CPU stage: q = 2p (misc on NUMA 0) and q = 2p + 1 ---- */
+    const uint32_t nbw = reinterpret_cast<const uint32_t*>(cx.s_needb)[(ti * 2 + (smt ? 1 : 0)) * 16 + (p & 15)];
+    const uint32_t fc0 = du.d.fc[0], fc1 = du.d.fc[1];
+    const bool okB0 = tup && (nbw & 0xFF) <= fc0 && ((nbw >> 8) & 0xFF) <= fc1;
+    const bool okB1 = tup && ((nbw >> 16) & 0xFF) <= fc0 && (nbw >> 24) <= fc1;
+
+    /* ---- static NIC layout of the node's hardware class (table shared with resolve_cpu2) ---- */
+    ClsNic* ce = &cx.clsnic[du.d.hw_class & cx.clsnic_mask];
+    const uint32_t want = (uint32_t)du.d.hw_class + 1u;
+    uint32_t m0 = ce->m0, m1 = ce->m1, nk = ce->nk, spk0 = ce->spk0, spk1 = ce->spk1;
+    unsigned long long sp0 = ce->sp0, sp1 = ce->sp1;
+    const bool cmiss = have && ce->tag != want;
+    if (cmiss) {
+        const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
+        const uint4 c7 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 7));
+        m0 = c5.x; m1 = c5.y;
+        sp0 = (unsigned long long)c7.x | ((unsigned long long)c7.y << 32);
+        sp1 = (unsigned long long)c7.z | ((unsigned long long)c7.w << 32);
+        const int n0 = popc32(m0), n1 = popc32(m1);
+        nk = (uint32_t)n0 | ((uint32_t)n1 << 8) | ((n0 > 8 || n1 > 8) ? 0x80000000u : 0u);
+        spk0 = spk1 = 0;
+        int j = 0;
+        for (uint32_t f = m0; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk0 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
+        j = 0;
+        for (uint32_t f = m1; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk1 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
+    }
+    {
+        /* one writer per instruction: lanes of different problems may map to the same table slot */
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cmiss && p == 0);
+        for (uint32_t m = mm; m; m &= m - 1) {
+            if (lane == ctz32(m)) {
+                ce->tag = 0;
+                ce->m0 = m0; ce->m1 = m1; ce->nk = nk; ce->sp0 = sp0; ce->sp1 = sp1; ce->spk0 = spk0; ce->spk1 = spk1;
+                ce->tag = want;
+            }
+            __syncwarp();
+        }
+    }
+
+    /* ---- NIC stage: the two halves of tuple p ---- */
+    const int S1 = tup ? (int)(__brev((unsigned)p) >> (32 - G)) : 0;        /* groups on NUMA 1 */
+    const int S0 = gmask & ~S1;
+    const uint32_t inuse = du.d.nic_inuse;
+    const bool wide = (nk >> 31) != 0;
+    uint32_t e01[2] = {0, 0};
+    bool smiss[2] = {false, false};
+    uint32_t skeys[2], skey2s[2], inuse_ks[2];
+    uint4* ses[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t mk = k ? m1 : m0;
+        const int S = k ? S1 : S0;
+        uint32_t inuse_k = 0;
+        {
+            int jl = 0;
+            for (uint32_t f = mk; f; f &= f - 1, jl++) inuse_k |= ((inuse >> ctz32(f)) & 1u) << jl;
+        }
+        const uint32_t n_k = (k ? (nk >> 8) : nk) & 0xFF;
+        const uint32_t skey = 0x80000000u | (uint32_t)ti | ((uint32_t)S << 12) | (n_k << 16) |
+                              (wide ? (0x40000000u | ((uint32_t)k << 24)) : 0u);
+        const uint32_t skey2 = wide ? (uint32_t)du.d.hw_class : (k ? spk1 : spk0);
+        uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u ^ skey2 * 0xC2B2AE3Du;
+        sh ^= sh >> 15;
+        uint4* se = &cx.spmemo[sh & cx.spmemo_mask];
+        const uint4 sv = *se;
+        if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) e01[k] = sv.w;
+        else smiss[k] = tup;
+        skeys[k] = skey; skey2s[k] = skey2; inuse_ks[k] = inuse_k; ses[k] = se;
+    }
+    {
+        /* misses are cold: one lane at a time solves and stores (16-byte entries, one writer per instruction) */
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, smiss[0] || smiss[1]);
+        for (uint32_t m = mm; m; m &= m - 1) {
+            if (lane == ctz32(m)) {
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                    if (smiss[k]) {
+                        e01[k] = nic_sub_solve(a.cap, t, k ? S1 : S0, k ? m1 : m0, inuse, sp0, sp1);
+                        *ses[k] = make_uint4(skeys[k], inuse_ks[k], skey2s[k], e01[k]);
+                    }
+            }
+            __syncwarp();
+        }
+    }
+    const bool okC = tup && (e01[0] >> 31) && (e01[1] >> 31);
+
+    /* ---- the three masks of every problem ---- */
+    const uint32_t bC = __ballot_sync(0xFFFFFFFFu, okC);
+    const uint32_t bB0 = __ballot_sync(0xFFFFFFFFu, okB0);
+    const uint32_t bB1 = __ballot_sync(0xFFFFFFFFu, okB1);
+    const uint32_t cb = (bC >> base) & lpm, b0 = (bB0 >> base) & lpm, b1 = (bB1 >> base) & lpm;
+    const uint32_t balB = spread16(b0) | (spread16(b1) << 1), balC = spread16(cb);
+    const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
+    bool feas = have && t.pod.hugepages_gb <= du.d.free_hugepages_gb && balB != 0 && balC != 0;     /* Matcher.py:78 */
+
+    /* ---- GetNumaGroupIdx: mapping memo (hit inline; a miss is cold and done by one lane at a time) ---- */
+    int v = -1;
+    {
+        const uint32_t tag = 0x80000000u | (2u << 24) | ((uint32_t)G << 16);
+        uint32_t h32 = (balB * 0x9E3779B1u) ^ (balC * 0x85EBCA77u) ^ (balA * 0xC2B2AE3Du) ^ tag;
+        h32 ^= h32 >> 15;
+        const int ss = (int)(h32 & (uint32_t)cx.smemo_mask);
+        const uint4 e = cx.smemo[ss];
+        bool mmiss = false;
+        if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
+            const int vv = (int)(e.w & 0xFFFF);
+            v = vv == 0xFFFF ? -1 : vv;
+        } else mmiss = feas;
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, mmiss && p == 0);
+        for (uint32_t m = mm; m; m &= m - 1) {
+            if (lane == ctz32(m)) v = choose_mapping_slow(cx.smemo, ss, a.memo, 2, G, balA, balB, balC, tag);
+            __syncwarp();
+        }
+        const int vl = __shfl_sync(0xFFFFFFFFu, v, base);          /* the group's leader did the miss */
+        if (mmiss) v = vl;
+    }
+    if (!feas) v = -1;
+
+    /* ---- the chosen tuple's NIC picks: held by lane ps of the group ---- */
+    const int ps = v >= 0 ? (v & 0xFF) : 0;
+    const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, e01[0], base + (ps & (LP - 1)));
+    const uint32_t x1 = __shfl_sync(0xFFFFFFFFu, e01[1], base + (ps & (LP - 1)));
+    if (!have) return;
+    if (v < 0) { o.state = 1; return; }
+    o.state = 2;
+    o.ms = (uint32_t)(v >> 8);
+    const int s1 = (int)(__brev((unsigned)ps) >> (32 - G));
+    o.pn = ((uint32_t)s1 & 1u) | (((uint32_t)s1 & 2u) << 7) | (((uint32_t)s1 & 4u) << 14) | (((uint32_t)s1 & 8u) << 21);   /* one byte per group */
+    uint32_t rec = 0;
+    int n_rec = 0, e0 = 0, e1 = 0;
+    for (int g = 0; g < G; g++) {
+        uint32_t l, x;
+        if ((s1 >> g) & 1) { x = (x1 >> (8 * e1)) & 0x7F; e1++; l = (uint32_t)nth_bit32(m1, (int)x); }
+        else { x = (x0 >> (8 * e0)) & 0x7F; e0++; l = (uint32_t)nth_bit32(m0, (int)x); }     /* NodeNic.idx -> index in Node.nics */
+        o.li |= l << (8 * g);
+        o.idx |= x << (8 * g);
+        if ((t.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
+    }
+    o.claimed = claimed_order_packed(rec, n_rec, o.ncl);
+}
+
+/*
+ * apply_decision for one lane: a placed CPU-only pod (no GPUs, cannot fail) on the summary `du`: the summary
+ * after the pod (SetBusy + the bookkeeping of SetPhysicalIdsFromMapping, Node.py:663-841, + ClaimPodNICResources)
+ * and the first 64 bytes of the binding.
+ */
+__device__ __forceinline__ void fast_apply(const PodType& t, int node, const DynU& du, const FastOut& o, double now,
+                                           DynU& da, uint4* b)
+{
+    const int G = t.G;
+    const bool smt_node = (du.d.info & NHD_DYN_SMT) != 0;
+    const uint8_t* cl = smt_node ? t.cl_smt : t.cl_nosmt;
+    uint32_t fcw = du.q[0].x;
+    const uint32_t fc_before = fcw, w14 = du.q[0].y;
+    for (int g = 0; g < G; g++) fcw -= (uint32_t)cl[g] << (8 * ((o.pn >> (8 * g)) & 0xFF));
+    {
+        const int sh = 8 * (int)o.ms;
+        const int wd = batch_width(smt_node, (t.pod.flags & NHD_POD_MISC_SMT) != 0, t.pod.n_misc, (fcw >> sh) & 0xFF);
+        fcw -= (uint32_t)wd << sh;
+    }
+    da.q[0] = du.q[0]; da.q[1] = du.q[1];
+    da.q[0].x = fcw;
+    da.q[0].y = w14 + (fc_before - fcw);                 /* per byte, no borrows: each width <= what is free */
+    da.d.info |= NHD_DYN_TOUCHED;
+    da.d.busy_time = now;                                 /* NHDScheduler.py:289 */
+    if (t.pod.hugepages_gb > 0) da.d.free_hugepages_gb -= t.pod.hugepages_gb;      /* Node.py:794-796 */
+    for (int e = 0; e < o.ncl; e++) da.d.nic_inuse |= 1u << ((o.claimed >> (8 * e)) & 0xFF);   /* Node.py:644-646 */
+    /* bytes: 12 gpu_numa[4] 16 cpu_numa[5] 21 nic_numa[4] 25 nic_idx[4] 29 nic_list_index[4] 33 claimed[4] 40 gpu_index[16] 56 cores */
+    const uint32_t w2 = (uint32_t)G | ((uint32_t)o.ncl << 24);
+    const uint32_t w4 = G < 4 ? (o.pn | (o.ms << (8 * G))) : o.pn;
+    const uint32_t w5 = (G == 4 ? o.ms : 0u) | (o.pn << 8);
+    const uint32_t w6 = (o.pn >> 24) | (o.idx << 8);
+    const uint32_t w7 = (o.idx >> 24) | (o.li << 8);
+    const uint32_t w8 = (o.li >> 24) | (o.claimed << 8);
+    const uint32_t w9 = o.claimed >> 24;
+    b[0] = make_uint4(NHD_PLACED, (uint32_t)node, w2, o.pn);
+    b[1] = make_uint4(w4, w5, w6, w7);
+    b[2] = make_uint4(w8, w9, 0, 0);
+    b[3] = make_uint4(0, 0, w14, 0);
+}
+
+/*
+ * Work the standing decisions of the given types out again (see above): CPU-only types 32 / LP at a time with
+ * fast_eval, GPU types one per lane.  A node that does not take a CPU-only type loses the type's bit for good
+ * (resources only shrink inside a batch) and the type moves on to its next candidate.
  */
 template <bool SMEM_BITMAPS>
-__device__ __forceinline__ void worker_refresh(const SweepArgs& a, const SweepCtx& cx, TSlot* sl, int ti, const PodType& t,
-                                               uint64_t* F, const uint64_t* NOGPU, int W, int32_t* cursor, double now)
+__device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx& cx, TSlot* slots, uint64_t* BM, const uint64_t* NOGPU,
+                                              const uint64_t* BUSY, const uint64_t* touched, int W, int32_t* cursors, int lg_lp,
+                                              double now, unsigned long long cpu_stale, unsigned long long gpu_stale)
 {
-    const int lane = cx.lane;
-    int seq = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);          /* only this warp ever writes it */
-    for (;;) {
+    const int lane = cx.lane, LP = 1 << lg_lp, p = lane & (LP - 1), gi = lane >> lg_lp, NP = 32 >> lg_lp;
+    while (cpu_stale) {
         __syncwarp();
-        /* first candidate of the GPU-less pass (Matcher.py:412-416) */
-        int c = __shfl_sync(0xFFFFFFFFu, ld_vol(cursor), 0);
-        const int c_in = c;
-        uint64_t raw = 0;
-        while (c < W) {
-            raw = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
-            raw = __shfl_sync(0xFFFFFFFFu, raw, 0);
-            if (raw) break;
-            int found = W;
-            for (int base = c + 1; base < W; base += 32) {
-                const int w = base + lane;
-                const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) : 0;
-                const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
-                if (nz) { found = base + ctz32(nz); break; }
-            }
-            c = found;
-        }
-        if (c != c_in && lane == 0) vol_store(cursor, c);          /* a lower bound stays one: bits are only cleared */
-        if (c >= W) {
-            /* nothing left on GPU-less nodes: pods of this type spill (ordinary path of the committing warp) */
-            if (lane == 0) vol_store(&sl->seq, seq + 1);
-            __threadfence_block();
-            if (lane == 0) { vol_store(&sl->node, -1); vol_store(&sl->kind, 2); }
-            __threadfence_block();
-            if (lane == 0) vol_store(&sl->seq, seq + 2);
-            __syncwarp();
-            return;
-        }
-        const int node = c * 64 + ctz64(raw);
-        DynU ds;
-        if (!spec_load_dyn(a, cx, node, ds)) continue;
-        PMap pms = {0, 0, 0, 0};
-        Picks pks;
-        pks.fail_status = 0;
-        bool ms;
-        const int st = __shfl_sync(0xFFFFFFFFu, resolve_decision(a, cx, ti, t, node, ds, pms, pks, ms), 0);
-        if (st < 2) {
-            if (lane == 0) bit_clear(F, node);
-            continue;
-        }
-        /* publish */
-        __syncwarp();
-        if (lane == 0) vol_store(&sl->seq, seq + 1);
-        __threadfence_block();
-        __syncwarp();
-        DynU da;
-        da.q[0] = ds.q[0]; da.q[1] = ds.q[1];
-        apply_decision(cx, t, node, da.d, pms, pks, now, reinterpret_cast<nhd_binding*>(sl->bind), 4);
+        int ti = -1;
         {
-            const uint4 hb = lane == 0 ? ds.q[0] : ds.q[1], ha = lane == 0 ? da.q[0] : da.q[1];
-            if (lane < 2) { sl->before[lane] = hb; sl->after[lane] = ha; }
+            unsigned long long m = cpu_stale;
+            for (int j = 0; j < gi && m; j++) m &= m - 1;
+            if (m) ti = ctz64(m);
         }
-        if (lane == 0) { vol_store(&sl->node, node); vol_store(&sl->kind, 1); }
-        __threadfence_block();
-        __syncwarp();
-        seq += 2;
-        if (lane == 0) vol_store(&sl->seq, seq);
-        __syncwarp();
-        /* the node may have been committed to while it was being worked out: look once more */
-        DynU dc;
-        if (spec_load_dyn(a, cx, node, dc) && same_dyn(dc, ds)) return;
+        const bool have = ti >= 0;
+        uint64_t* F = BM + (size_t)(have ? ti : 0) * W;
+        int node = -1, c_new = -1;
+        DynU du;
+        du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0];
+        if (have) {
+            /* first candidate of the GPU-less pass (Matcher.py:412-416); the lanes of a group walk together */
+            int c = cursors[ti * 3 + 0];
+            const int c_in = c;
+            uint64_t w = 0;
+            while (c < W) {
+                w = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
+                if (w) break;
+                c++;
+            }
+            c_new = c != c_in ? c : -1;
+            if (c < W) { node = c * 64 + ctz64(w); load_dyn(a, cx, node, du); }
+        }
+        const PodType& t = cx.types[have ? ti : 0];
+        const bool direct = node >= 0 && ((du.d.info >> 2) & 7) == 2 && du.d.hw_class != NHD_NO_CLASS && t.G <= lg_lp && !t.pci;
+        FastOut o;
+        fast_eval(a, cx, LP, direct, ti, node, du, o);
+        bool settled = false;
+        if (have && p == 0) {
+            if (c_new >= 0) cursors[ti * 3 + 0] = c_new;               /* a lower bound stays one: bits are only cleared */
+            TSlot* sl = &slots[ti];
+            if (!direct) {
+                /* GPU-less pass exhausted (the pod will spill), or a node / type the direct evaluation does not cover */
+                sl->node = node; sl->kind = NHD_SLOT_SLOW;
+                settled = true;
+            } else if (o.state == 1) {
+                bit_clear(F, node);
+            } else {
+                DynU da;
+                uint4 b[4];
+                fast_apply(t, node, du, o, now, da, b);
+                sl->node = node; sl->kind = NHD_SLOT_FAST;
+                sl->after[0] = da.q[0]; sl->after[1] = da.q[1];
+                sl->bind[0] = b[0]; sl->bind[1] = b[1]; sl->bind[2] = b[2]; sl->bind[3] = b[3];
+                settled = true;
+            }
+        }
+        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, settled);
+        for (int j = 0; j < NP; j++) {
+            const int tj = __shfl_sync(0xFFFFFFFFu, ti, j << lg_lp);
+            if ((dm >> (j << lg_lp)) & 1) cpu_stale &= ~(1ULL << tj);
+        }
     }
+    while (gpu_stale) {
+        __syncwarp();
+        int ti = -1;
+        {
+            unsigned long long m = gpu_stale;
+            for (int j = 0; j < lane && m; j++) m &= m - 1;
+            if (m) ti = ctz64(m);
+        }
+        if (ti >= 0) {
+            /* first candidate that is not busy (Matcher.py:107-111) */
+            const uint64_t* F = BM + (size_t)ti * W;
+            int c = cursors[ti * 3 + 2];
+            const int c_in = c;
+            uint64_t w = 0;
+            while (c < W) {
+                w = ldw<SMEM_BITMAPS>(&F[c]) & ~ldw<SMEM_BITMAPS>(&BUSY[c]);
+                if (w) break;
+                c++;
+            }
+            if (c != c_in) cursors[ti * 3 + 2] = c;
+            TSlot* sl = &slots[ti];
+            if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_NONE; }        /* final: busy bits are only set on a constant clock */
+            else {
+                const int node = c * 64 + ctz64(w);
+                sl->node = node;
+                /* no pod of this batch was bound there: the snapshot bit is exact; else the ordinary path */
+                sl->kind = ((touched[c] >> (node & 63)) & 1) ? NHD_SLOT_SLOW : NHD_SLOT_DEFER;
+            }
+        }
+        for (int j = 0; j < 32 && gpu_stale; j++) gpu_stale &= gpu_stale - 1;
+    }
+    __syncwarp();
 }
 
 /*
@@ -1220,6 +1490,7 @@ __device__ __forceinline__ void worker_refresh(const SweepArgs& a, const SweepCt
  *   assign      hugepages, busy stamp, per-socket core accounting, binding header, summary
  *               write-back (Node.py:663-841 minus the core ids);
  *   invalidate  every pod type that can no longer fit on the node loses its bit right away.
+ * On a constant clock the standing decisions above short-cut all of this for the common cases.
  */
 template <bool SMEM_BITMAPS>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
@@ -1229,42 +1500,28 @@ sweep_kernel(const SweepArgs a)
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = a.words, T = a.n_types;
     const int wid = tid >> 5;
-    const int dual = a.dual;
-    /* multi-warp mode: warp 0 walks (commits) the CPU-only pods, warps 1..ncw-1 keep one standing decision per
-     * CPU-only pod type current (TSlot), warp ncw walks the GPU pods; the CPU class shares one summary cache,
-     * the GPU warp has its own */
-    const int ncw = dual ? (a.n_cpu_warps & 0xFF) : 0;
-    const int dbg = a.n_cpu_warps >> 8;       /* debug switches: 1 = never adopt, 2 = no worker warps */
-    const int is_gpu_warp = dual && wid == ncw;
-    const bool is_worker = dual && wid >= 1 && wid < ncw;
-    /* decision memo (48-byte entries, generic path): half for the GPU-pod warp, which lives on it; the CPU-only
-     * warps (direct path, rarely here) share the other half in equal power-of-two slices */
-    const int cpu_slices = ncw <= 1 ? 1 : (ncw <= 2 ? 2 : (ncw <= 4 ? 4 : 8));
-    const int dm_slots = !dual ? DMEMO_SLOTS : (is_gpu_warp ? DMEMO_SLOTS / 2 : DMEMO_SLOTS / 2 / cpu_slices);
-    const int dm_first = !dual ? 0 : (is_gpu_warp ? DMEMO_SLOTS / 2 : wid * dm_slots);
+    const int dbg = a.n_cpu_warps >> 8;       /* debug switch: 1 = no standing decisions (ordinary path for every pod) */
     SweepCtx cx;
     cx.lane = lane;
-    /* mapping memo and NIC sub-problem memo: 16-byte entries, written and read whole, values pure functions of
-     * the key -> shared by all warps; the multi-chunk tables (decision memo, class layouts) are sliced per warp */
     cx.smemo_mask = SMEMO_SLOTS - 1;
-    cx.dmemo_mask = dm_slots - 1;
+    cx.dmemo_mask = DMEMO_SLOTS - 1;
     cx.spmemo_mask = SPMEMO_SLOTS - 1;
     cx.clsnic_mask = CLSNIC_SLOTS - 1;
-    cx.dcache_mask = (dual ? DCACHE_SLOTS / 2 : DCACHE_SLOTS) - 1;
+    cx.dcache_mask = DCACHE_SLOTS - 1;
     cx.peer_mask = cx.dcache_mask;
     cx.smemo = reinterpret_cast<uint4*>(smem);                                 /* SMEMO_SLOTS x 16 B */
-    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16) + dm_first * 3;          /* DMEMO_SLOTS x 48 B */
-    cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48) + is_gpu_warp * (DCACHE_SLOTS / 2) * 2;   /* DCACHE_SLOTS x 32 B */
+    cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16);              /* DMEMO_SLOTS x 48 B */
+    cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48);   /* DCACHE_SLOTS x 32 B */
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
-    cx.dtag = dtag_all + is_gpu_warp * (DCACHE_SLOTS / 2);
-    cx.peer_dtag = dual ? dtag_all + (1 - is_gpu_warp) * (DCACHE_SLOTS / 2) : nullptr;
-    volatile int* done = reinterpret_cast<volatile int*>(dtag_all + DCACHE_SLOTS);   /* [0] CPU-only pods committed and fenced, [1] GPU pods finished, [2] set once every CPU-only pod is in (the worker warps leave) */
+    cx.dtag = dtag_all;
+    cx.peer_dtag = nullptr;
+    int* misc = dtag_all + DCACHE_SLOTS;                                             /* [3] lock word of the class-layout table */
     ClsNic* clsnic_all = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);     /* CLSNIC_SLOTS x 48 B */
     uint4* spmemo_all = reinterpret_cast<uint4*>(clsnic_all + CLSNIC_SLOTS);         /* SPMEMO_SLOTS x 16 B */
     cx.clsnic = clsnic_all;
-    cx.clsnic_lock = const_cast<int*>(reinterpret_cast<volatile int*>(&done[3]));
+    cx.clsnic_lock = &misc[3];
     cx.spmemo = spmemo_all;
-    cx.write_back = dual && !is_gpu_warp && ncw > 1;      /* the workers read the summary cache while warp 0 updates it */
+    cx.write_back = false;                                 /* one sweeping warp: summaries are written through */
     uint8_t* p0 = reinterpret_cast<uint8_t*>(spmemo_all + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
@@ -1284,11 +1541,11 @@ sweep_kernel(const SweepArgs a)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(clsnic_all)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
-    if (tid < 4) done[tid] = 0;
+    if (tid < 4) misc[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
     if (cx.types_in_smem)
-        for (int i = tid; i < T * (int)(sizeof(TSlot) / 16); i += SWEEP_THREADS)     /* seq 0, node -1, kind 0, wake 1 */
-            reinterpret_cast<uint4*>(slots)[i] = (i % (int)(sizeof(TSlot) / 16)) == 0 ? make_uint4(0, 0xFFFFFFFFu, 0, 1) : make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < T * (int)(sizeof(TSlot) / 16); i += SWEEP_THREADS)     /* node -1, NHD_SLOT_SLOW */
+            reinterpret_cast<uint4*>(slots)[i] = (i % (int)(sizeof(TSlot) / 16)) == 0 ? make_uint4(0xFFFFFFFFu, NHD_SLOT_SLOW, 0, 0) : make_uint4(0, 0, 0, 0);
     if (cx.types_in_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.types);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_types);
@@ -1332,8 +1589,7 @@ sweep_kernel(const SweepArgs a)
     int32_t* cursors = SMEM_BITMAPS ? s_cursors : a.cursors;
     for (int i = tid; i < T * 3; i += SWEEP_THREADS) cursors[i] = 0;
     __syncthreads();
-    if (wid >= (dual ? ncw + 1 : 1)) return;
-    const int my_class = dual ? is_gpu_warp : -1;         /* 0: CPU-only pods, 1: GPU pods, -1: everything */
+    if (wid >= 1) return;                                  /* the sweep proper is one warp */
 
     uint64_t* const BM = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
     uint64_t* const NOGPU = BM + (size_t)T * W;
@@ -1355,43 +1611,25 @@ sweep_kernel(const SweepArgs a)
         all_gpus = ty.total_gpus > all_gpus ? ty.total_gpus : all_gpus;
     }
 
-    /* standing decisions need the types in shared memory and the node-group gate folded into them */
-    const bool use_workers = dual && ncw > 1 && !multi && cx.types_in_smem && !(dbg & 2);
-    if (is_worker) {
-        if (!use_workers) return;
-        /* the CPU-only types this warp owns: every (ncw-1)-th of them */
-        unsigned long long mine = 0;
-        {
-            int rank = 0;
-            for (int tt = 0; tt < T; tt++) {
-                if (types[tt].needs_gpu || !types[tt].valid_map) continue;
-                if ((rank++ % (ncw - 1)) == wid - 1) mine |= 1ULL << tt;
-            }
+    /* standing decisions: constant clock, the node-group gate folded into the types, types in shared memory */
+    const bool cclock = a.dual != 0;
+    const bool fast = cclock && !multi && cx.types_in_smem && !(dbg & 1);
+    unsigned long long cpu_mask = 0, gpu_mask = 0;
+    int lg_lp = 1;
+    if (fast) {
+        for (int tt = 0; tt < T; tt++) {
+            const PodType& ty = types[tt];
+            if (!ty.valid_map) continue;
+            if (ty.needs_gpu) gpu_mask |= 1ULL << tt;
+            else { cpu_mask |= 1ULL << tt; if (!ty.pci && ty.G > lg_lp) lg_lp = ty.G; }
         }
-        const double now0 = a.now[0];
-        while (mine) {
-            __syncwarp();
-            if (__shfl_sync(0xFFFFFFFFu, ld_vol((const volatile int*)&done[2]), 0)) break;     /* every CPU-only pod is in */
-            bool any = false;
-            for (unsigned long long m = mine; m; m &= m - 1) {
-                const int tt = ctz64(m);
-                TSlot* sl = &slots[tt];
-                if (!__shfl_sync(0xFFFFFFFFu, ld_vol(&sl->wake), 0)) continue;
-                /* the flag goes down before the state is read: a commit after this point raises it again */
-                if (lane == 0) vol_store(&sl->wake, 0);
-                __threadfence_block();
-                __syncwarp();
-                worker_refresh<SMEM_BITMAPS>(a, cx, sl, tt, types[tt], BM + (size_t)tt * W, NOGPU, W, &cursors[tt * 3 + 0], now0);
-                any = true;
-            }
-            if (!any && lane == 0) __nanosleep(20);
-        }
-        return;
+        if (lg_lp > 4) lg_lp = 4;
+        refresh_slots<SMEM_BITMAPS>(a, cx, slots, BM, NOGPU, BUSY, s_touched, W, cursors, lg_lp, a.n_pods > 0 ? a.now[0] : 0.0, cpu_mask, gpu_mask);
     }
 
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
     int n_busy = 0;
-    for (int w0 = 0; w0 < W && !dual; w0 += 32) {      /* (two-warp mode runs on a constant clock: no list needed) */
+    for (int w0 = 0; w0 < W && !cclock; w0 += 32) {      /* (a constant clock needs no list) */
         uint64_t word = (w0 + lane < W) ? ldw<SMEM_BITMAPS>(&BUSY[w0 + lane]) : 0;
         int cnt = popc64(word);
         int pre = cnt;                                   /* inclusive scan over lanes */
@@ -1408,7 +1646,6 @@ sweep_kernel(const SweepArgs a)
     }
     __syncwarp();
     double cur_now = a.n_pods > 0 ? a.now[0] : 0.0;
-    int n_cls[2] = {0, 0};
     PROF_DECL
 
     for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
@@ -1417,121 +1654,79 @@ sweep_kernel(const SweepArgs a)
       const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
       const unsigned long long my_gm = (multi && i0 + lane < a.n_pods) ? a.pod_groups[i0 + lane] : 0ULL;
       const int jn = (a.n_pods - i0) < 32 ? (a.n_pods - i0) : 32;
-      /* which of these pods ask for GPUs: bit j of one ballot; a sweeping warp walks only its own class */
-      const uint32_t in_chunk = jn >= 32 ? 0xFFFFFFFFu : ((1u << jn) - 1);
-      const uint32_t gpu_bits = __ballot_sync(0xFFFFFFFFu, lane < jn && types[my_ti].needs_gpu) & in_chunk;
-      const int base_cpu = n_cls[0], base_gpu = n_cls[1];
-      n_cls[0] += popc32(in_chunk & ~gpu_bits);
-      n_cls[1] += popc32(gpu_bits);
-      for (uint32_t todo = !dual ? in_chunk : (my_class == 1 ? gpu_bits : (in_chunk & ~gpu_bits)); todo; todo &= todo - 1) {
-        const int j = ctz32(todo);
-        const uint32_t below = (1u << j) - 1;
-        const int before_cpu = base_cpu + popc32(in_chunk & ~gpu_bits & below);   /* pods of each class ahead of this one */
-        const int before_gpu = base_gpu + popc32(gpu_bits & below);
+      for (int j = 0; j < jn; j++) {
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
         nhd_binding* bout = &a.out[i];
-        const int done_after = (t.needs_gpu ? before_gpu : before_cpu) + 1;
         uint64_t* F = BM + (size_t)ti * W;
 
-        /*
-         * ---- adoption (CPU-only pod whose type has a standing decision) ----
-         * The worker warps keep, per CPU-only type, the type's first-fit node on the GPU-less pass, the summary
-         * it was evaluated on, the summary after the pod and the binding header (TSlot).  The slot is used iff
-         * the node's summary is still bit for bit the evaluated one (and the bit is still set: bits are only ever
-         * cleared inside a batch, so a first set bit that is still set is still the first); otherwise the worker
-         * is kicked and this warp waits for the fresh result.  Pods are committed strictly in pod order, here.
-         */
-        bool adopted = false, n_touched = false;
-        int n_adopt = -1;
-        if (use_workers && my_class == 0 && t.valid_map && !(dbg & 1)) {
-            TSlot* sl = &slots[ti];
-            DynU db, da;
-            uint4 vbind = make_uint4(0, 0, 0, 0);
-            for (;;) {
-                __syncwarp();
-                const int s1 = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);
-                if (s1 & 1) { if (lane == 0) __nanosleep(20); continue; }
-                const int kind = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->kind), 0);
-                const int node = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->node), 0);
-                db.q[0] = sl->before[0]; db.q[1] = sl->before[1];
+        /* ---- standing decision of the pod's type ---- */
+        bool handled = false;
+        int commit_node = -1;                  /* node this pod changed (summary, BUSY / touched bits) */
+        if (fast) {
+            const TSlot* sl = &slots[ti];
+            const int kind = sl->kind, node = sl->node;
+            if (kind == NHD_SLOT_FAST) {
+                DynU da;
                 da.q[0] = sl->after[0]; da.q[1] = sl->after[1];
-                if (lane < 4) vbind = sl->bind[lane];
-                __threadfence_block();
-                const int s2 = __shfl_sync(0xFFFFFFFFu, ld_vol(&sl->seq), 0);
-                if (s2 != s1) continue;
-                if (kind == 2) break;                                    /* GPU-less pass exhausted: ordinary path (spill) */
-                bool ok = kind == 1;
-                if (ok) {
-                    /* lane 0's view decides (other warps clear bits of these words) */
-                    const uint32_t fw = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<const volatile uint32_t*>(&F[node >> 6])[(node >> 5) & 1], 0);
-                    ok = ((fw >> (node & 31)) & 1) != 0;
-                }
-                if (ok) {
-                    /* the node's summary now: the cache (this warp is its only writer), else the snapshot if no pod of
-                     * the batch was bound there, else HBM (evicted) */
-                    const int cs = node & cx.dcache_mask;
-                    n_touched = ((s_touched[node >> 6] >> (node & 63)) & 1) != 0;
-                    if (cx.dtag[cs] == node) {
-                        DynU dc;
-                        dc.q[0] = cx.dcache[2 * cs]; dc.q[1] = cx.dcache[2 * cs + 1];
-                        ok = same_dyn(dc, db);
-                    } else if (n_touched) {
-                        DynU dc;
-                        dc.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); dc.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]);
-                        ok = same_dyn(dc, db);
-                    }
-                    ok = __shfl_sync(0xFFFFFFFFu, (int)ok, 0) != 0;
-                }
-                if (ok) { n_adopt = node; break; }
-                /* nothing yet, or worked out on a summary that has changed since: have it redone */
-                PROF_COUNT(14);
-                if (lane == 0) {
-                    vol_store(&sl->wake, 1);
-                    while (ld_vol(&sl->seq) == s1) __nanosleep(20);
-                }
-            }
+                uint4 vb = make_uint4(0, 0, 0, 0);
+                if (lane < 4) vb = sl->bind[lane];
 #ifdef NHD_CHECKS
-            if (n_adopt >= 0) {
-                DynU dx; load_dyn(a, cx, n_adopt, dx);
-                CHK_SANE(dx, n_adopt, 2);
-                if (!same_dyn(dx, db)) CHK_FAIL(3, n_adopt, dx.q[0].x, db.q[0].x);
-                PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
-                const int stx = resolve_decision(a, cx, ti, t, n_adopt, dx, pmx, pkx, msx);
-                if (stx < 2) CHK_FAIL(4, n_adopt, stx, 0);
-                else {
-                    nhd_binding* scratch = &a.out[a.n_pods + wid];      /* spare records behind the batch */
-                    apply_decision(cx, t, n_adopt, dx.d, pmx, pkx, now, scratch);
-                    if (!same_dyn(dx, da)) CHK_FAIL(5, n_adopt, dx.q[0].x, da.q[0].x);
+                {
+                    DynU dx; load_dyn(a, cx, node, dx);
+                    CHK_SANE(dx, node, 2);
+                    PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
+                    const int stx = resolve_decision(a, cx, ti, t, node, dx, pmx, pkx, msx);
+                    if (stx < 2) CHK_FAIL(4, node, stx, 0);
+                    else {
+                        nhd_binding* scratch = &a.out[a.n_pods];      /* spare record behind the batch */
+                        apply_decision(cx, t, node, dx.d, pmx, pkx, now, scratch);
+                        __syncwarp();
+                        if (!same_dyn(dx, da)) CHK_FAIL(5, node, dx.q[0].x, da.q[0].x);
+                        const uint4 sb = lane < 4 ? reinterpret_cast<const uint4*>(scratch)[lane] : make_uint4(0, 0, 0, 0);
+                        if (lane < 4 && (sb.x != vb.x || sb.y != vb.y || sb.z != vb.z || sb.w != vb.w)) CHK_FAIL(8, node, lane, sb.x);
+                    }
+                    /* and it is the first fit of the GPU-less pass */
+                    for (int w = lane; w < (node >> 6); w += 32)
+                        if (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) CHK_FAIL(6, node, w, 0);
+                    if ((ldw<SMEM_BITMAPS>(&F[node >> 6]) & ldw<SMEM_BITMAPS>(&NOGPU[node >> 6])) & ((1ULL << (node & 63)) - 1)) CHK_FAIL(7, node, 0, 0);
+                    if (!((ldw<SMEM_BITMAPS>(&F[node >> 6]) >> (node & 63)) & 1)) CHK_FAIL(9, node, 0, 0);
                 }
-                /* and it is the first fit of the GPU-less pass */
-                for (int w = lane; w < (n_adopt >> 6); w += 32)
-                    if (ldw<SMEM_BITMAPS>(&F[w]) & ldw<SMEM_BITMAPS>(&NOGPU[w])) CHK_FAIL(6, n_adopt, w, 0);
-                if ((ldw<SMEM_BITMAPS>(&F[n_adopt >> 6]) & ldw<SMEM_BITMAPS>(&NOGPU[n_adopt >> 6])) & ((1ULL << (n_adopt & 63)) - 1)) CHK_FAIL(7, n_adopt, 0, 0);
-            }
 #endif
-            if (n_adopt >= 0) {
-                /* commit (a GPU-less node: no BUSY bookkeeping) */
-                store_dyn(a, cx, n_adopt, da);
-                if (lane == 0 && !n_touched) bit_set(s_touched, n_adopt);
-                if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = vbind;
-                adopted = true;
+                store_dyn(a, cx, node, da);
+                if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = vb;
+                commit_node = node;
+                handled = true;
                 PROF_COUNT(13);
+            } else if (kind == NHD_SLOT_DEFER) {
+                /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
+                const bool was_busy = ((ldw<SMEM_BITMAPS>(&BUSY[node >> 6]) >> (node & 63)) & 1) != 0;
+                __syncwarp();
+                if (lane == 0) {
+                    NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + node;
+                    gd->busy_time = now;
+                    atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
+                    a.pend_pod[node] = i;
+                    reinterpret_cast<uint2*>(bout)[0] = make_uint2(NHD_PENDING, (uint32_t)node);
+                    bit_set(s_touched, node);
+                    if (a.min_busy > 0.0 && !was_busy) bit_set(BUSY, node);      /* now - busy_time == 0 < MIN_BUSY_SECS */
+                }
+                commit_node = node;
+                handled = true;
+                PROF_COUNT(12);
+            } else if (kind == NHD_SLOT_NONE) {
+                if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_NO_CANDIDATE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
+                handled = true;
             }
-        } else if (dual && my_class == 1) {
-            /* a GPU pod must see every earlier CPU-only pod resolved: one of them may have spilled onto a GPU node */
-            while (done[0] < before_cpu) __nanosleep(40);
-            __threadfence_block();
         }
-        PROF_MARK(0);      /* pod header */
-        int commit_node = n_adopt;             /* CPU class: node whose summary this pod changed */
-        if (!adopted) do {
+        PROF_MARK(0);      /* pod header / standing decision */
+        if (!handled) do {
 
         /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
-        if (now != cur_now && !dual) {
+        if (now != cur_now) {
             if (now < cur_now) {
                 /* clock went backwards: rebuild from the summaries */
                 n_busy = 0;
@@ -1594,11 +1789,6 @@ sweep_kernel(const SweepArgs a)
             return e;
         };
         for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
-            if (dual && my_class == 0 && pass == 1) {
-                /* spill onto GPU nodes: every earlier GPU pod must be in, and later ones wait for us (done[0]) */
-                while (done[1] < before_gpu) __nanosleep(40);
-                __threadfence_block();
-            }
             /* (1) the cursor: first word with any candidate of this pass */
             int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* warps working ahead advance it too: one read for all lanes */
             const int c_in = c;
@@ -1670,6 +1860,7 @@ sweep_kernel(const SweepArgs a)
                 if (state >= 2) { chosen = node; break; }
                 PROF_COUNT(8);     /* stale candidate */
                 /* resources only shrink inside a batch: the node stays infeasible for this type */
+                __syncwarp();                            /* every lane has read the word */
                 if (lane == 0) bit_clear(F, node);
                 __syncwarp();
             }
@@ -1679,10 +1870,12 @@ sweep_kernel(const SweepArgs a)
             break;
         }
         PROF_MARK(4);      /* loop exit */
+        commit_node = chosen;
 
         bool placed = false;
         if (deferred) {
             /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
+            __syncwarp();                                /* every lane has read the touched word */
             if (lane == 0) {
                 NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + chosen;
                 gd->busy_time = now;
@@ -1694,10 +1887,8 @@ sweep_kernel(const SweepArgs a)
         } else {
             placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
             store_dyn(a, cx, chosen, du);
-            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node;
-             * with standing decisions the touched bit also says "the summary is no longer the snapshot's" */
-            if (lane == 0 && (du.d.n_gpus || use_workers)) bit_set(s_touched, chosen);
-            commit_node = chosen;
+            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
+            if (lane == 0 && du.d.n_gpus) bit_set(s_touched, chosen);
         }
         PROF_MARK(5);      /* assignment */
         if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
@@ -1706,7 +1897,7 @@ sweep_kernel(const SweepArgs a)
                 __syncwarp();
                 if (lane == 0) {
                     bit_set(BUSY, chosen);
-                    if (!dual) a.busy_list[n_busy] = chosen;
+                    if (!cclock) a.busy_list[n_busy] = chosen;
                 }
                 n_busy++;
             }
@@ -1733,36 +1924,22 @@ sweep_kernel(const SweepArgs a)
         }
         } while (0);
         __syncwarp();
-        if (dual) {                                        /* publish: this class is done up to and including pod i */
-            __threadfence_block();
-            if (use_workers && my_class == 0 && commit_node >= 0) {
-                /* every standing decision made for this node is out of date: wake the owners (after the summary
-                 * is in place; a worker lowers its flag before it reads the state) */
-                for (int tt = lane; tt < T; tt += 32)
-                    if (ld_vol(&slots[tt].node) == commit_node) vol_store(&slots[tt].wake, 1);
+        if (fast) {
+            /* every standing decision made for the node this pod changed is out of date; after the ordinary path
+             * the pod's own type as well (it may have given up the node its slot names) */
+            unsigned long long st = handled ? 0ULL : (1ULL << ti);
+            if (commit_node >= 0) {
+                const uint32_t lo = __ballot_sync(0xFFFFFFFFu, lane < T && slots[lane].node == commit_node);
+                const uint32_t hi = T > 32 ? __ballot_sync(0xFFFFFFFFu, lane + 32 < T && slots[lane + 32].node == commit_node) : 0u;
+                st |= (unsigned long long)lo | ((unsigned long long)hi << 32);
             }
-            if (lane == 0) done[my_class] = done_after;
+            if (st & (cpu_mask | gpu_mask))
+                refresh_slots<SMEM_BITMAPS>(a, cx, slots, BM, NOGPU, BUSY, s_touched, W, cursors, lg_lp, now, st & cpu_mask, st & gpu_mask);
         }
-        PROF_MARK(6);      /* write-back */
+        PROF_MARK(6);      /* write-back + refresh */
       }
     }
-    if (cx.write_back) {
-        /* summaries of GPU-less nodes still held only by the cache: once every CPU-only pod is in, warp 0 writes
-         * them out (GPU nodes were written through; the GPU-pod warp may still be rewriting those) */
-        if (wid == 0) {
-            if (lane == 0) done[2] = 1;                     /* every CPU-only pod is in: the workers leave */
-            __syncwarp();
-            for (int sl = lane; sl <= cx.dcache_mask; sl += 32) {
-                const int tg = ld_vol(cx.dtag + sl);
-                if (tg >= 0) {
-                    DynU ev;
-                    ev.q[0] = cx.dcache[2 * sl]; ev.q[1] = cx.dcache[2 * sl + 1];
-                    if (ev.d.n_gpus == 0) { a.dyn[(size_t)tg * 2] = ev.q[0]; a.dyn[(size_t)tg * 2 + 1] = ev.q[1]; }
-                }
-            }
-        }
-    }
-    if (wid == 0) { PROF_FLUSH(a.prof); }
+    PROF_FLUSH(a.prof);
 }
 
 /*

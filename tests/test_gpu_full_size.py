@@ -1,0 +1,77 @@
+"""Hardware parity at the sizes BASELINE.json names: every binding and every final node record of the CUDA
+solver against the C oracle (all host threads, ``nhd_oracle_solve_mt``), not just invariants.
+
+  config 3   16 384 nodes x 1 024 pods   (+GPU / NIC PCI-switch affinity)            in full
+  config 4   65 536 nodes x 4 096 pods   (the metric's configuration)                in full, every sweep mode
+  config 5  262 144 nodes x 8 192 pods   (SR-IOV VFs + node groups N:N)              all nodes, the first 1 024 pods
+                                          (the host needs minutes for all 8 192; NHD_FULL_CONFIG5=1 does them)
+
+The oracle walks every node for every pod like the reference does (nhd/Matcher.py:86-391), so these cost tens of
+seconds of host time each; they are `-m gpu` tests.  A multi-rank run (sharded filter + exchange + replicated
+sweep) is compared with the oracle in tests/test_gpu_multirank.py."""
+import os
+
+import numpy as np
+import pytest
+
+import workload
+from tests import helpers, ref_compare
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('NHD_B200_ALLOW_EMULATED') == '1',
+                                 reason='full sizes on the CPU-emulated device take too long for the suite '
+                                        '(tools/emu_full_size.py does them)')]
+
+THREADS = max(1, os.cpu_count() or 1)
+MODES = (dict(), dict(single_warp=True)) + tuple(dict(cpu_warps=c) for c in (1, 2, 3, 5, 7))
+
+
+def _cuda(recs, speed, pods, now, **mode):
+    from nhd_b200 import solver
+    s = solver.Solver(speed, **mode)
+    try:
+        s.load_nodes(recs)
+        b = s.solve_batch(pods, now)
+        return b, s.read_nodes()
+    finally:
+        s.close()
+
+
+def _check(ob, orecs, cb, crecs, tag):
+    assert helpers.binding_bytes_equal(ob, cb), (tag, helpers.first_binding_diff(ob, cb))
+    assert orecs.tobytes() == crecs.tobytes(), (tag, ref_compare.diff_records(orecs, crecs)[:3])
+
+
+def test_config3_full_size_equals_oracle(oracle_lib):
+    recs, speed, pods, now = workload.make_workload(3)
+    assert len(recs) == 16384 and len(pods) == 1024
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now, threads=THREADS)
+    for mode in MODES[:3]:
+        cb, crecs = _cuda(recs, speed, pods, now, **mode)
+        _check(ob, orecs, cb, crecs, mode)
+    assert int((ob['status'] == 0).sum()) > 900
+
+
+def test_config4_full_size_equals_oracle_in_every_sweep_mode(oracle_lib):
+    recs, speed, pods, now = workload.make_workload(4)
+    assert len(recs) == 65536 and len(pods) == 4096
+    ob, orecs = oracle_lib.solve(recs, speed, pods, now, threads=THREADS)
+    for mode in MODES:
+        cb, crecs = _cuda(recs, speed, pods, now, **mode)
+        _check(ob, orecs, cb, crecs, mode)
+    assert int((ob['status'] == 0).sum()) > 3000
+
+
+def test_config5_full_cluster_equals_oracle(oracle_lib):
+    recs, speed, pods, now = workload.make_workload(5)
+    assert len(recs) == 262144 and len(pods) == 8192
+    n = len(pods) if os.environ.get('NHD_FULL_CONFIG5') == '1' else 1024
+    ob, orecs = oracle_lib.solve(recs, speed, pods[:n], now[:n], threads=THREADS)
+    for mode in MODES[:2]:
+        cb, crecs = _cuda(recs, speed, pods[:n], now[:n], **mode)
+        _check(ob, orecs, cb, crecs, mode)
+    # and the whole stream is at least self-consistent across sweep modes
+    full = [_cuda(recs, speed, pods, now, **mode) for mode in MODES[:2]]
+    assert helpers.binding_bytes_equal(full[0][0], full[1][0])
+    assert full[0][1].tobytes() == full[1][1].tobytes()
+    assert helpers.binding_bytes_equal(full[0][0][:n], ob)

@@ -98,6 +98,9 @@ struct nhd_handle {
     unsigned long long* d_prof = nullptr;
     int* d_vresult = nullptr;
     uint64_t* d_memo = nullptr;
+    uint8_t* d_mapt = nullptr;            /* GetNumaGroupIdx table of the direct path */
+    uint32_t* d_sigs = nullptr;           /* per-NUMA NIC signatures */
+    ClsFast* d_cls_fast = nullptr;        /* per hardware class */
     double now0 = 0.0;
     bool const_clock = true;
     int n_names = 0;
@@ -220,7 +223,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); 
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_mapt); cudaFree(h->d_sigs); cudaFree(h->d_cls_fast); 
 #ifdef NHD_CHECKS
     cudaFreeHost(h->d_prof);
 #else
@@ -274,6 +277,13 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
 #endif
     CK(cudaMalloc((void**)&h->d_class_slots, (size_t)CLASS_SLOTS * sizeof(ClassSlot)));
     CK(cudaMemsetAsync(h->d_class_slots, 0, (size_t)CLASS_SLOTS * sizeof(ClassSlot), h->stream));
+    CK(cudaMalloc((void**)&h->d_mapt, (size_t)((MAPT_BYTES + 15) & ~15)));
+    CK(cudaMalloc((void**)&h->d_sigs, (size_t)FAST_NSIG * 4));
+    CK(cudaMemsetAsync(h->d_sigs, 0, (size_t)FAST_NSIG * 4, h->stream));
+    CK(cudaMalloc((void**)&h->d_cls_fast, (size_t)CLASS_SLOTS * sizeof(ClsFast)));
+    CK(cudaMemsetAsync(h->d_cls_fast, 0, (size_t)CLASS_SLOTS * sizeof(ClsFast), h->stream));
+    mapt_kernel<<<(MAPT_BYTES + 127) / 128, 128, 0, h->stream>>>(h->d_mapt);
+    CK(cudaGetLastError());
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             FILTER_STAGES * SUPER_BYTES + TYPES_SMEM_MAX * (int)sizeof(PodType)));
     CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -340,6 +350,7 @@ static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, co
     classify_claim_kernel<<<(n + threads - 1) / threads, threads, 0, h->stream>>>(h->d_nodes, d_idx, n, h->d_class_slots, h->d_class);
     CK(cudaGetLastError());
     classify_verify_kernel<<<(n + threads - 1) / threads, threads, 0, h->stream>>>(h->d_nodes, d_idx, n, h->d_class_slots, h->d_class);
+    cls_fast_kernel<<<(CLASS_SLOTS + 255) / 256, 256, 0, h->stream>>>(h->d_class_slots, h->d_cls_fast, h->d_sigs);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return NHD_OK;
@@ -622,6 +633,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         }
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
+        sa.mapt = h->d_mapt; sa.sigs = h->d_sigs; sa.cls_fast = h->d_cls_fast;
         sa.min_busy = h->params.min_busy_secs;
         memcpy(sa.cap, h->cap, sizeof(sa.cap));
         /* shared memory: memo front | pod types | cursors | (bitmaps when they fit) */
@@ -629,7 +641,8 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
                       (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16;
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
-        if (T <= SWEEP_TYPES_SMEM_MAX) smem += (size_t)T * sizeof(TSlot);
+        if (T <= FAST_MAX_TYPES)                /* standing decisions + their tables */
+            smem += (size_t)T * (sizeof(TSlot) + 256 + 2 * FAST_NSIG * 64 + 16 + sizeof(TyFast)) + ((MAPT_BYTES + 15) & ~15);
         const size_t with_bitmaps = smem + bm_bytes;
         if (with_bitmaps <= (size_t)h->smem_optin) {
             sweep_kernel<true><<<1, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);

@@ -345,9 +345,9 @@ filter_kernel(const FilterArgs a)
 #endif
 
 constexpr int SWEEP_THREADS = 256;
-constexpr int SMEMO_SLOTS = 1024;                 /* shared-memory front of the mapping memo (16 B)  */
+constexpr int SMEMO_SLOTS = 256;                  /* shared-memory front of the mapping memo (16 B)  */
 constexpr int DMEMO_SLOTS = 128;                  /* decision memo (48 B entries), generic path only  */
-constexpr int SPMEMO_SLOTS = 1024;                /* NIC sub-problem memo (16 B entries)             */
+constexpr int SPMEMO_SLOTS = 256;                 /* NIC sub-problem memo (16 B entries)             */
 
 constexpr int DCACHE_SLOTS = 512;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
@@ -362,8 +362,8 @@ struct SweepArgs {
     const double* now;
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
-    int dual;                    /* 1: constant clock -> GPU pods and CPU-only pods on separate warps */
-    int n_cpu_warps;             /* dual: warps walking the CPU-only class (speculate ahead, commit in pod order) */
+    int dual;                    /* 1: constant clock -> standing decisions per pod type (see sweep_kernel) */
+    int n_cpu_warps;             /* bits 8..: debug switches */
     int n_names;                 /* > 0: per-pod node-group masks, one bitmap per name after BUSY */
     uint64_t names_used;
     const uint64_t* pod_groups;  /* [n_pods] when n_names > 0 */
@@ -373,6 +373,9 @@ struct SweepArgs {
     int32_t* busy_list;          /* nodes whose BUSY bit is set */
     int32_t* pend_pod;           /* [n_nodes] pod whose resolution is pending on the node */
     uint64_t* memo;              /* MEMO_SLOTS x 2 words (global, persists across batches) */
+    const uint8_t* mapt;         /* MAPT_BYTES: GetNumaGroupIdx table of the direct path (mapt_kernel, once per handle) */
+    const uint32_t* sigs;        /* FAST_NSIG per-NUMA NIC signatures (cls_fast_kernel, at load / update time) */
+    const struct ClsFast* cls_fast;   /* [CLASS_SLOTS] */
     unsigned long long* prof;    /* debug counters (NHD_PROFILE builds) */
     double min_busy;
     double cap[NHD_MAX_SPEED_CLASSES];
@@ -1130,329 +1133,259 @@ __device__ __noinline__ void resolve_pending(const SweepArgs& a, const SweepCtx&
  * On a constant clock (the batch case) the sweep keeps, for every pod type, what the next pod of that type
  * will do — a pure function of (type, first-fit node, that node's summary):
  *   CPU-only types  the first-fit node of the GPU-less pass (first set bit of F[t] & NOGPU, Matcher.py:412-416),
- *                   the mapping, the node's summary after the pod and the binding header (NHD_SLOT_FAST);
+ *                   the mapping and the node's summary after the pod (NHD_SLOT_FAST);
  *   GPU types       the first candidate that is not busy (Matcher.py:107-111); if no pod of this batch was bound
  *                   there its snapshot bit is exact and the pod only stamps the node (NHD_SLOT_DEFER).
- * A pod then commits its type's slot in a handful of instructions, and the slots made for the node it changed
- * are worked out again at once — all of them in one pass, 32 / LP types side by side, LP = 2^G lanes per type
- * (one NUMA tuple of the groups per lane; G <= 2 in the reference's deployments, so eight types per pass).
- * Anything else (spills onto GPU nodes, GPU pods on nodes already bound to, nodes with more than two NUMA
- * nodes or without a hardware class, PCI-mode CPU pods, more groups than lanes) is NHD_SLOT_SLOW: the pod
- * takes the ordinary path below.  One warp does all of this in pod order: no inter-warp hand-off exists.
+ * A pod commits its type's slot in a handful of instructions; the slots made for the node it changed are then
+ * worked out again, ONE LANE PER TYPE, all types side by side.  So that this is short, everything a decision
+ * needs is tabulated when the sweep starts (all 256 threads, a few microseconds):
+ *   TB    [type][smt][numa][free cores]   -> which (G+1)-tuples pass the CPU stage on that socket (Matcher.py:203-212)
+ *   SUB0/1[type][NIC signature][in use]   -> per G-tuple: does the NIC stage (Matcher.py:242-268) survive on NUMA 0 / 1
+ *                                            for the groups the tuple puts there, and which NodeNic.idx they get
+ *                                            (nic_sub_solve: the reference's order, fp64 subtraction order)
+ *   MAPT  [CPU mask][NIC mask]            -> GetNumaGroupIdx (Matcher.py:423-452), i.e. CPython set order; a pure
+ *                                            function, filled once per handle (mapt_kernel)
+ *   GD    [type][smt][tuple]              -> cores the groups take from each socket
+ *   CLS   [hardware class]                -> NIC list indices per NUMA node and the two NIC signatures
+ * and a decision is five table reads and some arithmetic.  The direct path covers CPU-only NUMA-mode types with
+ * at most two groups on 2-NUMA nodes with a hardware class and at most four NICs per NUMA node (the reference's
+ * deployment shape).  Anything else — spills onto GPU nodes, GPU pods on nodes already bound to, other node or
+ * type shapes — is NHD_SLOT_SLOW: the pod takes the ordinary path below.  One warp does all of this in pod
+ * order: no inter-warp hand-off exists.  The binding of a directly decided pod is written out in packed form
+ * (NHD_PENDING_FAST) and formatted by resolve_kernel, off the sequential chain.
  */
 #define NHD_SLOT_SLOW   0
 #define NHD_SLOT_FAST   1
 #define NHD_SLOT_DEFER  2
 #define NHD_SLOT_NONE   3
 
+#define NHD_PENDING_FAST 101          /* internal binding status: node and packed mapping known, header not formatted yet */
+
+constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
+constexpr int FAST_NSIG = 4;          /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
+constexpr int MAPT_BYTES = 4096 + 64;
+
 struct TSlot {
     int node;                /* node the slot was made for (-1: none)                                   */
     int kind;                /* NHD_SLOT_*                                                              */
-    int pad_[2];
+    uint32_t dec;            /* FAST: tuple | misc NUMA << 2 | NIC picks on NUMA 0 << 8 | on NUMA 1 << 16 */
+    uint32_t w14;            /* FAST: NodeDyn.consumed before the pod (prefix offsets of its core ids)  */
     uint4 after[2];          /* FAST: NodeDyn once the pod is placed                                    */
-    uint4 bind[4];           /* FAST: first 64 bytes of the nhd_binding (the rest is zero until the core ids) */
 };
-static_assert(sizeof(TSlot) == 112, "TSlot is seven 16-byte chunks");
+static_assert(sizeof(TSlot) == 48, "TSlot is three 16-byte chunks");
 
-__device__ __forceinline__ uint32_t spread16(uint32_t x)       /* bit i -> bit 2i */
+struct ClsFast {             /* per hardware class, 16 bytes */
+    uint32_t li0, li1;       /* byte j = index in Node.nics of the j-th NIC of NUMA 0 / 1 */
+    uint8_t sig0, sig1;      /* signature ids of the two NUMA nodes */
+    uint8_t n0, n1;          /* NICs per NUMA node */
+    uint32_t ok;             /* 1: covered by the direct path */
+};
+
+struct TyFast {              /* per pod type, 16 bytes */
+    uint8_t G, n_misc, misc_smt, nic_groups;
+    uint8_t direct;          /* CPU-only, NUMA mode, G <= 2 */
+    uint8_t pad_[3];
+    int32_t hugepages_gb;
+    uint32_t pad2_;
+};
+
+struct FastTables {
+    const uint8_t* tb;       /* [T][2][2][64] */
+    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p */
+    const uint32_t* sub1;
+    const uint8_t* mapt;     /* MAPT_BYTES */
+    const uint16_t* gd;      /* [T][2][4] */
+    const TyFast* ty;        /* [T] */
+    const ClsFast* cls;      /* global, [CLASS_SLOTS] */
+};
+
+/* GetNumaGroupIdx for CPU-only pods on 2-NUMA nodes as a table (every GPU tuple passes the GPU stage):
+ * [0, 4096): G = 2, index = CPU mask (8 bits, q = 2p + m) << 4 | NIC mask (4 bits, p); [4096, 4160): G = 1,
+ * index = CPU mask (4 bits) << 2 | NIC mask (2 bits).  Value: 0x80 | tuple | misc NUMA << 2, or 0. */
+__global__ void mapt_kernel(uint8_t* mapt)
 {
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MAPT_BYTES) return;
+    const int G = i < 4096 ? 2 : 1;
+    const int j = i < 4096 ? i : i - 4096;
+    TMask ma = tm_zero(), mb = tm_zero(), mc = tm_zero();
+    ma.w[0] = (1u << (1 << G)) - 1;
+    mb.w[0] = G == 2 ? (uint32_t)(j >> 4) : (uint32_t)(j >> 2);
+    mc.w[0] = G == 2 ? (uint32_t)(j & 15) : (uint32_t)(j & 3);
+    int ps = 0, ms = 0;
+    mapt[i] = choose_mapping(2, G, ma, mb, mc, &ps, &ms) ? (uint8_t)(0x80 | ps | (ms << 2)) : (uint8_t)0;
 }
 
-struct FastOut {
-    int state;                       /* 0 idle lane, 1 the node does not take the pod, 2 placed */
-    uint32_t pn, idx, li, ms;        /* the mapping, one byte per group (PMap) */
-    uint32_t claimed;
-    int ncl;
-};
+/*
+ * Per hardware class (ClassSlot key = the static description of its nodes): the NIC list indices of each NUMA
+ * node in NodeNic.idx order and the signature ids (NIC count + speed classes in that order) of the two NUMA
+ * nodes.  Runs after classification (load / update); signatures are only ever added.
+ */
+__global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cls, uint32_t* sigs)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= CLASS_SLOTS) return;
+    ClsFast cf;
+    cf.li0 = cf.li1 = 0; cf.sig0 = cf.sig1 = 0; cf.n0 = cf.n1 = 0; cf.ok = 0;
+    if (slots[s].hash != 0ULL) {
+        const uint32_t* key = slots[s].key;
+        const int n_numa = (int)((key[16] >> 16) & 0xFF);
+        const uint32_t m[2] = {key[4], key[5]};
+        const unsigned long long sp0 = (unsigned long long)key[12] | ((unsigned long long)key[13] << 32);
+        const unsigned long long sp1 = (unsigned long long)key[14] | ((unsigned long long)key[15] << 32);
+        const int n0 = popc32(m[0]), n1 = popc32(m[1]);
+        bool ok = n_numa == 2 && n0 <= 4 && n1 <= 4;
+        uint32_t li[2] = {0, 0};
+        uint8_t sg[2] = {0, 0};
+        for (int k = 0; k < 2 && ok; k++) {
+            uint32_t sv = 0x80000000u | (uint32_t)(k ? n1 : n0);
+            int j = 0;
+            for (uint32_t f = m[k]; f; f &= f - 1, j++) {
+                const int l = ctz32(f);
+                li[k] |= (uint32_t)l << (8 * j);
+                sv |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 + 4 * j);
+            }
+            int id = -1;
+            for (int q = 0; q < FAST_NSIG; q++) {
+                const uint32_t old = atomicCAS(&sigs[q], 0u, sv);
+                if (old == 0u || old == sv) { id = q; break; }
+            }
+            if (id < 0) ok = false; else sg[k] = (uint8_t)id;
+        }
+        if (ok) { cf.li0 = li[0]; cf.li1 = li[1]; cf.sig0 = sg[0]; cf.sig1 = sg[1]; cf.n0 = (uint8_t)n0; cf.n1 = (uint8_t)n1; cf.ok = 1; }
+    }
+    cls[s] = cf;
+}
+
+/* bit 7 of each byte of x -> bits 0..3 */
+__device__ __forceinline__ uint32_t gather_b7(uint32_t x)
+{
+    return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+}
 
 /*
- * resolve_cpu2 for 32 / LP problems at once: lanes [j*LP, (j+1)*LP) work on problem j = (type ti, node with
- * summary du); lane p of a group owns the NUMA tuple p of the groups (digit g = bit G-1-g) and both positions
- * of the misc cores.  Same tables and the same results as resolve_cpu2:
- *   CPU stage (Matcher.py:203-212)  two compares per lane against the type's per-tuple socket demands;
- *   NIC stage (Matcher.py:242-268)  factorised per NUMA node: lane p looks up "groups on NUMA 0" and "groups on
- *                                   NUMA 1" of its tuple in the sub-problem memo (nic_sub_solve on a miss);
- *   mapping   (Matcher.py:423-452)  the mapping memo on the three masks, gathered with three ballots;
- *   claim order (NHDScheduler.py:302) of the chosen tuple's NICs.
- * Preconditions (checked by the caller, `have` false otherwise): CPU-only type, NUMA mode, 2^G <= LP, 2-NUMA
- * node with a hardware class.  All 32 lanes must call.
+ * One lane, one pod type: what AttemptScheduling does with a pod of type ti on a node with summary du
+ * (CPU-only type and node shape covered by the tables; the caller checks TyFast.direct).
+ * Returns 0 (node or class outside the direct path), 1 (FindNode would not offer the node), 2 (placed).
  */
-__device__ __forceinline__ void fast_eval(const SweepArgs& a, const SweepCtx& cx, int LP, bool have, int ti, int node,
-                                          const DynU& du, FastOut& o)
+__device__ __forceinline__ int fast_eval(const FastTables& ft, int ti, const DynU& du, double now, uint32_t& dec, DynU& da)
 {
-    const int lane = cx.lane, p = lane & (LP - 1), base = lane - p;
-    const uint32_t lpm = LP >= 32 ? 0xFFFFFFFFu : ((1u << LP) - 1);
-    if (!have) ti = 0;
-    const PodType& t = cx.types[ti];
-    const int G = t.G, gmask = (1 << G) - 1, nq = 1 << (G + 1);
-    const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
-    const bool tup = have && p <= gmask;
-    o.state = 0; o.pn = o.idx = o.li = o.ms = o.claimed = 0; o.ncl = 0;
-
-    /* ---- CPU stage: q = 2p (misc on NUMA 0) and q = 2p + 1 ---- */
-    const uint32_t nbw = reinterpret_cast<const uint32_t*>(cx.s_needb)[(ti * 2 + (smt ? 1 : 0)) * 16 + (p & 15)];
-    const uint32_t fc0 = du.d.fc[0], fc1 = du.d.fc[1];
-    const bool okB0 = tup && (nbw & 0xFF) <= fc0 && ((nbw >> 8) & 0xFF) <= fc1;
-    const bool okB1 = tup && ((nbw >> 16) & 0xFF) <= fc0 && (nbw >> 24) <= fc1;
-
-    /* ---- static NIC layout of the node's hardware class (table shared with resolve_cpu2) ---- */
-    ClsNic* ce = &cx.clsnic[du.d.hw_class & cx.clsnic_mask];
-    const uint32_t want = (uint32_t)du.d.hw_class + 1u;
-    uint32_t m0 = ce->m0, m1 = ce->m1, nk = ce->nk, spk0 = ce->spk0, spk1 = ce->spk1;
-    unsigned long long sp0 = ce->sp0, sp1 = ce->sp1;
-    const bool cmiss = have && ce->tag != want;
-    if (cmiss) {
-        const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
-        const uint4 c7 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 7));
-        m0 = c5.x; m1 = c5.y;
-        sp0 = (unsigned long long)c7.x | ((unsigned long long)c7.y << 32);
-        sp1 = (unsigned long long)c7.z | ((unsigned long long)c7.w << 32);
-        const int n0 = popc32(m0), n1 = popc32(m1);
-        nk = (uint32_t)n0 | ((uint32_t)n1 << 8) | ((n0 > 8 || n1 > 8) ? 0x80000000u : 0u);
-        spk0 = spk1 = 0;
-        int j = 0;
-        for (uint32_t f = m0; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk0 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
-        j = 0;
-        for (uint32_t f = m1; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk1 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
-    }
-    {
-        /* one writer per instruction: lanes of different problems may map to the same table slot */
-        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cmiss && p == 0);
-        for (uint32_t m = mm; m; m &= m - 1) {
-            if (lane == ctz32(m)) {
-                ce->tag = 0;
-                ce->m0 = m0; ce->m1 = m1; ce->nk = nk; ce->sp0 = sp0; ce->sp1 = sp1; ce->spk0 = spk0; ce->spk1 = spk1;
-                ce->tag = want;
-            }
-            __syncwarp();
-        }
-    }
-
-    /* ---- NIC stage: the two halves of tuple p ---- */
-    const int S1 = tup ? (int)(__brev((unsigned)p) >> (32 - G)) : 0;        /* groups on NUMA 1 */
-    const int S0 = gmask & ~S1;
+    if (((du.d.info >> 2) & 7) != 2 || du.d.hw_class == NHD_NO_CLASS) return 0;
+    const ClsFast cf = ft.cls[du.d.hw_class];
+    if (!cf.ok) return 0;
+    const TyFast ty = ft.ty[ti];
+    const int smt = (du.d.info & NHD_DYN_SMT) ? 1 : 0;
     const uint32_t inuse = du.d.nic_inuse;
-    const bool wide = (nk >> 31) != 0;
-    uint32_t e01[2] = {0, 0};
-    bool smiss[2] = {false, false};
-    uint32_t skeys[2], skey2s[2], inuse_ks[2];
-    uint4* ses[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const uint32_t mk = k ? m1 : m0;
-        const int S = k ? S1 : S0;
-        uint32_t inuse_k = 0;
-        {
-            int jl = 0;
-            for (uint32_t f = mk; f; f &= f - 1, jl++) inuse_k |= ((inuse >> ctz32(f)) & 1u) << jl;
-        }
-        const uint32_t n_k = (k ? (nk >> 8) : nk) & 0xFF;
-        const uint32_t skey = 0x80000000u | (uint32_t)ti | ((uint32_t)S << 12) | (n_k << 16) |
-                              (wide ? (0x40000000u | ((uint32_t)k << 24)) : 0u);
-        const uint32_t skey2 = wide ? (uint32_t)du.d.hw_class : (k ? spk1 : spk0);
-        uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u ^ skey2 * 0xC2B2AE3Du;
-        sh ^= sh >> 15;
-        uint4* se = &cx.spmemo[sh & cx.spmemo_mask];
-        const uint4 sv = *se;
-        if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) e01[k] = sv.w;
-        else smiss[k] = tup;
-        skeys[k] = skey; skey2s[k] = skey2; inuse_ks[k] = inuse_k; ses[k] = se;
-    }
+    /* NICs in use, per NUMA node, in NodeNic.idx order */
+    uint32_t iu0 = 0, iu1 = 0;
+    for (int j = 0; j < cf.n0; j++) iu0 |= ((inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;
+    for (int j = 0; j < cf.n1; j++) iu1 |= ((inuse >> ((cf.li1 >> (8 * j)) & 31)) & 1u) << j;
+    const uint32_t w0 = ft.sub0[(ti * FAST_NSIG + cf.sig0) * 16 + iu0];
+    const uint32_t w1 = ft.sub1[(ti * FAST_NSIG + cf.sig1) * 16 + iu1];
+    const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
+    const uint32_t fc0 = du.d.fc[0], fc1 = du.d.fc[1];
+    const uint32_t mB = ft.tb[((ti * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
+                        ft.tb[((ti * 2 + smt) * 2 + 1) * 64 + (fc1 < 63 ? fc1 : 63)];      /* Matcher.py:203-212 */
+    const uint32_t mv = ty.G == 2 ? ft.mapt[(mB << 4) | mC] : ft.mapt[4096 + (((mB & 15) << 2) | (mC & 3))];
+#ifdef NHD_DEBUG_PRINT
+    printf("fast_eval ti=%d G=%d smt=%d cls=%d sig=%d,%d n=%d,%d iu=%u,%u w0=%08x w1=%08x mC=%x fc=%u,%u mB=%x mv=%x hp=%d/%d\n", ti, ty.G, smt, du.d.hw_class, cf.sig0, cf.sig1, cf.n0, cf.n1, iu0, iu1, w0, w1, mC, fc0, fc1, mB, mv, ty.hugepages_gb, du.d.free_hugepages_gb);
+#endif
+    if (!(mv & 0x80) || ty.hugepages_gb > du.d.free_hugepages_gb) return 1;    /* Matcher.py:78, :349 */
+    const int ps = mv & 3, ms = (mv >> 2) & 1;
+    /* bookkeeping of SetPhysicalIdsFromMapping on the summary (apply_decision for a CPU-only pod) */
+    const uint32_t gd = ft.gd[(ti * 2 + smt) * 4 + ps];
+    uint32_t f0 = fc0 - (gd & 0xFF), f1 = fc1 - (gd >> 8);
     {
-        /* misses are cold: one lane at a time solves and stores (16-byte entries, one writer per instruction) */
-        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, smiss[0] || smiss[1]);
-        for (uint32_t m = mm; m; m &= m - 1) {
-            if (lane == ctz32(m)) {
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                    if (smiss[k]) {
-                        e01[k] = nic_sub_solve(a.cap, t, k ? S1 : S0, k ? m1 : m0, inuse, sp0, sp1);
-                        *ses[k] = make_uint4(skeys[k], inuse_ks[k], skey2s[k], e01[k]);
-                    }
-            }
-            __syncwarp();
-        }
+        const uint32_t avail = ms ? f1 : f0;
+        const uint32_t n = ty.n_misc;
+        const uint32_t wd = !smt ? n : (ty.misc_smt ? (n + 1) / 2 : (n < avail ? n : avail));     /* batch_width */
+        if (ms) f1 -= wd; else f0 -= wd;
     }
-    const bool okC = tup && (e01[0] >> 31) && (e01[1] >> 31);
-
-    /* ---- the three masks of every problem ---- */
-    const uint32_t bC = __ballot_sync(0xFFFFFFFFu, okC);
-    const uint32_t bB0 = __ballot_sync(0xFFFFFFFFu, okB0);
-    const uint32_t bB1 = __ballot_sync(0xFFFFFFFFu, okB1);
-    const uint32_t cb = (bC >> base) & lpm, b0 = (bB0 >> base) & lpm, b1 = (bB1 >> base) & lpm;
-    const uint32_t balB = spread16(b0) | (spread16(b1) << 1), balC = spread16(cb);
-    const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
-    bool feas = have && t.pod.hugepages_gb <= du.d.free_hugepages_gb && balB != 0 && balC != 0;     /* Matcher.py:78 */
-
-    /* ---- GetNumaGroupIdx: mapping memo (hit inline; a miss is cold and done by one lane at a time) ---- */
-    int v = -1;
+    const uint32_t e0 = (w0 >> (8 * ps)) & 0xFF, e1 = (w1 >> (8 * ps)) & 0xFF;
+    uint32_t claim = 0;
     {
-        const uint32_t tag = 0x80000000u | (2u << 24) | ((uint32_t)G << 16);
-        uint32_t h32 = (balB * 0x9E3779B1u) ^ (balC * 0x85EBCA77u) ^ (balA * 0xC2B2AE3Du) ^ tag;
-        h32 ^= h32 >> 15;
-        const int ss = (int)(h32 & (uint32_t)cx.smemo_mask);
-        const uint4 e = cx.smemo[ss];
-        bool mmiss = false;
-        if (e.x == balA && e.y == balB && e.z == balC && (e.w & 0xFFFF0000u) == tag) {
-            const int vv = (int)(e.w & 0xFFFF);
-            v = vv == 0xFFFF ? -1 : vv;
-        } else mmiss = feas;
-        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, mmiss && p == 0);
-        for (uint32_t m = mm; m; m &= m - 1) {
-            if (lane == ctz32(m)) v = choose_mapping_slow(cx.smemo, ss, a.memo, 2, G, balA, balB, balC, tag);
-            __syncwarp();
+        int m0 = 0, m1 = 0;                              /* members seen so far on NUMA 0 / 1 */
+        for (int g = 0; g < ty.G; g++) {
+            const int numa = (ps >> (ty.G - 1 - g)) & 1;
+            const uint32_t x = numa ? (e1 >> (2 * m1)) & 3 : (e0 >> (2 * m0)) & 3;
+            if (numa) m1++; else m0++;
+            const uint32_t l = ((numa ? cf.li1 : cf.li0) >> (8 * x)) & 31;
+            if ((ty.nic_groups >> g) & 1) claim |= 1u << l;
         }
-        const int vl = __shfl_sync(0xFFFFFFFFu, v, base);          /* the group's leader did the miss */
-        if (mmiss) v = vl;
-    }
-    if (!feas) v = -1;
-
-    /* ---- the chosen tuple's NIC picks: held by lane ps of the group ---- */
-    const int ps = v >= 0 ? (v & 0xFF) : 0;
-    const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, e01[0], base + (ps & (LP - 1)));
-    const uint32_t x1 = __shfl_sync(0xFFFFFFFFu, e01[1], base + (ps & (LP - 1)));
-    if (!have) return;
-    if (v < 0) { o.state = 1; return; }
-    o.state = 2;
-    o.ms = (uint32_t)(v >> 8);
-    const int s1 = (int)(__brev((unsigned)ps) >> (32 - G));
-    o.pn = ((uint32_t)s1 & 1u) | (((uint32_t)s1 & 2u) << 7) | (((uint32_t)s1 & 4u) << 14) | (((uint32_t)s1 & 8u) << 21);   /* one byte per group */
-    uint32_t rec = 0;
-    int n_rec = 0, e0 = 0, e1 = 0;
-    for (int g = 0; g < G; g++) {
-        uint32_t l, x;
-        if ((s1 >> g) & 1) { x = (x1 >> (8 * e1)) & 0x7F; e1++; l = (uint32_t)nth_bit32(m1, (int)x); }
-        else { x = (x0 >> (8 * e0)) & 0x7F; e0++; l = (uint32_t)nth_bit32(m0, (int)x); }     /* NodeNic.idx -> index in Node.nics */
-        o.li |= l << (8 * g);
-        o.idx |= x << (8 * g);
-        if ((t.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
-    }
-    o.claimed = claimed_order_packed(rec, n_rec, o.ncl);
-}
-
-/*
- * apply_decision for one lane: a placed CPU-only pod (no GPUs, cannot fail) on the summary `du`: the summary
- * after the pod (SetBusy + the bookkeeping of SetPhysicalIdsFromMapping, Node.py:663-841, + ClaimPodNICResources)
- * and the first 64 bytes of the binding.
- */
-__device__ __forceinline__ void fast_apply(const PodType& t, int node, const DynU& du, const FastOut& o, double now,
-                                           DynU& da, uint4* b)
-{
-    const int G = t.G;
-    const bool smt_node = (du.d.info & NHD_DYN_SMT) != 0;
-    const uint8_t* cl = smt_node ? t.cl_smt : t.cl_nosmt;
-    uint32_t fcw = du.q[0].x;
-    const uint32_t fc_before = fcw, w14 = du.q[0].y;
-    for (int g = 0; g < G; g++) fcw -= (uint32_t)cl[g] << (8 * ((o.pn >> (8 * g)) & 0xFF));
-    {
-        const int sh = 8 * (int)o.ms;
-        const int wd = batch_width(smt_node, (t.pod.flags & NHD_POD_MISC_SMT) != 0, t.pod.n_misc, (fcw >> sh) & 0xFF);
-        fcw -= (uint32_t)wd << sh;
     }
     da.q[0] = du.q[0]; da.q[1] = du.q[1];
+    const uint32_t fcw = (du.q[0].x & 0xFFFF0000u) | f0 | (f1 << 8);
     da.q[0].x = fcw;
-    da.q[0].y = w14 + (fc_before - fcw);                 /* per byte, no borrows: each width <= what is free */
+    da.q[0].y = du.q[0].y + (du.q[0].x - fcw);              /* per byte, no borrows: each width <= what is free */
     da.d.info |= NHD_DYN_TOUCHED;
-    da.d.busy_time = now;                                 /* NHDScheduler.py:289 */
-    if (t.pod.hugepages_gb > 0) da.d.free_hugepages_gb -= t.pod.hugepages_gb;      /* Node.py:794-796 */
-    for (int e = 0; e < o.ncl; e++) da.d.nic_inuse |= 1u << ((o.claimed >> (8 * e)) & 0xFF);   /* Node.py:644-646 */
-    /* bytes: 12 gpu_numa[4] 16 cpu_numa[5] 21 nic_numa[4] 25 nic_idx[4] 29 nic_list_index[4] 33 claimed[4] 40 gpu_index[16] 56 cores */
-    const uint32_t w2 = (uint32_t)G | ((uint32_t)o.ncl << 24);
-    const uint32_t w4 = G < 4 ? (o.pn | (o.ms << (8 * G))) : o.pn;
-    const uint32_t w5 = (G == 4 ? o.ms : 0u) | (o.pn << 8);
-    const uint32_t w6 = (o.pn >> 24) | (o.idx << 8);
-    const uint32_t w7 = (o.idx >> 24) | (o.li << 8);
-    const uint32_t w8 = (o.li >> 24) | (o.claimed << 8);
-    const uint32_t w9 = o.claimed >> 24;
-    b[0] = make_uint4(NHD_PLACED, (uint32_t)node, w2, o.pn);
-    b[1] = make_uint4(w4, w5, w6, w7);
-    b[2] = make_uint4(w8, w9, 0, 0);
-    b[3] = make_uint4(0, 0, w14, 0);
+    da.d.nic_inuse = inuse | claim;                           /* Node.py:644-646 */
+    if (ty.hugepages_gb > 0) da.d.free_hugepages_gb -= ty.hugepages_gb;      /* Node.py:794-796 */
+    da.d.busy_time = now;                                     /* NHDScheduler.py:289 */
+    dec = (uint32_t)ps | ((uint32_t)ms << 2) | (e0 << 8) | (e1 << 16);
+    return 2;
+}
+
+/* summary of a node for the direct path: the cache, else HBM — through L1 while no pod of the batch has been
+ * bound to the node (its summary is the snapshot's, immutable), from L2 otherwise */
+__device__ __forceinline__ void fast_load_dyn(const SweepArgs& a, const SweepCtx& cx, const uint64_t* touched, int node, DynU& du)
+{
+    const int cs = node & cx.dcache_mask;
+    if (cx.dtag[cs] == node) { du.q[0] = cx.dcache[2 * cs]; du.q[1] = cx.dcache[2 * cs + 1]; }
+    else if ((touched[node >> 6] >> (node & 63)) & 1) { du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]); }
+    else { du.q[0] = a.dyn[(size_t)node * 2]; du.q[1] = a.dyn[(size_t)node * 2 + 1]; }
 }
 
 /*
- * Work the standing decisions of the given types out again (see above): CPU-only types 32 / LP at a time with
- * fast_eval, GPU types one per lane.  A node that does not take a CPU-only type loses the type's bit for good
- * (resources only shrink inside a batch) and the type moves on to its next candidate.
+ * Work the standing decisions of the types in `stale` out again, lane t = type t.  CPU-only types start from
+ * (node, st) when the caller just committed there (node >= 0), else from their first candidate; a node that
+ * does not take the type loses the type's bit for good (resources only shrink inside a batch) and the lane moves
+ * on to the next candidate.  GPU types look for their first candidate that is not busy.
  */
 template <bool SMEM_BITMAPS>
-__device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx& cx, TSlot* slots, uint64_t* BM, const uint64_t* NOGPU,
-                                              const uint64_t* BUSY, const uint64_t* touched, int W, int32_t* cursors, int lg_lp,
-                                              double now, unsigned long long cpu_stale, unsigned long long gpu_stale)
+__device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx& cx, const FastTables& ft, TSlot* slots,
+                                              uint64_t* BM, const uint64_t* NOGPU, const uint64_t* BUSY, const uint64_t* touched,
+                                              int W, int32_t* cursors, double now, uint32_t stale, uint32_t cpu_mask,
+                                              int node0, const DynU& st)
 {
-    const int lane = cx.lane, LP = 1 << lg_lp, p = lane & (LP - 1), gi = lane >> lg_lp, NP = 32 >> lg_lp;
-    while (cpu_stale) {
-        __syncwarp();
-        int ti = -1;
-        {
-            unsigned long long m = cpu_stale;
-            for (int j = 0; j < gi && m; j++) m &= m - 1;
-            if (m) ti = ctz64(m);
-        }
-        const bool have = ti >= 0;
-        uint64_t* F = BM + (size_t)(have ? ti : 0) * W;
-        int node = -1, c_new = -1;
-        DynU du;
-        du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0];
-        if (have) {
-            /* first candidate of the GPU-less pass (Matcher.py:412-416); the lanes of a group walk together */
-            int c = cursors[ti * 3 + 0];
-            const int c_in = c;
-            uint64_t w = 0;
-            while (c < W) {
-                w = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
-                if (w) break;
-                c++;
-            }
-            c_new = c != c_in ? c : -1;
-            if (c < W) { node = c * 64 + ctz64(w); load_dyn(a, cx, node, du); }
-        }
-        const PodType& t = cx.types[have ? ti : 0];
-        const bool direct = node >= 0 && ((du.d.info >> 2) & 7) == 2 && du.d.hw_class != NHD_NO_CLASS && t.G <= lg_lp && !t.pci;
-        FastOut o;
-        fast_eval(a, cx, LP, direct, ti, node, du, o);
-        bool settled = false;
-        if (have && p == 0) {
-            if (c_new >= 0) cursors[ti * 3 + 0] = c_new;               /* a lower bound stays one: bits are only cleared */
-            TSlot* sl = &slots[ti];
-            if (!direct) {
-                /* GPU-less pass exhausted (the pod will spill), or a node / type the direct evaluation does not cover */
-                sl->node = node; sl->kind = NHD_SLOT_SLOW;
-                settled = true;
-            } else if (o.state == 1) {
-                bit_clear(F, node);
-            } else {
+    const int ti = cx.lane;
+    __syncwarp();
+    if ((stale >> ti) & 1) {
+        TSlot* sl = &slots[ti];
+        uint64_t* F = BM + (size_t)ti * W;
+        if ((cpu_mask >> ti) & 1) {
+            int node = node0;
+            DynU du;
+            du.q[0] = st.q[0]; du.q[1] = st.q[1];
+            for (;;) {
+                if (node < 0) {
+                    /* first candidate of the GPU-less pass (Matcher.py:412-416) */
+                    int c = cursors[ti * 3 + 0];
+                    const int c_in = c;
+                    uint64_t w = 0;
+                    while (c < W) {
+                        w = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
+                        if (w) break;
+                        c++;
+                    }
+                    if (c != c_in) cursors[ti * 3 + 0] = c;            /* a lower bound stays one: bits are only cleared */
+                    if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_SLOW; break; }      /* the pod will spill: ordinary path */
+                    node = c * 64 + ctz64(w);
+                    fast_load_dyn(a, cx, touched, node, du);
+                }
+                uint32_t dec = 0;
                 DynU da;
-                uint4 b[4];
-                fast_apply(t, node, du, o, now, da, b);
-                sl->node = node; sl->kind = NHD_SLOT_FAST;
-                sl->after[0] = da.q[0]; sl->after[1] = da.q[1];
-                sl->bind[0] = b[0]; sl->bind[1] = b[1]; sl->bind[2] = b[2]; sl->bind[3] = b[3];
-                settled = true;
+                const int state = ft.ty[ti].direct ? fast_eval(ft, ti, du, now, dec, da) : 0;
+                if (state == 2) {
+                    sl->node = node; sl->kind = NHD_SLOT_FAST; sl->dec = dec; sl->w14 = du.q[0].y;
+                    sl->after[0] = da.q[0]; sl->after[1] = da.q[1];
+                    break;
+                }
+                if (state == 0) { sl->node = node; sl->kind = NHD_SLOT_SLOW; break; }     /* a shape the tables do not cover */
+                bit_clear(F, node);
+                node = -1;
             }
-        }
-        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, settled);
-        for (int j = 0; j < NP; j++) {
-            const int tj = __shfl_sync(0xFFFFFFFFu, ti, j << lg_lp);
-            if ((dm >> (j << lg_lp)) & 1) cpu_stale &= ~(1ULL << tj);
-        }
-    }
-    while (gpu_stale) {
-        __syncwarp();
-        int ti = -1;
-        {
-            unsigned long long m = gpu_stale;
-            for (int j = 0; j < lane && m; j++) m &= m - 1;
-            if (m) ti = ctz64(m);
-        }
-        if (ti >= 0) {
+        } else {
             /* first candidate that is not busy (Matcher.py:107-111) */
-            const uint64_t* F = BM + (size_t)ti * W;
             int c = cursors[ti * 3 + 2];
             const int c_in = c;
             uint64_t w = 0;
@@ -1462,7 +1395,6 @@ __device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx
                 c++;
             }
             if (c != c_in) cursors[ti * 3 + 2] = c;
-            TSlot* sl = &slots[ti];
             if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_NONE; }        /* final: busy bits are only set on a constant clock */
             else {
                 const int node = c * 64 + ctz64(w);
@@ -1471,7 +1403,6 @@ __device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx
                 sl->kind = ((touched[c] >> (node & 63)) & 1) ? NHD_SLOT_SLOW : NHD_SLOT_DEFER;
             }
         }
-        for (int j = 0; j < 32 && gpu_stale; j++) gpu_stale &= gpu_stale - 1;
     }
     __syncwarp();
 }
@@ -1533,8 +1464,16 @@ sweep_kernel(const SweepArgs a)
     uint8_t* p2 = reinterpret_cast<uint8_t*>(s_needb) + (cx.types_in_smem ? (size_t)T * 128 : 0);
     int32_t* s_cursors = reinterpret_cast<int32_t*>(p2);                        /* [T][3] */
     uint8_t* p3 = p2 + (((size_t)T * 3 * 4 + 15) & ~(size_t)15);
-    TSlot* slots = reinterpret_cast<TSlot*>(p3);                                /* [T] standing decisions (types in shared memory only) */
-    uint64_t* s_touched = reinterpret_cast<uint64_t*>(p3 + (cx.types_in_smem ? (size_t)T * sizeof(TSlot) : 0));   /* [W] */
+    /* standing decisions and their tables (constant clock, one lane per type) */
+    const bool fast_cap = cx.types_in_smem && T <= FAST_MAX_TYPES;
+    TSlot* slots = reinterpret_cast<TSlot*>(p3);                                /* [T] */
+    uint8_t* s_tb = p3 + (fast_cap ? (size_t)T * sizeof(TSlot) : 0);            /* [T][2][2][64] */
+    uint32_t* s_sub0 = reinterpret_cast<uint32_t*>(s_tb + (fast_cap ? (size_t)T * 256 : 0));      /* [T][FAST_NSIG][16] */
+    uint32_t* s_sub1 = s_sub0 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0);
+    uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_sub1 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0));   /* [T][2][4] */
+    TyFast* s_ty = reinterpret_cast<TyFast*>(s_gd + (fast_cap ? (size_t)T * 8 : 0));                       /* [T] */
+    uint8_t* s_mapt = reinterpret_cast<uint8_t*>(s_ty + (fast_cap ? T : 0));                               /* MAPT_BYTES (+ pad) */
+    uint64_t* s_touched = reinterpret_cast<uint64_t*>(s_mapt + (fast_cap ? ((MAPT_BYTES + 15) & ~15) : 0));   /* [W] */
     uint64_t* s_bitmaps = s_touched + W;
 
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
@@ -1543,9 +1482,66 @@ sweep_kernel(const SweepArgs a)
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) misc[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
-    if (cx.types_in_smem)
+    const bool fast = fast_cap && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
+    if (fast) {
         for (int i = tid; i < T * (int)(sizeof(TSlot) / 16); i += SWEEP_THREADS)     /* node -1, NHD_SLOT_SLOW */
             reinterpret_cast<uint4*>(slots)[i] = (i % (int)(sizeof(TSlot) / 16)) == 0 ? make_uint4(0xFFFFFFFFu, NHD_SLOT_SLOW, 0, 0) : make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (MAPT_BYTES + 15) / 16; i += SWEEP_THREADS)
+            reinterpret_cast<uint4*>(s_mapt)[i] = reinterpret_cast<const uint4*>(a.mapt)[i];
+        for (int tt = tid; tt < T; tt += SWEEP_THREADS) {
+            const PodType& ty = a.types[tt];
+            TyFast f;
+            f.G = ty.G; f.n_misc = ty.pod.n_misc; f.misc_smt = (ty.pod.flags & NHD_POD_MISC_SMT) ? 1 : 0; f.nic_groups = ty.nic_groups;
+            f.direct = (ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2) ? 1 : 0;
+            f.pad_[0] = f.pad_[1] = f.pad_[2] = 0; f.hugepages_gb = ty.pod.hugepages_gb; f.pad2_ = 0;
+            s_ty[tt] = f;
+        }
+        /* CPU stage per socket (Matcher.py:203-212 with K = 2): which tuples q = 2p + m fit c free cores on NUMA k */
+        for (int i = tid; i < T * 256; i += SWEEP_THREADS) {
+            const int tt = i >> 8, f = (i >> 7) & 1, k = (i >> 6) & 1, c = i & 63;
+            const PodType& ty = a.types[tt];
+            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+            const int L = ty.G + 1;
+            uint32_t m = 0;
+            for (int q = 0; q < (1 << L) && L <= 3; q++) {
+                int n = 0;
+                for (int g = 0; g < L; g++) if (((q >> (L - 1 - g)) & 1) == k) n += cl[g];
+                if (n <= c || (c == 63 && n <= 255)) m |= 1u << q;       /* the free count saturates at 63 in the index */
+            }
+            s_tb[i] = (uint8_t)m;
+        }
+        /* cores the groups of tuple p take from each socket */
+        for (int i = tid; i < T * 8; i += SWEEP_THREADS) {
+            const int tt = i >> 3, f = (i >> 2) & 1, p = i & 3;
+            const PodType& ty = a.types[tt];
+            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+            int n0 = 0, n1 = 0;
+            for (int g = 0; g < ty.G && ty.G <= 2; g++) { if ((p >> (ty.G - 1 - g)) & 1) n1 += cl[g]; else n0 += cl[g]; }
+            s_gd[i] = (uint16_t)((n0 & 0xFF) | ((n1 & 0xFF) << 8));
+        }
+        /* NIC stage per NUMA node (Matcher.py:242-268): per (type, NIC signature, NICs in use) and tuple p, whether
+         * the groups p puts on NUMA 0 (SUB0) / NUMA 1 (SUB1) get NICs there, and which */
+        for (int i = tid; i < T * FAST_NSIG * 16; i += SWEEP_THREADS) {
+            const int tt = i / (FAST_NSIG * 16), sg = (i >> 4) % FAST_NSIG, iu = i & 15;
+            const PodType& ty = a.types[tt];
+            const uint32_t sv = a.sigs[sg];
+            uint32_t w0 = 0, w1 = 0;
+            const int n_k = (int)(sv & 15);
+            if ((sv >> 31) && ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2 && iu < (1 << n_k)) {
+                const uint32_t mk = (1u << n_k) - 1;
+                const unsigned long long sp = (sv >> 4) & 0xFFFFu;
+                const int G = ty.G, gmask = (1 << G) - 1;
+                for (int p = 0; p <= gmask; p++) {
+                    const int S1 = (int)(__brev((unsigned)p) >> (32 - G)), S0 = gmask & ~S1;
+                    const uint32_t r0 = nic_sub_solve(a.cap, ty, S0, mk, (uint32_t)iu, sp, 0ULL);
+                    const uint32_t r1 = nic_sub_solve(a.cap, ty, S1, mk, (uint32_t)iu, sp, 0ULL);
+                    w0 |= (((r0 >> 31) << 7) | (r0 & 3) | (((r0 >> 8) & 3) << 2)) << (8 * p);
+                    w1 |= (((r1 >> 31) << 7) | (r1 & 3) | (((r1 >> 8) & 3) << 2)) << (8 * p);
+                }
+            }
+            s_sub0[i] = w0; s_sub1[i] = w1;
+        }
+    }
     if (cx.types_in_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.types);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_types);
@@ -1611,20 +1607,21 @@ sweep_kernel(const SweepArgs a)
         all_gpus = ty.total_gpus > all_gpus ? ty.total_gpus : all_gpus;
     }
 
-    /* standing decisions: constant clock, the node-group gate folded into the types, types in shared memory */
+    /* standing decisions: constant clock, the node-group gate folded into the types, one lane per type */
     const bool cclock = a.dual != 0;
-    const bool fast = cclock && !multi && cx.types_in_smem && !(dbg & 1);
-    unsigned long long cpu_mask = 0, gpu_mask = 0;
-    int lg_lp = 1;
+    uint32_t cpu_mask = 0, gpu_mask = 0;
+    FastTables ft;
+    ft.tb = s_tb; ft.sub0 = s_sub0; ft.sub1 = s_sub1; ft.mapt = s_mapt; ft.gd = s_gd; ft.ty = s_ty; ft.cls = a.cls_fast;
+    DynU st_none;
+    st_none.q[0] = make_uint4(0, 0, 0, 0); st_none.q[1] = st_none.q[0];
     if (fast) {
         for (int tt = 0; tt < T; tt++) {
             const PodType& ty = types[tt];
             if (!ty.valid_map) continue;
-            if (ty.needs_gpu) gpu_mask |= 1ULL << tt;
-            else { cpu_mask |= 1ULL << tt; if (!ty.pci && ty.G > lg_lp) lg_lp = ty.G; }
+            if (ty.needs_gpu) gpu_mask |= 1u << tt; else cpu_mask |= 1u << tt;
         }
-        if (lg_lp > 4) lg_lp = 4;
-        refresh_slots<SMEM_BITMAPS>(a, cx, slots, BM, NOGPU, BUSY, s_touched, W, cursors, lg_lp, a.n_pods > 0 ? a.now[0] : 0.0, cpu_mask, gpu_mask);
+        refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, a.n_pods > 0 ? a.now[0] : 0.0,
+                                    cpu_mask | gpu_mask, cpu_mask, -1, st_none);
     }
 
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
@@ -1664,20 +1661,21 @@ sweep_kernel(const SweepArgs a)
         uint64_t* F = BM + (size_t)ti * W;
 
         /* ---- standing decision of the pod's type ---- */
-        bool handled = false;
+        bool handled = false, fast_commit = false;
         int commit_node = -1;                  /* node this pod changed (summary, BUSY / touched bits) */
+        DynU da;
+        da.q[0] = make_uint4(0, 0, 0, 0); da.q[1] = da.q[0];
         if (fast) {
             const TSlot* sl = &slots[ti];
-            const int kind = sl->kind, node = sl->node;
+            const uint4 hd = *reinterpret_cast<const uint4*>(sl);       /* node, kind, packed mapping, consumed before */
+            const int node = (int)hd.x, kind = (int)hd.y;
             if (kind == NHD_SLOT_FAST) {
-                DynU da;
                 da.q[0] = sl->after[0]; da.q[1] = sl->after[1];
-                uint4 vb = make_uint4(0, 0, 0, 0);
-                if (lane < 4) vb = sl->bind[lane];
 #ifdef NHD_CHECKS
                 {
                     DynU dx; load_dyn(a, cx, node, dx);
                     CHK_SANE(dx, node, 2);
+                    if (dx.q[0].y != hd.w) CHK_FAIL(3, node, dx.q[0].y, hd.w);
                     PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
                     const int stx = resolve_decision(a, cx, ti, t, node, dx, pmx, pkx, msx);
                     if (stx < 2) CHK_FAIL(4, node, stx, 0);
@@ -1686,8 +1684,15 @@ sweep_kernel(const SweepArgs a)
                         apply_decision(cx, t, node, dx.d, pmx, pkx, now, scratch);
                         __syncwarp();
                         if (!same_dyn(dx, da)) CHK_FAIL(5, node, dx.q[0].x, da.q[0].x);
-                        const uint4 sb = lane < 4 ? reinterpret_cast<const uint4*>(scratch)[lane] : make_uint4(0, 0, 0, 0);
-                        if (lane < 4 && (sb.x != vb.x || sb.y != vb.y || sb.z != vb.z || sb.w != vb.w)) CHK_FAIL(8, node, lane, sb.x);
+                        /* the packed mapping: tuple, misc NUMA, NodeNic.idx per group */
+                        const int ps = hd.z & 3, G = t.G;
+                        uint32_t pn = 0, ix = 0; int k0 = 0, k1 = 0;
+                        for (int g = 0; g < G; g++) {
+                            const int numa = (ps >> (G - 1 - g)) & 1;
+                            const uint32_t x = numa ? (((hd.z >> 16) & 0xFF) >> (2 * k1++)) & 3 : (((hd.z >> 8) & 0xFF) >> (2 * k0++)) & 3;
+                            pn |= (uint32_t)numa << (8 * g); ix |= x << (8 * g);
+                        }
+                        if (pn != pmx.pn || ix != pmx.idx || ((hd.z >> 2) & 1) != pmx.ms) CHK_FAIL(8, node, hd.z, pmx.pn);
                     }
                     /* and it is the first fit of the GPU-less pass */
                     for (int w = lane; w < (node >> 6); w += 32)
@@ -1696,10 +1701,18 @@ sweep_kernel(const SweepArgs a)
                     if (!((ldw<SMEM_BITMAPS>(&F[node >> 6]) >> (node & 63)) & 1)) CHK_FAIL(9, node, 0, 0);
                 }
 #endif
-                store_dyn(a, cx, node, da);
-                if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = vb;
+                /* commit: summary (cache + HBM, written through), touched bit, packed binding */
+                const int cs = node & cx.dcache_mask;
+                __syncwarp();
+                if (lane < 2) {
+                    const uint4 half = lane == 0 ? da.q[0] : da.q[1];
+                    cx.dcache[2 * cs + lane] = half;
+                    a.dyn[(size_t)node * 2 + lane] = half;
+                } else if (lane == 2) cx.dtag[cs] = node;
+                else if (lane == 3) bit_set(s_touched, node);
+                else if (lane == 4) *reinterpret_cast<uint4*>(bout) = make_uint4(NHD_PENDING_FAST, (uint32_t)node, hd.z, hd.w);
                 commit_node = node;
-                handled = true;
+                handled = true; fast_commit = true;
                 PROF_COUNT(13);
             } else if (kind == NHD_SLOT_DEFER) {
                 /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
@@ -1711,9 +1724,8 @@ sweep_kernel(const SweepArgs a)
                     atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
                     a.pend_pod[node] = i;
                     reinterpret_cast<uint2*>(bout)[0] = make_uint2(NHD_PENDING, (uint32_t)node);
-                    bit_set(s_touched, node);
-                    if (a.min_busy > 0.0 && !was_busy) bit_set(BUSY, node);      /* now - busy_time == 0 < MIN_BUSY_SECS */
-                }
+                } else if (lane == 1) bit_set(s_touched, node);
+                else if (lane == 2 && a.min_busy > 0.0 && !was_busy) bit_set(BUSY, node);      /* now - busy_time == 0 < MIN_BUSY_SECS */
                 commit_node = node;
                 handled = true;
                 PROF_COUNT(12);
@@ -1888,7 +1900,7 @@ sweep_kernel(const SweepArgs a)
             placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
             store_dyn(a, cx, chosen, du);
             /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
-            if (lane == 0 && du.d.n_gpus) bit_set(s_touched, chosen);
+            if (lane == 0 && (du.d.n_gpus || fast)) bit_set(s_touched, chosen);
         }
         PROF_MARK(5);      /* assignment */
         if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
@@ -1927,14 +1939,13 @@ sweep_kernel(const SweepArgs a)
         if (fast) {
             /* every standing decision made for the node this pod changed is out of date; after the ordinary path
              * the pod's own type as well (it may have given up the node its slot names) */
-            unsigned long long st = handled ? 0ULL : (1ULL << ti);
-            if (commit_node >= 0) {
-                const uint32_t lo = __ballot_sync(0xFFFFFFFFu, lane < T && slots[lane].node == commit_node);
-                const uint32_t hi = T > 32 ? __ballot_sync(0xFFFFFFFFu, lane + 32 < T && slots[lane + 32].node == commit_node) : 0u;
-                st |= (unsigned long long)lo | ((unsigned long long)hi << 32);
+            uint32_t st = handled ? 0u : (1u << ti);
+            if (commit_node >= 0) st |= __ballot_sync(0xFFFFFFFFu, lane < T && slots[lane].node == commit_node);
+            st &= cpu_mask | gpu_mask;
+            if (st) {
+                if (fast_commit) refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, commit_node, da);
+                else refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, -1, st_none);
             }
-            if (st & (cpu_mask | gpu_mask))
-                refresh_slots<SMEM_BITMAPS>(a, cx, slots, BM, NOGPU, BUSY, s_touched, W, cursors, lg_lp, now, st & cpu_mask, st & gpu_mask);
         }
         PROF_MARK(6);      /* write-back + refresh */
       }
@@ -1951,7 +1962,43 @@ __global__ void resolve_kernel(const SweepArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_pods) return;
-    if (a.out[i].status != NHD_PENDING) return;
+    const int status = a.out[i].status;
+    if (status == NHD_PENDING_FAST) {
+        /* decided directly by the sweep: format the binding header from the packed mapping (the node's summary is
+         * final already); same words as apply_decision writes */
+        const uint4 hd = *reinterpret_cast<const uint4*>(&a.out[i]);
+        const int node = (int)hd.y;
+        const PodType& t = a.types[a.pod_type[i]];
+        const int G = t.G, ps = hd.z & 3;
+        const uint32_t ms = (hd.z >> 2) & 1, e0 = (hd.z >> 8) & 0xFF, e1 = (hd.z >> 16) & 0xFF;
+        const uint4 c5 = *reinterpret_cast<const uint4*>(a.nodes + chunk_off(node, 5));
+        uint32_t pn = 0, idx = 0, li = 0, rec = 0;
+        int n_rec = 0, k0 = 0, k1 = 0;
+        for (int g = 0; g < G; g++) {
+            const int numa = (ps >> (G - 1 - g)) & 1;
+            const uint32_t x = numa ? (e1 >> (2 * k1++)) & 3 : (e0 >> (2 * k0++)) & 3;
+            const uint32_t l = (uint32_t)nth_bit32(numa ? c5.y : c5.x, (int)x);        /* NodeNic.idx -> index in Node.nics */
+            pn |= (uint32_t)numa << (8 * g); idx |= x << (8 * g); li |= l << (8 * g);
+            if ((t.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
+        }
+        int ncl = 0;
+        const uint32_t claimed = claimed_order_packed(rec, n_rec, ncl);                 /* NHDScheduler.py:302 */
+        const uint32_t w2 = (uint32_t)G | ((uint32_t)ncl << 24);
+        const uint32_t w4 = G < 4 ? (pn | (ms << (8 * G))) : pn;
+        const uint32_t w5 = (G == 4 ? ms : 0u) | (pn << 8);
+        const uint32_t w6 = (pn >> 24) | (idx << 8);
+        const uint32_t w7 = (idx >> 24) | (li << 8);
+        const uint32_t w8 = (li >> 24) | (claimed << 8);
+        const uint32_t w9 = claimed >> 24;
+        uint4* o = reinterpret_cast<uint4*>(&a.out[i]);
+        o[0] = make_uint4(NHD_PLACED, (uint32_t)node, w2, pn);
+        o[1] = make_uint4(w4, w5, w6, w7);
+        o[2] = make_uint4(w8, w9, 0, 0);
+        o[3] = make_uint4(0, 0, hd.w, 0);
+        for (int c = 4; c < 8; c++) o[c] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    if (status != NHD_PENDING) return;
     const int node = a.out[i].node;
     const PodType& t = a.types[a.pod_type[i]];
     RecU u;

@@ -96,7 +96,7 @@ def build(force=False, verbose=False, asan=False, ubsan=False):
                 .replace('__noinline__', 'EMU_NOINLINE'))
     with open(os.path.join(GEN, 'nhd_ingest.cpp'), 'w') as f:
         f.write(open(os.path.join(CSRC, 'nhd_ingest.cpp')).read().replace('"../../include/nhd_b200.h"', '"%s"' % inc))
-    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-w'] + \
+    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-w'] + (['-DNHD_DEBUG_PRINT'] if os.environ.get('EMU_DEBUG_PRINT') else []) + \
           (['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + \
           (['-fsanitize=alignment,bounds', '-fno-sanitize-recover=all'] if ubsan else []) + [
            '-I', os.path.join(HERE, 'fake_cuda'), '-I', GEN, '-o', OUT,

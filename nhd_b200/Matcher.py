@@ -28,6 +28,7 @@ class Matcher:
         self._layout = packing.ClusterLayout()
         self._speeds: List[float] = []
         self._min_busy = None
+        self.unsupported_nodes: Dict[str, str] = {}      # active nodes kept out of placement: name -> reason
 
     # ------------------------------------------------------------------ internals
     def _ensure_solver(self, nodes: Sequence):
@@ -45,7 +46,9 @@ class Matcher:
     def _load(self, nl: Dict[str, object]):
         names = list(nl.keys())
         nodes = [nl[n] for n in names]
-        recs = packing.pack_nodes(nodes, self._layout)      # may add speed classes / group names
+        # may add speed classes / group names; a node outside the packed limits becomes an inactive stub (logged,
+        # listed in unsupported_nodes) and the others stay schedulable, as with the reference
+        recs = packing.pack_nodes(nodes, self._layout, unsupported=self.unsupported_nodes)
         solver = self._ensure_solver(nodes)
         solver.load_nodes(recs)
         return names, nodes, solver

@@ -143,10 +143,10 @@ class DeviceCluster:
                 # described to the solver either: it is kept out of placement (never approximated) and named in
                 # unsupported_nodes for the operator.
                 if node.active:
+                    if node.name not in self.unsupported_nodes:
+                        packing._log.warning('node %s is outside the packed limits and is kept out of placement: %s', node.name, err)
                     self.unsupported_nodes[node.name] = str(err)
-                recs[i] = np.zeros((), dtype=wire.NODE_DTYPE)
-                recs[i]['n_numa'] = 1
-                recs[i]['phys_cores'] = 1
+                packing.stub_record(recs[i])
                 self.stubs.add(node.name)
         return recs
 

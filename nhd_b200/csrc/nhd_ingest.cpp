@@ -281,6 +281,9 @@ int32_t nhd_ingest_node(nhd_ingest* g, int32_t n_labels, const char* const* keys
         if (gpus.size() > NHD_MAX_GPUS) return NHD_ERR_UNSUPPORTED;
         for (size_t i = 0; i < gpus.size(); i++) {
             if (gpus[i].numa < 0 || gpus[i].numa >= sockets) return NHD_ERR_UNSUPPORTED;
+            /* the reference's failure unwind frees self.gpus[device_id] (Node.py:828): exact only while the device
+             * ids are the list positions (same rule as packing.pack_node) */
+            if (gpus[i].device_id != (long)i) return NHD_ERR_UNSUPPORTED;
             r.gpu_numa_mask[gpus[i].numa] |= (uint16_t)(1u << i);
             r.gpu_sw |= local_switch(gpus[i].sw) << (4 * i);
             ax.gpu_device_id[i] = (int32_t)gpus[i].device_id;

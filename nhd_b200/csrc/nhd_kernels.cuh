@@ -363,7 +363,7 @@ struct SweepArgs {
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
     int dual;                    /* 1: constant clock -> standing decisions per pod type (see sweep_kernel) */
-    int n_cpu_warps;             /* bits 8..: debug switches */
+    int n_cpu_warps;             /* low byte 1: never sweep the two pod classes side by side; bits 8..: debug switches */
     int n_names;                 /* > 0: per-pod node-group masks, one bitmap per name after BUSY */
     uint64_t names_used;
     const uint64_t* pod_groups;  /* [n_pods] when n_names > 0 */
@@ -1473,9 +1473,12 @@ sweep_kernel(const SweepArgs a)
     uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_sub1 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0));   /* [T][2][4] */
     TyFast* s_ty = reinterpret_cast<TyFast*>(s_gd + (fast_cap ? (size_t)T * 8 : 0));                       /* [T] */
     uint8_t* s_mapt = reinterpret_cast<uint8_t*>(s_ty + (fast_cap ? T : 0));                               /* MAPT_BYTES (+ pad) */
-    uint64_t* s_touched = reinterpret_cast<uint64_t*>(s_mapt + (fast_cap ? ((MAPT_BYTES + 15) & ~15) : 0));   /* [W] */
+    int* s_cnt = reinterpret_cast<int*>(s_mapt + (fast_cap ? ((MAPT_BYTES + 15) & ~15) : 0));              /* [T + 2] candidate counts, CPU-only pods, flag */
+    uint64_t* s_touched = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_cnt) + (fast_cap ? (((size_t)(T + 2) * 4 + 15) & ~(size_t)15) : 0));   /* [W] */
     uint64_t* s_bitmaps = s_touched + W;
 
+    if (fast_cap && tid < T + 2) s_cnt[tid] = 0;
+    __syncthreads();
     for (int i = tid; i < SMEMO_SLOTS + DMEMO_SLOTS * 3; i += SWEEP_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(clsnic_all)[i] = make_uint4(0, 0, 0, 0);
@@ -1541,6 +1544,28 @@ sweep_kernel(const SweepArgs a)
             }
             s_sub0[i] = w0; s_sub1[i] = w1;
         }
+        /* "no CPU-only pod can spill" certificate: a CPU-only pod touches one node, and a node no pod of the batch
+         * was bound to keeps its exact snapshot bit; a type with more GPU-less candidates than there are CPU-only
+         * pods therefore never runs out of them (or it has no candidate anywhere).  Then CPU-only pods only ever
+         * touch GPU-less nodes, GPU pods only GPU nodes, and the two classes can be swept side by side. */
+        {
+            const uint64_t* gb = a.bitmaps;                                  /* HBM copy: the shared-memory one is still being staged */
+            for (int tt = 0; tt < T; tt++) {
+                const PodType& ty = a.types[tt];
+                if (ty.needs_gpu || !ty.valid_map) continue;
+                int c0 = 0, c1 = 0;
+                for (int w = tid; w < W; w += SWEEP_THREADS) {
+                    const uint64_t f = gb[(size_t)tt * W + w];
+                    c0 += popc64(f & gb[(size_t)T * W + w]);
+                    c1 += f != 0;
+                }
+                if (c0) atomicAdd(&s_cnt[tt], c0);
+                if (c1) atomicOr(&s_cnt[T + 1], 1 << (tt & 31));              /* the type has candidates at all */
+            }
+            int nc = 0;
+            for (int i = tid; i < a.n_pods; i += SWEEP_THREADS) nc += a.types[a.pod_type[i]].needs_gpu ? 0 : 1;
+            if (nc) atomicAdd(&s_cnt[T], nc);
+        }
     }
     if (cx.types_in_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.types);
@@ -1585,7 +1610,63 @@ sweep_kernel(const SweepArgs a)
     int32_t* cursors = SMEM_BITMAPS ? s_cursors : a.cursors;
     for (int i = tid; i < T * 3; i += SWEEP_THREADS) cursors[i] = 0;
     __syncthreads();
-    if (wid >= 1) return;                                  /* the sweep proper is one warp */
+    /* side-by-side mode: warp 0 sweeps the CPU-only pods, warp 1 the GPU pods (see the certificate above); with a
+     * busy window every GPU pod of the batch lands on a node no pod was bound to, so warp 1 only scans and stamps */
+    bool split = false;
+    if (fast && a.min_busy > 0.0 && !(dbg & 2) && (a.n_cpu_warps & 0xFF) != 1) {
+        split = true;
+        for (int tt = 0; tt < T; tt++) {
+            const PodType& ty = a.types[tt];
+            if (ty.needs_gpu || !ty.valid_map) continue;
+            if (!(s_cnt[tt] > s_cnt[T] || !((s_cnt[T + 1] >> (tt & 31)) & 1))) split = false;
+        }
+    }
+    if (wid >= (split ? 2 : 1)) return;                    /* the sweep proper is one warp, or one per pod class */
+    if (wid == 1) {
+        uint64_t* const BMg = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
+        uint64_t* const BUSYg = BMg + (size_t)(T + 1) * W;
+        int32_t* const curs = SMEM_BITMAPS ? s_cursors : a.cursors;
+        const PodType* tys = cx.types_in_smem ? s_types : a.types;
+        for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
+            const int my_ti = (i0 + lane < a.n_pods) ? a.pod_type[i0 + lane] : 0;
+            const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, i0 + lane < a.n_pods && tys[my_ti].needs_gpu && tys[my_ti].valid_map);
+            for (; todo; todo &= todo - 1) {
+                const int j = ctz32(todo), i = i0 + j;
+                const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
+                const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
+                const uint64_t* F = BMg + (size_t)ti * W;
+                /* first candidate that is not busy (Matcher.py:107-111); every lane walks the same words */
+                int c = curs[ti * 3 + 2];
+                uint64_t w = 0;
+                while (c < W) {
+                    w = ldw<SMEM_BITMAPS>(&F[c]) & ~ldw<SMEM_BITMAPS>(&BUSYg[c]);
+                    if (w) break;
+                    c++;
+                }
+                __syncwarp();
+                if (c >= W) {
+                    if (lane < 8) reinterpret_cast<uint4*>(&a.out[i])[lane] = make_uint4(lane == 0 ? NHD_NO_CANDIDATE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? tys[ti].G : 0, 0);
+                    if (lane == 8) curs[ti * 3 + 2] = c;
+                    __syncwarp();
+                    continue;
+                }
+                const int node = c * 64 + ctz64(w);
+                /* stamp the node (NHDScheduler.py:289), note the pod for resolve_kernel, take the node out of this
+                 * window's candidates (now - busy_time == 0 < MIN_BUSY_SECS): one store per lane */
+                NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + node;
+                if (lane == 0) gd->busy_time = now;
+                else if (lane == 1) atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
+                else if (lane == 2) a.pend_pod[node] = i;
+                else if (lane == 3) reinterpret_cast<uint2*>(&a.out[i])[0] = make_uint2(NHD_PENDING, (uint32_t)node);
+                else if (lane == 4) bit_set(BUSYg, node);
+                else if (lane == 5) bit_set(s_touched, node);
+                else if (lane == 6) curs[ti * 3 + 2] = c;
+                __syncwarp();
+            }
+        }
+        return;
+    }
 
     uint64_t* const BM = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
     uint64_t* const NOGPU = BM + (size_t)T * W;
@@ -1620,6 +1701,7 @@ sweep_kernel(const SweepArgs a)
             if (!ty.valid_map) continue;
             if (ty.needs_gpu) gpu_mask |= 1u << tt; else cpu_mask |= 1u << tt;
         }
+        if (split) gpu_mask = 0;                            /* warp 1 sweeps the GPU pods */
         refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, a.n_pods > 0 ? a.now[0] : 0.0,
                                     cpu_mask | gpu_mask, cpu_mask, -1, st_none);
     }
@@ -1657,6 +1739,7 @@ sweep_kernel(const SweepArgs a)
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
+        if (split && t.needs_gpu && t.valid_map) continue;          /* warp 1's pod */
         nhd_binding* bout = &a.out[i];
         uint64_t* F = BM + (size_t)ti * W;
 

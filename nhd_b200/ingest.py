@@ -61,21 +61,37 @@ class LabelIngest:
             raise LabelError(rc, name)
         return rec, aux
 
-    def nodes(self, items: Sequence[Tuple[Mapping[str, str], bool, int, int]], skip_rejected: bool = False):
-        """Many nodes: ``items`` = ``(labels, active, hugepages_alloc_gb, hugepages_free_gb)``.  Returns the
-        records (and the positions kept when ``skip_rejected`` drops the nodes ``ParseLabels`` would refuse,
-        as ``NHDScheduler.BuildInitialNodeList`` does)."""
+    def nodes(self, items: Sequence[Tuple[Mapping[str, str], bool, int, int]], skip_rejected: bool = False,
+              strict: bool = False):
+        """Many nodes, as ``NHDScheduler.BuildInitialNodeList`` brings a cluster up (``NHDScheduler.py:83-100``):
+        ``items`` = ``(labels, active, hugepages_alloc_gb, hugepages_free_gb)``.  Every node keeps its position in
+        the order (the node index is the scheduler's preference order); a node is left in place as an INACTIVE
+        record when ``ParseLabels`` would return False (``:87-90``), when it would raise (``except Exception``,
+        ``:96-98``), when its allocatable hugepages are 0 (``:92-94``), or when it is beyond the packed limits.
+        Returns ``(records, kept)`` with ``kept`` the positions that came up active-capable.
+
+        ``skip_rejected=True`` instead DROPS the nodes ``ParseLabels`` refuses (positions shift; for callers that
+        build their own node list); ``strict=True`` re-raises instead of deactivating."""
         recs = np.zeros(len(items), dtype=wire.NODE_DTYPE)
         kept = []
+        n_out = 0
         for i, (labels, active, alloc, free) in enumerate(items):
             try:
-                self.node(labels, active, alloc, free, name=str(i), out=recs[len(kept):len(kept) + 1])
+                self.node(labels, active, alloc, free, name=str(i), out=recs[n_out:n_out + 1])
+                if int(alloc) == 0:                                   # NHDScheduler.py:92-94
+                    recs[n_out]['flags'] &= ~np.uint8(wire.NODE_ACTIVE)
+                else:
+                    kept.append(i)
             except LabelError as e:
                 if skip_rejected and e.code == wire.ERR_LABELS:
                     continue
-                raise
-            kept.append(i)
-        return recs[:len(kept)], kept
+                if strict or (skip_rejected and e.code != wire.ERR_LABELS):
+                    raise
+                recs[n_out] = np.zeros((), dtype=wire.NODE_DTYPE)      # inactive stub, holds the position
+                recs[n_out]['n_numa'] = 1
+                recs[n_out]['phys_cores'] = 1
+            n_out += 1
+        return recs[:n_out], kept
 
     def group_mask(self, names: Iterable[str], create: bool = False) -> int:
         m = ctypes.c_uint64(0)

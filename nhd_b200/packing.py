@@ -9,11 +9,15 @@ writes a solver binding back where ``Node.SetPhysicalIdsFromMapping``
 
 No placement decisions are taken here — only format conversion.
 """
+import logging
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
 from nhd_b200 import wire
+
+
+_log = logging.getLogger('nhd_b200')
 
 
 class UnsupportedError(ValueError):
@@ -115,6 +119,9 @@ def pack_node(node, layout: ClusterLayout, out=None):
     for i, g in enumerate(node.gpus):
         if not 0 <= g.numa_node < K:
             raise UnsupportedError(f'node {node.name}: GPU {i} on NUMA node {g.numa_node} of {K}')
+        # the reference's failure unwind frees self.gpus[device_id] (Node.py:828): only exact while ids are positions
+        if int(getattr(g, 'device_id', i)) != i:
+            raise UnsupportedError(f'node {node.name}: GPU {i} carries device id {g.device_id} (ids must equal list positions)')
         gpu_numa[g.numa_node] |= 1 << i
         gpu_sw |= local_switch(g.pciesw) << (4 * i)
         if g.used:
@@ -150,10 +157,30 @@ def pack_node(node, layout: ClusterLayout, out=None):
     return rec
 
 
-def pack_nodes(nodes: Sequence, layout: ClusterLayout) -> np.ndarray:
+def stub_record(out):
+    """Inactive place-holder record: keeps a node's position in the order, is never a candidate."""
+    out[()] = np.zeros((), dtype=wire.NODE_DTYPE)
+    out['n_numa'] = 1
+    out['phys_cores'] = 1
+    return out
+
+
+def pack_nodes(nodes: Sequence, layout: ClusterLayout, unsupported: dict = None) -> np.ndarray:
+    """Records of ``nodes`` in order.  A node the packed layout cannot describe (beyond ``NHD_MAX_*``, irregular
+    core / NIC / GPU numbering) becomes an inactive stub at its position: the remaining nodes stay schedulable, as
+    they would with the reference, instead of the whole call failing.  Such nodes are logged, and reported through
+    ``unsupported`` (name -> reason) when given."""
     recs = np.zeros(len(nodes), dtype=wire.NODE_DTYPE)
     for i, n in enumerate(nodes):
-        pack_node(n, layout, out=recs[i])
+        try:
+            pack_node(n, layout, out=recs[i])
+        except UnsupportedError as err:
+            stub_record(recs[i])
+            if getattr(n, 'active', True):
+                _log.warning('node %s is outside the packed limits and is kept out of placement: %s',
+                             getattr(n, 'name', i), err)
+                if unsupported is not None:
+                    unsupported[getattr(n, 'name', str(i))] = str(err)
     return recs
 
 

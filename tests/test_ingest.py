@@ -117,7 +117,36 @@ def test_batch_ingest_feeds_the_record_validator():
     for i in range(len(recs)):
         assert L.nhd_validate_node(recs[i:i + 1].ctypes.data) == 0
     with pytest.raises(LabelError):
-        ing.nodes(items, skip_rejected=False)
+        ing.nodes(items, strict=True)
+
+
+def test_batch_ingest_brings_a_cluster_up_like_build_initial_node_list():
+    """nodes(): the flow of NHDScheduler.BuildInitialNodeList (NHDScheduler.py:83-100) — a node whose labels are
+    refused, whose parsing raises, or whose allocatable hugepages are 0 stays in the list, deactivated, and every
+    node keeps its index (= the scheduler's preference order)."""
+    scn = scenarios.random_scenario(4243, n_nodes=12, n_pods=1, flavor='mixed')
+    items = [(nd['labels'], True, max(1, nd['hp_alloc']), nd['hp_free']) for nd in scn['nodes']]
+    refused = dict(items[2][0]); del refused['DATA_PLANE_VLAN']                    # ParseLabels returns False
+    items[2] = (refused,) + items[2][1:]
+    raising = dict(items[5][0]); raising['DATA_PLANE_VLAN'] = 'not-a-number'        # int() raises inside ParseLabels
+    items[5] = (raising,) + items[5][1:]
+    items[7] = (items[7][0], True, 0, items[7][3])                                   # alloc == 0
+    ing = LabelIngest()
+    recs, kept = ing.nodes(items)
+    assert len(recs) == 12 and kept == [i for i in range(12) if i not in (2, 5, 7)]
+    active = (recs['flags'] & wire.NODE_ACTIVE) != 0
+    assert active.tolist() == [i not in (2, 5, 7) for i in range(12)]
+    # the untouched nodes are byte-identical to one-by-one ingest in the same order of dictionary growth
+    ing2 = LabelIngest()
+    for i, it in enumerate(items):
+        if i in (2, 5):
+            with pytest.raises(LabelError):
+                ing2.node(*it)
+            continue
+        r, _ = ing2.node(*it)
+        if i == 7:
+            r = r.copy(); r['flags'] &= ~np.uint8(wire.NODE_ACTIVE)
+        assert recs[i].tobytes() == r.tobytes(), i
 
 
 @pytest.mark.reference

@@ -646,9 +646,12 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
                     (((size_t)(T + 2) * 4 + 15) & ~(size_t)15);
         const size_t with_bitmaps = smem + bm_bytes;
         if (with_bitmaps <= (size_t)h->smem_optin) {
-            sweep_kernel<true><<<1, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);
+        /* a second CTA takes the GPU pods when the two pod classes cannot meet (decided on the device, see sweep_kernel) */
+        const int sweep_ctas = sa.dual ? 2 : 1;
+        if (with_bitmaps <= (size_t)h->smem_optin) {
+            sweep_kernel<true><<<sweep_ctas, SWEEP_THREADS, with_bitmaps, h->stream>>>(sa);
         } else {
-            sweep_kernel<false><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
+            sweep_kernel<false><<<sweep_ctas, SWEEP_THREADS, smem, h->stream>>>(sa);
         }
         CK(cudaGetLastError());
         FinishArgs fin;

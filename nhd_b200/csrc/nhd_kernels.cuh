@@ -324,7 +324,11 @@ filter_kernel(const FilterArgs a)
 #define PROF2_DECL long long p2_t0 = clock64();
 #define PROF2(i) do { long long t_ = clock64(); if (cx.lane == 0) atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - p2_t0)); p2_t0 = t_; } while (0)
 #define PROF_FLUSH(buf) do { if (lane == 0) for (int i_ = 0; i_ < 16; i_++) { (buf)[i_] = (unsigned long long)prof_acc[i_]; (buf)[32 + i_] = (unsigned long long)prof_cnt[i_]; } } while (0)
+#define PROFL_DECL long long pl_t0 = clock64();
+#define PROFL(i) do { long long t_ = clock64(); atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - pl_t0)); atomicAdd(&a.prof[48 + (i)], 1ULL); pl_t0 = clock64(); } while (0)
 #else
+#define PROFL_DECL
+#define PROFL(i)
 #define PROF2_DECL
 #define PROF2(i)
 #define PROF_DECL
@@ -1356,6 +1360,7 @@ __device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx
             int node = node0;
             DynU du;
             du.q[0] = st.q[0]; du.q[1] = st.q[1];
+            PROFL_DECL
             for (;;) {
                 if (node < 0) {
                     /* first candidate of the GPU-less pass (Matcher.py:412-416) */
@@ -1370,14 +1375,18 @@ __device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx
                     if (c != c_in) cursors[ti * 3 + 0] = c;            /* a lower bound stays one: bits are only cleared */
                     if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_SLOW; break; }      /* the pod will spill: ordinary path */
                     node = c * 64 + ctz64(w);
+                    PROFL(0);      /* scan */
                     fast_load_dyn(a, cx, touched, node, du);
+                    PROFL(1);      /* summary load (value used: the clock read waits for it) */
                 }
                 uint32_t dec = 0;
                 DynU da;
                 const int state = ft.ty[ti].direct ? fast_eval(ft, ti, du, now, dec, da) : 0;
+                PROFL(2);          /* evaluation */
                 if (state == 2) {
                     sl->node = node; sl->kind = NHD_SLOT_FAST; sl->dec = dec; sl->w14 = du.q[0].y;
                     sl->after[0] = da.q[0]; sl->after[1] = da.q[1];
+                    PROFL(3);      /* slot store */
                     break;
                 }
                 if (state == 0) { sl->node = node; sl->kind = NHD_SLOT_SLOW; break; }     /* a shape the tables do not cover */
@@ -1607,11 +1616,12 @@ sweep_kernel(const SweepArgs a)
     }
     /* cursors[t*3 + 0/1]: first word that may hold a candidate (pass 0 / 1); [t*3 + 2]: first
      * word that may hold a NON-BUSY candidate (valid while the clock stands still) */
-    int32_t* cursors = SMEM_BITMAPS ? s_cursors : a.cursors;
+    int32_t* cursors = s_cursors;
     for (int i = tid; i < T * 3; i += SWEEP_THREADS) cursors[i] = 0;
     __syncthreads();
-    /* side-by-side mode: warp 0 sweeps the CPU-only pods, warp 1 the GPU pods (see the certificate above); with a
-     * busy window every GPU pod of the batch lands on a node no pod was bound to, so warp 1 only scans and stamps */
+    /* side-by-side mode: CTA 0 sweeps the CPU-only pods, CTA 1 the GPU pods (see the certificate above; both CTAs
+     * compute it from the same inputs); with a busy window every GPU pod of the batch lands on a node no pod was
+     * bound to, so CTA 1 only scans and stamps */
     bool split = false;
     if (fast && a.min_busy > 0.0 && !(dbg & 2) && (a.n_cpu_warps & 0xFF) != 1) {
         split = true;
@@ -1621,11 +1631,13 @@ sweep_kernel(const SweepArgs a)
             if (!(s_cnt[tt] > s_cnt[T] || !((s_cnt[T + 1] >> (tt & 31)) & 1))) split = false;
         }
     }
-    if (wid >= (split ? 2 : 1)) return;                    /* the sweep proper is one warp, or one per pod class */
-    if (wid == 1) {
+    /* the sweep proper is one warp; side by side: warp 0 of CTA 0 takes the CPU-only pods, warp 0 of CTA 1 (its own
+     * SM, its own copy of the bitmaps) the GPU pods — the two classes share nothing they both write */
+    if (wid >= 1 || (blockIdx.x == 1 && !split)) return;
+    if (blockIdx.x == 1) {
         uint64_t* const BMg = SMEM_BITMAPS ? s_bitmaps : a.bitmaps;
         uint64_t* const BUSYg = BMg + (size_t)(T + 1) * W;
-        int32_t* const curs = SMEM_BITMAPS ? s_cursors : a.cursors;
+        int32_t* const curs = s_cursors;
         const PodType* tys = cx.types_in_smem ? s_types : a.types;
         for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
             const int my_ti = (i0 + lane < a.n_pods) ? a.pod_type[i0 + lane] : 0;
@@ -1701,7 +1713,7 @@ sweep_kernel(const SweepArgs a)
             if (!ty.valid_map) continue;
             if (ty.needs_gpu) gpu_mask |= 1u << tt; else cpu_mask |= 1u << tt;
         }
-        if (split) gpu_mask = 0;                            /* warp 1 sweeps the GPU pods */
+        if (split) gpu_mask = 0;                            /* CTA 1 sweeps the GPU pods */
         refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, a.n_pods > 0 ? a.now[0] : 0.0,
                                     cpu_mask | gpu_mask, cpu_mask, -1, st_none);
     }
@@ -1739,7 +1751,7 @@ sweep_kernel(const SweepArgs a)
         const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
-        if (split && t.needs_gpu && t.valid_map) continue;          /* warp 1's pod */
+        if (split && t.needs_gpu && t.valid_map) continue;          /* CTA 1's pod */
         nhd_binding* bout = &a.out[i];
         uint64_t* F = BM + (size_t)ti * W;
 
@@ -2025,6 +2037,7 @@ sweep_kernel(const SweepArgs a)
             uint32_t st = handled ? 0u : (1u << ti);
             if (commit_node >= 0) st |= __ballot_sync(0xFFFFFFFFu, lane < T && slots[lane].node == commit_node);
             st &= cpu_mask | gpu_mask;
+            PROF_MARK(5);      /* (fast path) stale mask */
             if (st) {
                 if (fast_commit) refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, commit_node, da);
                 else refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, -1, st_none);

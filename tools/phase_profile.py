@@ -12,14 +12,14 @@ for _ in range(3):
     s.restore(); s.solve_staged(); s.sync()
     c = s.debug_counters()
 t = s.timing()
-names = ['pod header', 'bitmap scan', 'summary+memo lookup', 'full eval (miss)', 'decode/exit', 'assign_resources', 'write-back']
+names = ['pod header + slot commit', 'bitmap scan (ordinary)', 'summary+memo (ordinary)', 'full eval (ordinary)', 'decode/exit (ordinary)',
+         'assign / stale mask', 'refresh of standing decisions']
 tot = sum(int(x) for x in c[:16])
-print(f'cfg{cfg}: sweep {t["sweep_ms"]:.3f} ms, {len(pods)} pods, total cycles {tot} ({tot/len(pods):.0f}/pod)')
+print(f'cfg{cfg}: sweep {t["sweep_ms"]:.3f} ms, {len(pods)} pods, warp-0 cycles {tot}')
 for i, n in enumerate(names):
-    print(f'  {n:24s} cycles {int(c[i]):10d} ({100*int(c[i])/max(tot,1):5.1f}%)  count {int(c[32+i]):7d}  avg {int(c[i])/max(int(c[32+i]),1):8.1f}')
-print('  stale candidates', int(c[32 + 8]))
-# CPU-class warp 0 only: pods it worked out ahead / results that went stale while waiting / results adopted
-print('  warp 0: speculations', int(c[32 + 15]), 'invalidated', int(c[32 + 14]), 'adopted', int(c[32 + 13]))
-for i, n in enumerate(['cpu2: B mask + layout', 'cpu2: sub-problems', 'cpu2: combine', 'cpu2: mapping memo', 'cpu2: expand', 'cpu2: claim order']):
-    print(f'  {n:24s} cycles {int(c[16+i]):10d}  per CPU pod {int(c[16+i])/2048:8.1f}')
+    print(f'  {n:34s} cycles {int(c[i]):10d} ({100*int(c[i])/max(tot,1):5.1f}%)  count {int(c[32+i]):7d}  avg {int(c[i])/max(int(c[32+i]),1):8.1f}')
+print('  stale candidates (ordinary path)', int(c[32 + 8]), ' direct commits', int(c[32 + 13]), ' deferred GPU commits', int(c[32 + 12]))
+# lane-level, inside the refresh (summed over lanes = pod types)
+for i, n in enumerate(['refresh: candidate scan', 'refresh: summary load', 'refresh: evaluation', 'refresh: slot store']):
+    print(f'  {n:34s} lane-cycles {int(c[16+i]):10d}  count {int(c[48+i]):7d}  avg {int(c[16+i])/max(int(c[48+i]),1):8.1f}')
 s.close()

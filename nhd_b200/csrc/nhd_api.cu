@@ -645,7 +645,6 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
             smem += (size_t)T * (sizeof(TSlot) + 256 + 2 * FAST_NSIG * 64 + 16 + sizeof(TyFast)) + ((MAPT_BYTES + 15) & ~15) +
                     (((size_t)(T + 2) * 4 + 15) & ~(size_t)15);
         const size_t with_bitmaps = smem + bm_bytes;
-        if (with_bitmaps <= (size_t)h->smem_optin) {
         /* a second CTA takes the GPU pods when the two pod classes cannot meet (decided on the device, see sweep_kernel) */
         const int sweep_ctas = sa.dual ? 2 : 1;
         if (with_bitmaps <= (size_t)h->smem_optin) {

@@ -642,7 +642,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
         if (T <= FAST_MAX_TYPES)                /* standing decisions + their tables */
-            smem += (size_t)T * (sizeof(TSlot) + 256 + 2 * FAST_NSIG * 64 + 16 + sizeof(TyFast)) + ((MAPT_BYTES + 15) & ~15) +
+            smem += (size_t)T * (256 + 2 * FAST_NSIG * 64 + 16 + sizeof(TyFast)) + ((MAPT_BYTES + 15) & ~15) +
                     (((size_t)(T + 2) * 4 + 15) & ~(size_t)15);
         const size_t with_bitmaps = smem + bm_bytes;
         /* a second CTA takes the GPU pods when the two pod classes cannot meet (decided on the device, see sweep_kernel) */

@@ -1169,15 +1169,6 @@ constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
 constexpr int FAST_NSIG = 4;          /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
 constexpr int MAPT_BYTES = 4096 + 64;
 
-struct TSlot {
-    int node;                /* node the slot was made for (-1: none)                                   */
-    int kind;                /* NHD_SLOT_*                                                              */
-    uint32_t dec;            /* FAST: tuple | misc NUMA << 2 | NIC picks on NUMA 0 << 8 | on NUMA 1 << 16 */
-    uint32_t w14;            /* FAST: NodeDyn.consumed before the pod (prefix offsets of its core ids)  */
-    uint4 after[2];          /* FAST: NodeDyn once the pod is placed                                    */
-};
-static_assert(sizeof(TSlot) == 48, "TSlot is three 16-byte chunks");
-
 struct ClsFast {             /* per hardware class, 16 bytes */
     uint32_t li0, li1;       /* byte j = index in Node.nics of the j-th NIC of NUMA 0 / 1 */
     uint8_t sig0, sig1;      /* signature ids of the two NUMA nodes */
@@ -1267,66 +1258,66 @@ __device__ __forceinline__ uint32_t gather_b7(uint32_t x)
     return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
 }
 
+/* what a lane knows about the node it evaluates besides the summary: the NICs in use in NodeNic.idx order
+ * (NUMA 0 in bits 0-3, NUMA 1 in bits 4-7) and the class entry (li0, li1, sig0 | sig1 << 8 | n0 << 16 | n1 << 24) */
+struct NodeAux { uint32_t iu, li0, li1, sig; };
+
 /*
- * One lane, one pod type: what AttemptScheduling does with a pod of type ti on a node with summary du
- * (CPU-only type and node shape covered by the tables; the caller checks TyFast.direct).
- * Returns 0 (node or class outside the direct path), 1 (FindNode would not offer the node), 2 (placed).
+ * One lane, one pod type, no branches: what AttemptScheduling does with a pod of type `tl` on a node with
+ * summary du (CPU-only type and node shape covered by the tables: the caller checks TyFast.direct / ClsFast.ok).
+ * Returns true when the pod is placed; then dec / da / iu_after describe the mapping, the summary after the pod
+ * (SetBusy + the bookkeeping of SetPhysicalIdsFromMapping, Node.py:663-841, + ClaimPodNICResources) and the NICs
+ * in use afterwards.
  */
-__device__ __forceinline__ int fast_eval(const FastTables& ft, int ti, const DynU& du, double now, uint32_t& dec, DynU& da)
+__device__ __forceinline__ bool fast_eval(const FastTables& ft, int tl, const TyFast& ty, const DynU& du, const NodeAux& ax,
+                                          double now, uint32_t& dec, DynU& da, uint32_t& iu_after)
 {
-    if (((du.d.info >> 2) & 7) != 2 || du.d.hw_class == NHD_NO_CLASS) return 0;
-    const ClsFast cf = ft.cls[du.d.hw_class];
-    if (!cf.ok) return 0;
-    const TyFast ty = ft.ty[ti];
-    const int smt = (du.d.info & NHD_DYN_SMT) ? 1 : 0;
-    const uint32_t inuse = du.d.nic_inuse;
-    /* NICs in use, per NUMA node, in NodeNic.idx order */
-    uint32_t iu0 = 0, iu1 = 0;
-    for (int j = 0; j < cf.n0; j++) iu0 |= ((inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;
-    for (int j = 0; j < cf.n1; j++) iu1 |= ((inuse >> ((cf.li1 >> (8 * j)) & 31)) & 1u) << j;
-    const uint32_t w0 = ft.sub0[(ti * FAST_NSIG + cf.sig0) * 16 + iu0];
-    const uint32_t w1 = ft.sub1[(ti * FAST_NSIG + cf.sig1) * 16 + iu1];
+    const int smt = (du.d.info >> 1) & 1;                                     /* NHD_DYN_SMT */
+    const uint32_t w0 = ft.sub0[(tl * FAST_NSIG + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)];
+    const uint32_t w1 = ft.sub1[(tl * FAST_NSIG + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)];
     const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
-    const uint32_t fc0 = du.d.fc[0], fc1 = du.d.fc[1];
-    const uint32_t mB = ft.tb[((ti * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
-                        ft.tb[((ti * 2 + smt) * 2 + 1) * 64 + (fc1 < 63 ? fc1 : 63)];      /* Matcher.py:203-212 */
-    const uint32_t mv = ty.G == 2 ? ft.mapt[(mB << 4) | mC] : ft.mapt[4096 + (((mB & 15) << 2) | (mC & 3))];
-#ifdef NHD_DEBUG_PRINT
-    printf("fast_eval ti=%d G=%d smt=%d cls=%d sig=%d,%d n=%d,%d iu=%u,%u w0=%08x w1=%08x mC=%x fc=%u,%u mB=%x mv=%x hp=%d/%d\n", ti, ty.G, smt, du.d.hw_class, cf.sig0, cf.sig1, cf.n0, cf.n1, iu0, iu1, w0, w1, mC, fc0, fc1, mB, mv, ty.hugepages_gb, du.d.free_hugepages_gb);
-#endif
-    if (!(mv & 0x80) || ty.hugepages_gb > du.d.free_hugepages_gb) return 1;    /* Matcher.py:78, :349 */
-    const int ps = mv & 3, ms = (mv >> 2) & 1;
-    /* bookkeeping of SetPhysicalIdsFromMapping on the summary (apply_decision for a CPU-only pod) */
-    const uint32_t gd = ft.gd[(ti * 2 + smt) * 4 + ps];
+    const uint32_t fc0 = du.q[0].x & 0xFF, fc1 = (du.q[0].x >> 8) & 0xFF;
+    const uint32_t mB = ft.tb[((tl * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
+                        ft.tb[((tl * 2 + smt) * 2 + 1) * 64 + (fc1 < 63 ? fc1 : 63)];      /* Matcher.py:203-212 */
+    const uint32_t mi = ty.G == 2 ? ((mB << 4) | mC) : (4096 + (((mB & 15) << 2) | (mC & 3)));
+    const uint32_t mv = ft.mapt[mi];                                          /* Matcher.py:349, :423-452 */
+    const bool feas = (mv & 0x80) != 0 && ty.hugepages_gb <= du.d.free_hugepages_gb;      /* Matcher.py:78 */
+    const uint32_t ps = mv & 3, ms = (mv >> 2) & 1;
+    const uint32_t gd = ft.gd[(tl * 2 + smt) * 4 + ps];
     uint32_t f0 = fc0 - (gd & 0xFF), f1 = fc1 - (gd >> 8);
     {
-        const uint32_t avail = ms ? f1 : f0;
-        const uint32_t n = ty.n_misc;
-        const uint32_t wd = !smt ? n : (ty.misc_smt ? (n + 1) / 2 : (n < avail ? n : avail));     /* batch_width */
-        if (ms) f1 -= wd; else f0 -= wd;
+        const uint32_t avail = ms ? f1 : f0, n = ty.n_misc;
+        const uint32_t wd = !smt ? n : (ty.misc_smt ? (n + 1) >> 1 : (n < avail ? n : avail));     /* batch_width */
+        f0 -= ms ? 0u : wd;
+        f1 -= ms ? wd : 0u;
     }
     const uint32_t e0 = (w0 >> (8 * ps)) & 0xFF, e1 = (w1 >> (8 * ps)) & 0xFF;
-    uint32_t claim = 0;
+    /* NICs the groups claim (Node.py:742-755, :644-646); G <= 2: group 0 is the high digit of the tuple */
+    uint32_t claim = 0, ciu = 0;
     {
-        int m0 = 0, m1 = 0;                              /* members seen so far on NUMA 0 / 1 */
-        for (int g = 0; g < ty.G; g++) {
-            const int numa = (ps >> (ty.G - 1 - g)) & 1;
-            const uint32_t x = numa ? (e1 >> (2 * m1)) & 3 : (e0 >> (2 * m0)) & 3;
-            if (numa) m1++; else m0++;
-            const uint32_t l = ((numa ? cf.li1 : cf.li0) >> (8 * x)) & 31;
-            if ((ty.nic_groups >> g) & 1) claim |= 1u << l;
-        }
+        const uint32_t numa0 = ty.G == 2 ? (ps >> 1) & 1 : ps & 1;
+        const uint32_t x0 = (numa0 ? e1 : e0) & 3;
+        const uint32_t l0 = ((numa0 ? ax.li1 : ax.li0) >> (8 * x0)) & 31;
+        const uint32_t t0 = ty.nic_groups & 1u;
+        claim |= t0 << l0; ciu |= t0 << (x0 + 4 * numa0);
+        const uint32_t numa1 = ps & 1;
+        const uint32_t sh1 = numa1 == numa0 ? 2u : 0u;                        /* second member of that NUMA node's set, or first */
+        const uint32_t x1 = ((numa1 ? e1 : e0) >> sh1) & 3;
+        const uint32_t l1 = ((numa1 ? ax.li1 : ax.li0) >> (8 * x1)) & 31;
+        const uint32_t t1 = ty.G == 2 ? (ty.nic_groups >> 1) & 1u : 0u;
+        claim |= t1 << l1; ciu |= t1 << (x1 + 4 * numa1);
     }
     da.q[0] = du.q[0]; da.q[1] = du.q[1];
     const uint32_t fcw = (du.q[0].x & 0xFFFF0000u) | f0 | (f1 << 8);
     da.q[0].x = fcw;
     da.q[0].y = du.q[0].y + (du.q[0].x - fcw);              /* per byte, no borrows: each width <= what is free */
-    da.d.info |= NHD_DYN_TOUCHED;
-    da.d.nic_inuse = inuse | claim;                           /* Node.py:644-646 */
-    if (ty.hugepages_gb > 0) da.d.free_hugepages_gb -= ty.hugepages_gb;      /* Node.py:794-796 */
+    da.q[0].z = du.q[0].z | ((uint32_t)NHD_DYN_TOUCHED << 16);
+    da.q[0].w = du.q[0].w | claim;
+    da.q[1].x = du.q[1].x - (uint32_t)(ty.hugepages_gb > 0 ? ty.hugepages_gb : 0);       /* Node.py:794-796 */
     da.d.busy_time = now;                                     /* NHDScheduler.py:289 */
-    dec = (uint32_t)ps | ((uint32_t)ms << 2) | (e0 << 8) | (e1 << 16);
-    return 2;
+    iu_after = ax.iu | ciu;
+    dec = ps | (ms << 2) | (e0 << 8) | (e1 << 16);
+    return feas;
 }
 
 /* summary of a node for the direct path: the cache, else HBM — through L1 while no pod of the batch has been
@@ -1339,78 +1330,117 @@ __device__ __forceinline__ void fast_load_dyn(const SweepArgs& a, const SweepCtx
     else { du.q[0] = a.dyn[(size_t)node * 2]; du.q[1] = a.dyn[(size_t)node * 2 + 1]; }
 }
 
+/* class entry and compact in-use bits of a node with summary du; false when the direct path does not cover it */
+__device__ __forceinline__ bool fast_node_aux(const FastTables& ft, const DynU& du, NodeAux& ax)
+{
+    ax.iu = ax.li0 = ax.li1 = ax.sig = 0;
+    if (((du.d.info >> 2) & 7) != 2 || du.d.hw_class == NHD_NO_CLASS) return false;
+    const ClsFast cf = ft.cls[du.d.hw_class];
+    if (!cf.ok) return false;
+    const uint32_t inuse = du.d.nic_inuse;
+    uint32_t iu = 0;
+    for (int j = 0; j < cf.n0; j++) iu |= ((inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;
+    for (int j = 0; j < cf.n1; j++) iu |= ((inuse >> ((cf.li1 >> (8 * j)) & 31)) & 1u) << (4 + j);
+    ax.iu = iu; ax.li0 = cf.li0; ax.li1 = cf.li1;
+    ax.sig = (uint32_t)cf.sig0 | ((uint32_t)cf.sig1 << 8) | ((uint32_t)cf.n0 << 16) | ((uint32_t)cf.n1 << 24);
+    return true;
+}
+
+/* per-lane standing decision (lane t = pod type t), kept in registers */
+struct LaneSlot {
+    int node, kind;          /* NHD_SLOT_* */
+    uint32_t dec, w14;       /* FAST: packed mapping; NodeDyn.consumed before the pod */
+    DynU after;              /* FAST: summary once the pod is placed */
+    NodeAux ax;              /* FAST: class entry of the node, NICs in use once the pod is placed */
+    int c;                   /* CPU-only types: word of F[t] & NOGPU the lane is at, and what is left of it */
+    uint64_t w;
+};
+
 /*
- * Work the standing decisions of the types in `stale` out again, lane t = type t.  CPU-only types start from
- * (node, st) when the caller just committed there (node >= 0), else from their first candidate; a node that
- * does not take the type loses the type's bit for good (resources only shrink inside a batch) and the lane moves
- * on to the next candidate.  GPU types look for their first candidate that is not busy.
+ * Bring the lanes' standing decisions up to date after a pod (lane t = pod type t; all 32 lanes call).
+ *   eval_first   a directly decided pod was just committed at node0 (summary st0, aux ax0): EVERY lane with a
+ *                directly evaluable CPU-only type evaluates its type there, so that the bits of F at nodes pods have
+ *                been bound to stay exact; lanes whose decision was for node0 take the result as their new decision.
+ *                A lane whose type no longer fits clears the bit (resources only shrink inside a batch) and, if node0
+ *                was its candidate, moves on to its next one;
+ *   rescan_cpu / rescan_gpu   lanes that must look their candidate up again (after the ordinary path).
+ * Every pass of the loop evaluates all lanes that need it side by side; lanes only part ways to scan and load.
  */
 template <bool SMEM_BITMAPS>
-__device__ __forceinline__ void refresh_slots(const SweepArgs& a, const SweepCtx& cx, const FastTables& ft, TSlot* slots,
-                                              uint64_t* BM, const uint64_t* NOGPU, const uint64_t* BUSY, const uint64_t* touched,
-                                              int W, int32_t* cursors, double now, uint32_t stale, uint32_t cpu_mask,
-                                              int node0, const DynU& st)
+__device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx& cx, const FastTables& ft, const TyFast& ty, int tl,
+                                              bool l_direct, bool l_cpu, bool l_gpu, LaneSlot& sl, uint64_t* BM, const uint64_t* NOGPU,
+                                              const uint64_t* BUSY, const uint64_t* touched, int W, int32_t* cursors, double now,
+                                              bool eval_first, int node0, const DynU& st0, const NodeAux& ax0,
+                                              uint32_t rescan_cpu, uint32_t rescan_gpu)
 {
-    const int ti = cx.lane;
+    const int lane = cx.lane;
+    uint64_t* F = BM + (size_t)tl * W;
+    bool need = eval_first && l_direct;
+    bool pointing = sl.node == node0;
+    bool dead = !eval_first && l_cpu && ((rescan_cpu >> lane) & 1);
+    int cur_node = node0;
+    DynU cur;
+    cur.q[0] = st0.q[0]; cur.q[1] = st0.q[1];
+    NodeAux cax = ax0;
     __syncwarp();
-    if ((stale >> ti) & 1) {
-        TSlot* sl = &slots[ti];
-        uint64_t* F = BM + (size_t)ti * W;
-        if ((cpu_mask >> ti) & 1) {
-            int node = node0;
-            DynU du;
-            du.q[0] = st.q[0]; du.q[1] = st.q[1];
-            PROFL_DECL
-            for (;;) {
-                if (node < 0) {
-                    /* first candidate of the GPU-less pass (Matcher.py:412-416) */
-                    int c = cursors[ti * 3 + 0];
-                    const int c_in = c;
-                    uint64_t w = 0;
-                    while (c < W) {
-                        w = ldw<SMEM_BITMAPS>(&F[c]) & ldw<SMEM_BITMAPS>(&NOGPU[c]);
-                        if (w) break;
-                        c++;
+    if (dead && sl.c >= 0 && sl.c < W)                       /* the ordinary path may have cleared bits of this word */
+        sl.w &= ldw<SMEM_BITMAPS>(&F[sl.c]);
+    for (;;) {
+        if (__any_sync(0xFFFFFFFFu, need)) {
+            uint32_t dec = 0, iu2 = 0;
+            DynU da;
+            const bool feas = fast_eval(ft, tl, ty, cur, cax, now, dec, da, iu2);
+            if (need) {
+                if (feas) {
+                    if (pointing) {
+                        sl.node = cur_node; sl.kind = NHD_SLOT_FAST; sl.dec = dec; sl.w14 = cur.q[0].y;
+                        sl.after.q[0] = da.q[0]; sl.after.q[1] = da.q[1];
+                        sl.ax = cax; sl.ax.iu = iu2;
                     }
-                    if (c != c_in) cursors[ti * 3 + 0] = c;            /* a lower bound stays one: bits are only cleared */
-                    if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_SLOW; break; }      /* the pod will spill: ordinary path */
-                    node = c * 64 + ctz64(w);
-                    PROFL(0);      /* scan */
-                    fast_load_dyn(a, cx, touched, node, du);
-                    PROFL(1);      /* summary load (value used: the clock read waits for it) */
+                } else {
+                    bit_clear(F, cur_node);
+                    if (sl.c == (cur_node >> 6)) sl.w &= ~(1ULL << (cur_node & 63));
+                    dead = pointing;
                 }
-                uint32_t dec = 0;
-                DynU da;
-                const int state = ft.ty[ti].direct ? fast_eval(ft, ti, du, now, dec, da) : 0;
-                PROFL(2);          /* evaluation */
-                if (state == 2) {
-                    sl->node = node; sl->kind = NHD_SLOT_FAST; sl->dec = dec; sl->w14 = du.q[0].y;
-                    sl->after[0] = da.q[0]; sl->after[1] = da.q[1];
-                    PROFL(3);      /* slot store */
-                    break;
+            }
+            need = false;
+        }
+        if (!__any_sync(0xFFFFFFFFu, dead)) break;
+        if (dead) {
+            /* next candidate of the GPU-less pass (Matcher.py:412-416) */
+            if (sl.c < W)
+                while (sl.w == 0) {
+                    sl.c++;
+                    if (sl.c >= W) break;
+                    sl.w = ldw<SMEM_BITMAPS>(&F[sl.c]) & ldw<SMEM_BITMAPS>(&NOGPU[sl.c]);
                 }
-                if (state == 0) { sl->node = node; sl->kind = NHD_SLOT_SLOW; break; }     /* a shape the tables do not cover */
-                bit_clear(F, node);
-                node = -1;
-            }
-        } else {
-            /* first candidate that is not busy (Matcher.py:107-111) */
-            int c = cursors[ti * 3 + 2];
-            const int c_in = c;
-            uint64_t w = 0;
-            while (c < W) {
-                w = ldw<SMEM_BITMAPS>(&F[c]) & ~ldw<SMEM_BITMAPS>(&BUSY[c]);
-                if (w) break;
-                c++;
-            }
-            if (c != c_in) cursors[ti * 3 + 2] = c;
-            if (c >= W) { sl->node = -1; sl->kind = NHD_SLOT_NONE; }        /* final: busy bits are only set on a constant clock */
+            if (sl.c >= W) { sl.node = -1; sl.kind = NHD_SLOT_SLOW; }        /* the pod will spill: ordinary path */
             else {
-                const int node = c * 64 + ctz64(w);
-                sl->node = node;
-                /* no pod of this batch was bound there: the snapshot bit is exact; else the ordinary path */
-                sl->kind = ((touched[c] >> (node & 63)) & 1) ? NHD_SLOT_SLOW : NHD_SLOT_DEFER;
+                cur_node = sl.c * 64 + ctz64(sl.w);
+                fast_load_dyn(a, cx, touched, cur_node, cur);
+                if (l_direct && fast_node_aux(ft, cur, cax)) { need = true; pointing = true; }
+                else { sl.node = cur_node; sl.kind = NHD_SLOT_SLOW; }         /* a shape the tables do not cover */
             }
+            dead = false;
+        }
+    }
+    if (l_gpu && ((rescan_gpu >> lane) & 1)) {
+        /* first candidate that is not busy (Matcher.py:107-111) */
+        int c = cursors[tl * 3 + 2];
+        const int c_in = c;
+        uint64_t w = 0;
+        while (c < W) {
+            w = ldw<SMEM_BITMAPS>(&F[c]) & ~ldw<SMEM_BITMAPS>(&BUSY[c]);
+            if (w) break;
+            c++;
+        }
+        if (c != c_in) cursors[tl * 3 + 2] = c;
+        if (c >= W) { sl.node = -1; sl.kind = NHD_SLOT_NONE; }            /* final: busy bits are only set on a constant clock */
+        else {
+            const int node = c * 64 + ctz64(w);
+            sl.node = node;
+            /* no pod of this batch was bound there: the snapshot bit is exact; else the ordinary path */
+            sl.kind = ((touched[c] >> (node & 63)) & 1) ? NHD_SLOT_SLOW : NHD_SLOT_DEFER;
         }
     }
     __syncwarp();
@@ -1475,8 +1505,7 @@ sweep_kernel(const SweepArgs a)
     uint8_t* p3 = p2 + (((size_t)T * 3 * 4 + 15) & ~(size_t)15);
     /* standing decisions and their tables (constant clock, one lane per type) */
     const bool fast_cap = cx.types_in_smem && T <= FAST_MAX_TYPES;
-    TSlot* slots = reinterpret_cast<TSlot*>(p3);                                /* [T] */
-    uint8_t* s_tb = p3 + (fast_cap ? (size_t)T * sizeof(TSlot) : 0);            /* [T][2][2][64] */
+    uint8_t* s_tb = p3;                                                         /* [T][2][2][64] */
     uint32_t* s_sub0 = reinterpret_cast<uint32_t*>(s_tb + (fast_cap ? (size_t)T * 256 : 0));      /* [T][FAST_NSIG][16] */
     uint32_t* s_sub1 = s_sub0 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0);
     uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_sub1 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0));   /* [T][2][4] */
@@ -1496,8 +1525,6 @@ sweep_kernel(const SweepArgs a)
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
     const bool fast = fast_cap && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
     if (fast) {
-        for (int i = tid; i < T * (int)(sizeof(TSlot) / 16); i += SWEEP_THREADS)     /* node -1, NHD_SLOT_SLOW */
-            reinterpret_cast<uint4*>(slots)[i] = (i % (int)(sizeof(TSlot) / 16)) == 0 ? make_uint4(0xFFFFFFFFu, NHD_SLOT_SLOW, 0, 0) : make_uint4(0, 0, 0, 0);
         for (int i = tid; i < (MAPT_BYTES + 15) / 16; i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_mapt)[i] = reinterpret_cast<const uint4*>(a.mapt)[i];
         for (int tt = tid; tt < T; tt += SWEEP_THREADS) {
@@ -1703,19 +1730,34 @@ sweep_kernel(const SweepArgs a)
     /* standing decisions: constant clock, the node-group gate folded into the types, one lane per type */
     const bool cclock = a.dual != 0;
     uint32_t cpu_mask = 0, gpu_mask = 0;
+    unsigned long long gpu_pods_mask = 0;                   /* (side by side) types whose pods CTA 1 sweeps */
     FastTables ft;
     ft.tb = s_tb; ft.sub0 = s_sub0; ft.sub1 = s_sub1; ft.mapt = s_mapt; ft.gd = s_gd; ft.ty = s_ty; ft.cls = a.cls_fast;
     DynU st_none;
     st_none.q[0] = make_uint4(0, 0, 0, 0); st_none.q[1] = st_none.q[0];
+    NodeAux ax_none = {0, 0, 0, 0};
+    /* lane t = pod type t: its type record and its standing decision live in registers */
+    const int tl = lane < T ? lane : 0;
+    TyFast myty;
+    myty.G = 1; myty.n_misc = 0; myty.misc_smt = 0; myty.nic_groups = 0; myty.direct = 0; myty.hugepages_gb = 0;
+    bool l_cpu = false, l_gpu = false, l_direct = false;
+    LaneSlot sl;
+    sl.node = -1; sl.kind = NHD_SLOT_SLOW; sl.dec = sl.w14 = 0; sl.after.q[0] = st_none.q[0]; sl.after.q[1] = st_none.q[0];
+    sl.ax = ax_none; sl.c = -1; sl.w = 0;
+    const double now0 = a.n_pods > 0 ? a.now[0] : 0.0;
     if (fast) {
         for (int tt = 0; tt < T; tt++) {
             const PodType& ty = types[tt];
             if (!ty.valid_map) continue;
             if (ty.needs_gpu) gpu_mask |= 1u << tt; else cpu_mask |= 1u << tt;
         }
+        gpu_pods_mask = gpu_mask;
         if (split) gpu_mask = 0;                            /* CTA 1 sweeps the GPU pods */
-        refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, a.n_pods > 0 ? a.now[0] : 0.0,
-                                    cpu_mask | gpu_mask, cpu_mask, -1, st_none);
+        if (lane < T) myty = s_ty[lane];
+        l_cpu = (cpu_mask >> lane) & 1; l_gpu = (gpu_mask >> lane) & 1;
+        l_direct = l_cpu && myty.direct;
+        lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now0,
+                                    false, -1, st_none, ax_none, cpu_mask, gpu_mask);
     }
 
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
@@ -1744,33 +1786,40 @@ sweep_kernel(const SweepArgs a)
       const int my_ti = (i0 + lane < a.n_pods) ? a.pod_type[i0 + lane] : 0;
       const double my_now = (i0 + lane < a.n_pods) ? a.now[i0 + lane] : 0.0;
       const unsigned long long my_gm = (multi && i0 + lane < a.n_pods) ? a.pod_groups[i0 + lane] : 0ULL;
-      const int jn = (a.n_pods - i0) < 32 ? (a.n_pods - i0) : 32;
-      for (int j = 0; j < jn; j++) {
+      /* this CTA's pods of the chunk: all of them, or (side by side) all but the GPU pods CTA 1 sweeps */
+      const bool in_chunk = i0 + lane < a.n_pods;
+      uint32_t todo = __ballot_sync(0xFFFFFFFFu, in_chunk && !(split && ((gpu_pods_mask >> my_ti) & 1)));
+      for (; todo; todo &= todo - 1) {
+        const int j = ctz32(todo);
         const int i = i0 + j;
         const int ti = __shfl_sync(0xFFFFFFFFu, my_ti, j);
-        const double now = __shfl_sync(0xFFFFFFFFu, my_now, j);
+        const double now = cclock ? now0 : __shfl_sync(0xFFFFFFFFu, my_now, j);
         const unsigned long long gm = multi ? (__shfl_sync(0xFFFFFFFFu, my_gm, j) & a.names_used) : 0ULL;
         const PodType& t = types[ti];
-        if (split && t.needs_gpu && t.valid_map) continue;          /* CTA 1's pod */
         nhd_binding* bout = &a.out[i];
         uint64_t* F = BM + (size_t)ti * W;
 
-        /* ---- standing decision of the pod's type ---- */
+        /* ---- standing decision of the pod's type (held by lane ti) ---- */
         bool handled = false, fast_commit = false;
         int commit_node = -1;                  /* node this pod changed (summary, BUSY / touched bits) */
         DynU da;
         da.q[0] = make_uint4(0, 0, 0, 0); da.q[1] = da.q[0];
+        NodeAux dax = ax_none;
         if (fast) {
-            const TSlot* sl = &slots[ti];
-            const uint4 hd = *reinterpret_cast<const uint4*>(sl);       /* node, kind, packed mapping, consumed before */
-            const int node = (int)hd.x, kind = (int)hd.y;
+            const int kind = __shfl_sync(0xFFFFFFFFu, sl.kind, ti), node = __shfl_sync(0xFFFFFFFFu, sl.node, ti);
             if (kind == NHD_SLOT_FAST) {
-                da.q[0] = sl->after[0]; da.q[1] = sl->after[1];
+                const uint32_t dec = __shfl_sync(0xFFFFFFFFu, sl.dec, ti), w14 = __shfl_sync(0xFFFFFFFFu, sl.w14, ti);
+                da.q[0].x = __shfl_sync(0xFFFFFFFFu, sl.after.q[0].x, ti); da.q[0].y = __shfl_sync(0xFFFFFFFFu, sl.after.q[0].y, ti);
+                da.q[0].z = __shfl_sync(0xFFFFFFFFu, sl.after.q[0].z, ti); da.q[0].w = __shfl_sync(0xFFFFFFFFu, sl.after.q[0].w, ti);
+                da.q[1].x = __shfl_sync(0xFFFFFFFFu, sl.after.q[1].x, ti); da.q[1].y = __shfl_sync(0xFFFFFFFFu, sl.after.q[1].y, ti);
+                da.q[1].z = __shfl_sync(0xFFFFFFFFu, sl.after.q[1].z, ti); da.q[1].w = __shfl_sync(0xFFFFFFFFu, sl.after.q[1].w, ti);
+                dax.iu = __shfl_sync(0xFFFFFFFFu, sl.ax.iu, ti); dax.li0 = __shfl_sync(0xFFFFFFFFu, sl.ax.li0, ti);
+                dax.li1 = __shfl_sync(0xFFFFFFFFu, sl.ax.li1, ti); dax.sig = __shfl_sync(0xFFFFFFFFu, sl.ax.sig, ti);
 #ifdef NHD_CHECKS
                 {
                     DynU dx; load_dyn(a, cx, node, dx);
                     CHK_SANE(dx, node, 2);
-                    if (dx.q[0].y != hd.w) CHK_FAIL(3, node, dx.q[0].y, hd.w);
+                    if (dx.q[0].y != w14) CHK_FAIL(3, node, dx.q[0].y, w14);
                     PMap pmx = {0, 0, 0, 0}; Picks pkx; pkx.fail_status = 0; bool msx;
                     const int stx = resolve_decision(a, cx, ti, t, node, dx, pmx, pkx, msx);
                     if (stx < 2) CHK_FAIL(4, node, stx, 0);
@@ -1780,14 +1829,14 @@ sweep_kernel(const SweepArgs a)
                         __syncwarp();
                         if (!same_dyn(dx, da)) CHK_FAIL(5, node, dx.q[0].x, da.q[0].x);
                         /* the packed mapping: tuple, misc NUMA, NodeNic.idx per group */
-                        const int ps = hd.z & 3, G = t.G;
+                        const int ps = dec & 3, G = t.G;
                         uint32_t pn = 0, ix = 0; int k0 = 0, k1 = 0;
                         for (int g = 0; g < G; g++) {
                             const int numa = (ps >> (G - 1 - g)) & 1;
-                            const uint32_t x = numa ? (((hd.z >> 16) & 0xFF) >> (2 * k1++)) & 3 : (((hd.z >> 8) & 0xFF) >> (2 * k0++)) & 3;
+                            const uint32_t x = numa ? (((dec >> 16) & 0xFF) >> (2 * k1++)) & 3 : (((dec >> 8) & 0xFF) >> (2 * k0++)) & 3;
                             pn |= (uint32_t)numa << (8 * g); ix |= x << (8 * g);
                         }
-                        if (pn != pmx.pn || ix != pmx.idx || ((hd.z >> 2) & 1) != pmx.ms) CHK_FAIL(8, node, hd.z, pmx.pn);
+                        if (pn != pmx.pn || ix != pmx.idx || ((dec >> 2) & 1) != pmx.ms) CHK_FAIL(8, node, dec, pmx.pn);
                     }
                     /* and it is the first fit of the GPU-less pass */
                     for (int w = lane; w < (node >> 6); w += 32)
@@ -1803,9 +1852,8 @@ sweep_kernel(const SweepArgs a)
                     const uint4 half = lane == 0 ? da.q[0] : da.q[1];
                     cx.dcache[2 * cs + lane] = half;
                     a.dyn[(size_t)node * 2 + lane] = half;
-                } else if (lane == 2) cx.dtag[cs] = node;
-                else if (lane == 3) bit_set(s_touched, node);
-                else if (lane == 4) *reinterpret_cast<uint4*>(bout) = make_uint4(NHD_PENDING_FAST, (uint32_t)node, hd.z, hd.w);
+                } else if (lane == 2) { cx.dtag[cs] = node; bit_set(s_touched, node); }
+                else if (lane == 3) *reinterpret_cast<uint4*>(bout) = make_uint4(NHD_PENDING_FAST, (uint32_t)node, dec, w14);
                 commit_node = node;
                 handled = true; fast_commit = true;
                 PROF_COUNT(13);
@@ -2032,15 +2080,17 @@ sweep_kernel(const SweepArgs a)
         } while (0);
         __syncwarp();
         if (fast) {
-            /* every standing decision made for the node this pod changed is out of date; after the ordinary path
-             * the pod's own type as well (it may have given up the node its slot names) */
-            uint32_t st = handled ? 0u : (1u << ti);
-            if (commit_node >= 0) st |= __ballot_sync(0xFFFFFFFFu, lane < T && slots[lane].node == commit_node);
-            st &= cpu_mask | gpu_mask;
-            PROF_MARK(5);      /* (fast path) stale mask */
-            if (st) {
-                if (fast_commit) refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, commit_node, da);
-                else refresh_slots<SMEM_BITMAPS>(a, cx, ft, slots, BM, NOGPU, BUSY, s_touched, W, cursors, now, st, cpu_mask, -1, st_none);
+            if (fast_commit) {
+                lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now,
+                                            true, commit_node, da, dax, 0u, 0u);
+            } else {
+                /* every standing decision made for the node this pod changed is out of date; after the ordinary path
+                 * the pod's own type as well (it may have given up the node its slot names) */
+                uint32_t st = handled ? 0u : (1u << ti);
+                if (commit_node >= 0) st |= __ballot_sync(0xFFFFFFFFu, sl.node == commit_node);
+                if (st & (cpu_mask | gpu_mask))
+                    lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now,
+                                                false, -1, st_none, ax_none, st & cpu_mask, st & gpu_mask);
             }
         }
         PROF_MARK(6);      /* write-back + refresh */

@@ -49,7 +49,8 @@ _PINNED = {}
 
 class Solver:
     def __init__(self, speed_table, nic_bw_avail_percent=0.9, min_busy_secs=30.0, device=0,
-                 rank=0, world_size=1, nccl_id: bytes = None, single_warp: bool = False, cpu_warps: int = 0):
+                 rank=0, world_size=1, nccl_id: bytes = None, single_warp: bool = False, cpu_warps: int = 0,
+                 sweep_debug: int = 0):
         self._L = _lib.load()
         p = _lib.Params()
         self._L.nhd_default_params(ctypes.byref(p))
@@ -61,8 +62,11 @@ class Solver:
         for i, s in enumerate(speeds[:16]):
             p.speed_gbps[i] = s
         p.device, p.rank, p.world_size = device, rank, world_size
-        # debug knobs: force the one-warp sweep, or pick the number of CPU-class sweeping warps (1..3)
-        p.reserved_ = (1 if single_warp else (cpu_warps + 1 if cpu_warps else 0)) | (int(os.environ.get('NHD_SWEEP_DEBUG', '0')) << 8)
+        # test knobs (all settings produce identical bindings): single_warp = the general one-warp sweep only;
+        # cpu_warps = 1: never sweep the two pod classes side by side; sweep_debug bit 0: no standing decisions,
+        # bit 1: same as cpu_warps = 1
+        p.reserved_ = (1 if single_warp else (cpu_warps + 1 if cpu_warps else 0)) | \
+            ((int(sweep_debug) | int(os.environ.get('NHD_SWEEP_DEBUG', '0'))) << 8)
         if world_size > 1:
             if not nccl_id or len(nccl_id) != 128:
                 raise ValueError('world_size > 1 needs the 128-byte NCCL unique id of rank 0')

@@ -170,6 +170,7 @@ template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred, int line = __builtin_LINE()) { return (unsigned)emu::collective(emu::OP_BALLOT, mask, pred ? 1 : 0, 0, line); }
 static inline int __all_sync(unsigned mask, int pred, int line = __builtin_LINE()) { return (int)emu::collective(emu::OP_ALL, mask, pred ? 1 : 0, 0, line); }
+static inline int __any_sync(unsigned mask, int pred, int line = __builtin_LINE()) { return emu::collective(emu::OP_BALLOT, mask, pred ? 1 : 0, 0, line) != 0; }
 static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu, int line = __builtin_LINE()) { emu::collective(emu::OP_SYNCWARP, mask, 0, 0, line); }
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __nanosleep(unsigned) { emu::yield(); }

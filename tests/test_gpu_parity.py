@@ -8,8 +8,9 @@ from tests import helpers, ref_compare, scenarios
 
 pytestmark = pytest.mark.gpu
 
-# constant-clock batches run the multi-warp sweep: every number of CPU-class warps must agree with the rest
-ALL_CPU_WARPS = (1, 2, 3, 5, 7)
+# constant-clock batches use standing decisions per pod type and, when no CPU-only pod can spill, sweep the two pod
+# classes side by side on two CTAs: every way of running the sweep must agree with the rest byte for byte
+ALL_CPU_WARPS = (1, 2)          # 1: never side by side; 2: default
 
 
 @pytest.fixture(scope='module')
@@ -23,15 +24,18 @@ def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0, extra_cpu_warps
     clock is constant), with the forced one-warp sweep and with one / two CPU-class warps; all must agree
     byte for byte."""
     outs = []
-    for single, cw in ((False, 0), (True, 0)) + tuple((False, c) for c in extra_cpu_warps):
-        s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single, cpu_warps=cw)
+    modes = ((False, 0, 0), (True, 0, 0)) + tuple((False, c, 0) for c in extra_cpu_warps)
+    if extra_cpu_warps:
+        modes += ((False, 0, 1),)              # constant-clock sweep without standing decisions
+    for single, cw, dbg in modes:
+        s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single, cpu_warps=cw, sweep_debug=dbg)
         try:
             s.load_nodes(recs)
             b = s.solve_batch(pods, now)
             final = s.read_nodes()
             outs.append((b, final, s.timing()))
         except Exception as e:
-            raise AssertionError(f'sweep mode single_warp={single} cpu_warps={cw}: {e}') from e
+            raise AssertionError(f'sweep mode single_warp={single} cpu_warps={cw} debug={dbg}: {e}') from e
         finally:
             s.close()
     for k, o in enumerate(outs[1:]):

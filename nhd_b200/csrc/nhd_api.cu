@@ -288,6 +288,17 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
                             FILTER_STAGES * SUPER_BYTES + TYPES_SMEM_MAX * (int)sizeof(PodType)));
     CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     CK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    {
+        /* one empty launch of the big kernel: its code is loaded (lazy module loading) and resident before the first
+         * real batch instead of inside it (a first sweep used to take tens of milliseconds) */
+        SweepArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        const size_t smem = (size_t)SMEMO_SLOTS * 16 + (size_t)DMEMO_SLOTS * 48 + (size_t)DCACHE_SLOTS * 36 + 16 +
+                            (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16 + 4096;
+        sweep_kernel<true><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
+        sweep_kernel<false><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
+        CK(cudaGetLastError());
+    }
     if (p->world_size > 1) {
         if (!g_nccl.load()) return fail(h, NHD_ERR_NCCL, "libnccl.so.2 not loadable");
         ncclUniqueId_ id;

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import workload
-from nhd_b200 import sharding
+from tests import sharding_helpers as sharding
 
 
 def test_shard_ranges_partition_the_cluster():

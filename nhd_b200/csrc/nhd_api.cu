@@ -31,14 +31,14 @@ using namespace nhd;
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId_;
 typedef int ncclResult_t_;
-enum { NCCL_UINT64 = 5, NCCL_SUM = 0 };      /* ncclUint64, ncclSum (nccl.h, stable since 2.0) */
+enum { NCCL_INT8 = 0 };                       /* ncclInt8 / ncclChar (nccl.h, stable since 2.0) */
 
 struct NcclApi {
     void* lib = nullptr;
     ncclResult_t_ (*GetUniqueId)(ncclUniqueId_*) = nullptr;
     ncclResult_t_ (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_, int) = nullptr;
     ncclResult_t_ (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t_ (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t_ (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t_) = nullptr;
     bool load()
     {
@@ -51,9 +51,9 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
-        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather;
     }
 };
 static NcclApi g_nccl;
@@ -98,6 +98,7 @@ struct nhd_handle {
     unsigned long long* d_prof = nullptr;
     int* d_vresult = nullptr;
     uint64_t* d_memo = nullptr;
+    uint8_t* d_xchg = nullptr;  size_t xchg_cap = 0;     /* node-sharded ranks: one slot per rank (summaries + bitmap columns) */
     uint8_t* d_mapt = nullptr;            /* GetNumaGroupIdx table of the direct path */
     uint32_t* d_sigs = nullptr;           /* per-NUMA NIC signatures */
     ClsFast* d_cls_fast = nullptr;        /* per hardware class */
@@ -223,7 +224,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_mapt); cudaFree(h->d_sigs); cudaFree(h->d_cls_fast); 
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_mapt); cudaFree(h->d_xchg); cudaFree(h->d_sigs); cudaFree(h->d_cls_fast); 
 #ifdef NHD_CHECKS
     cudaFreeHost(h->d_prof);
 #else
@@ -598,19 +599,39 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     int launches = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
 
-    /* 1. snapshot predicate kernel over this rank's node shard */
+    /* 1. snapshot predicate kernel over this rank's node shard.  With several ranks every rank filters the nodes
+     * of S consecutive super-tiles into its slot of an exchange buffer (their NodeDyn summaries, then their
+     * columns of every bitmap row); one all-gather hands every rank all slots, and a small kernel lays them out
+     * as the arrays the (replicated) sweep reads.  Clusters too small for that to pay are filtered whole by
+     * every rank, without any exchange. */
     const int ws = h->params.world_size, rk = h->params.rank;
-    const int super_lo = (int)((long)h->n_super * rk / ws), super_hi = (int)((long)h->n_super * (rk + 1) / ws);
-    const size_t bm_bytes = (size_t)(T + 2 + h->n_names) * W * 8;
-    if (ws > 1) CK(cudaMemsetAsync(h->d_bitmaps, 0, bm_bytes, h->stream));
-    if (h->n_pods > 0) {
+    const int rows = T + 2 + h->n_names;
+    const size_t bm_bytes = (size_t)rows * W * 8;
+    const bool sharded = ws > 1 && h->n_pods > 0 && (long)h->n_nodes * T >= 16384;
+    const int S = sharded ? (h->n_super + ws - 1) / ws : h->n_super;
+    const int super_lo = sharded ? std::min(rk * S, h->n_super) : 0;
+    const int super_hi = sharded ? std::min(super_lo + S, h->n_super) : h->n_super;
+    const size_t slot_bytes = (size_t)S * 32 * (SUPER_NODES + rows);
+    if (sharded) CK(grow_dev(h->d_xchg, h->xchg_cap, slot_bytes * ws));
+    if (h->n_pods > 0 && super_hi > super_lo) {
         FilterArgs fa;
         fa.nodes = h->d_nodes; fa.types = h->d_types; fa.n_types = T; fa.n_nodes = h->n_nodes;
-        fa.n_super = h->n_super; fa.super_lo = super_lo; fa.super_hi = super_hi; fa.words = W;
-        fa.bitmaps = h->d_bitmaps; fa.dyn = h->d_dyn; fa.class_id = h->d_class; fa.names_used = h->names_used;
+        fa.super_lo = super_lo; fa.super_hi = super_hi;
+        if (sharded) {
+            uint8_t* slot = h->d_xchg + slot_bytes * rk;
+            fa.dyn = reinterpret_cast<uint4*>(slot);
+            fa.bitmaps = reinterpret_cast<uint64_t*>(slot + (size_t)S * SUPER_NODES * 32);
+            fa.words = S * 4; fa.word_base = super_lo * 4;
+        } else {
+            fa.dyn = h->d_dyn; fa.bitmaps = h->d_bitmaps; fa.words = W; fa.word_base = 0;
+        }
+        fa.class_id = h->d_class; fa.names_used = h->names_used;
         fa.now0 = h->now0; fa.min_busy = h->params.min_busy_secs;
         memcpy(fa.cap, h->cap, sizeof(fa.cap));
-        const int grid = std::min(h->n_super, h->sm_count * 2);
+        /* few super-tiles (small cluster, or a rank's shard): deal the pod types over several CTAs per super-tile */
+        const int n_sh = super_hi - super_lo;
+        fa.type_split = std::max(1, std::min(T, (h->sm_count * 2) / n_sh));
+        const int grid = std::min(n_sh, h->sm_count * 2) * fa.type_split;
         const size_t smem = FILTER_STAGES * SUPER_BYTES + (T <= TYPES_SMEM_MAX ? (size_t)T * sizeof(PodType) : 0);
         filter_kernel<<<grid, FILTER_THREADS, smem, h->stream>>>(fa);
         CK(cudaGetLastError());
@@ -618,11 +639,15 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     }
     CK(cudaEventRecord(h->ev[1], h->stream));
 
-    /* 2. one collective per batch: every rank contributes its disjoint slice of the bitmaps */
-    if (ws > 1 && h->n_pods > 0) {
-        ncclResult_t_ r = g_nccl.AllReduce(h->d_bitmaps, h->d_bitmaps, bm_bytes / 8, NCCL_UINT64, NCCL_SUM, h->comm, h->stream);
-        if (r != 0) return fail(h, NHD_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-        launches++;
+    /* 2. one collective per batch: every rank contributes its slot */
+    if (sharded) {
+        ncclResult_t_ r = g_nccl.AllGather(h->d_xchg + slot_bytes * rk, h->d_xchg, slot_bytes, NCCL_INT8, h->comm, h->stream);
+        if (r != 0) return fail(h, NHD_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        const size_t n16 = slot_bytes / 16 * ws;
+        unpack_slots_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const uint4*>(h->d_xchg), ws, S, h->n_super,
+                                                                              rows, W, h->d_dyn, h->d_bitmaps);
+        CK(cudaGetLastError());
+        launches += 2;
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
 

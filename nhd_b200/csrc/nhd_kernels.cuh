@@ -215,12 +215,13 @@ struct FilterArgs {
     const PodType* types;
     int n_types;
     int n_nodes;
-    int n_super;                 /* all super-tiles (summaries are produced for every node)  */
-    int super_lo, super_hi;      /* this rank's shard, in super-tiles (bitmaps only for it)   */
-    int words;                   /* u64 words per bitmap */
+    int super_lo, super_hi;      /* super-tiles this launch covers (this rank's shard)        */
+    int type_split;              /* CTAs per super-tile: the pod types are dealt over them     */
+    int words;                   /* u64 words per bitmap row of the OUTPUT window              */
+    int word_base;               /* first u64 word (node / 64) of the output window            */
     uint64_t* bitmaps;           /* [n_types + 2 + n_names][words]: F[0..T), NOGPU, BUSY, one per node-group name in use */
     uint64_t names_used;         /* node-group names some pod of the batch asks for (0: gate folded into the types) */
-    uint4* dyn;                  /* [n_nodes padded][2]: NodeDyn summaries */
+    uint4* dyn;                  /* [window nodes][2]: NodeDyn summaries; entry 0 = node 64 * word_base */
     const uint16_t* class_id;    /* hardware class of every node */
     double now0;                 /* clock of the first pod, for the BUSY snapshot */
     double min_busy;
@@ -236,7 +237,10 @@ filter_kernel(const FilterArgs a)
     __shared__ __align__(8) uint64_t full_bar[FILTER_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_my = (a.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    /* CTA = (position in the walk over the super-tiles, type chunk): with few super-tiles per GPU (small clusters,
+     * node-sharded ranks) the pod types are dealt over several CTAs so that the whole machine still works */
+    const int TS = a.type_split, tch = (int)blockIdx.x % TS, cta = (int)blockIdx.x / TS, ncta = (int)gridDim.x / TS;
+    const int n_my = (a.super_hi - a.super_lo - cta + ncta - 1) / ncta;
     if (n_my <= 0) return;
 
     if (tid == 0) {
@@ -246,7 +250,7 @@ filter_kernel(const FilterArgs a)
     __syncthreads();
 
     auto issue = [&](int it) {                                          /* thread 0 only */
-        int st = blockIdx.x + it * gridDim.x;
+        int st = a.super_lo + cta + it * ncta;
         int s = it % FILTER_STAGES;
         mbar_expect_tx(&full_bar[s], SUPER_BYTES);
         tma_load_1d(stage_buf + s * SUPER_BYTES, a.nodes + (size_t)st * SUPER_BYTES, SUPER_BYTES, &full_bar[s]);
@@ -269,7 +273,7 @@ filter_kernel(const FilterArgs a)
 
     for (int it = 0; it < n_my; it++) {
         const int s = it % FILTER_STAGES;
-        const int st = blockIdx.x + it * gridDim.x;
+        const int st = a.super_lo + cta + it * ncta;
         mbar_wait(&full_bar[s], (it / FILTER_STAGES) & 1);
 
         RecU u;
@@ -283,22 +287,23 @@ filter_kernel(const FilterArgs a)
         const int node = st * SUPER_NODES + tid;
         const bool valid = node < a.n_nodes;
 
-        /* per-node summary for the sweep (every rank needs all of them) */
-        {
+        /* per-node summary for the sweep */
+        if (tch == 0) {
             union { NodeDyn d; uint4 q[2]; } du;
             if (valid) { make_dyn(u.r, du.d); du.d.hw_class = a.class_id[node]; }
             else { du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0]; }
-            a.dyn[(size_t)node * 2] = du.q[0];
-            a.dyn[(size_t)node * 2 + 1] = du.q[1];
+            const size_t dn = (size_t)node - (size_t)a.word_base * 64;
+            a.dyn[dn * 2] = du.q[0];
+            a.dyn[dn * 2 + 1] = du.q[1];
         }
-        if (st < a.super_lo || st >= a.super_hi) continue;              /* bitmaps: own shard only */
 
-        const size_t w32 = (size_t)node >> 5;
-        for (int t = 0; t < a.n_types; t++) {
+        const size_t w32 = ((size_t)node >> 5) - (size_t)a.word_base * 2;
+        for (int t = tch; t < a.n_types; t += TS) {
             bool f = valid && node_feasible(u.r, types[t], a.cap);
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, f);
             if (lane == 0) out32[(size_t)t * words32 + w32] = bal;
         }
+        if (tch != 0) continue;
         uint32_t nog = __ballot_sync(0xFFFFFFFFu, valid && u.r.n_gpus == 0);
         uint32_t bsy = __ballot_sync(0xFFFFFFFFu, valid && node_busy(u.r, a.now0, a.min_busy));
         if (lane == 0) {
@@ -311,6 +316,36 @@ filter_kernel(const FilterArgs a)
             const int jn = ctz64(g);
             const uint32_t hasg = __ballot_sync(0xFFFFFFFFu, valid && ((u.r.group_mask >> jn) & 1));
             if (lane == 0) out32[(size_t)(a.n_types + 2 + r) * words32 + w32] = hasg;
+        }
+    }
+}
+
+/*
+ * Node-sharded ranks: after the one collective of the batch (an all-gather of every rank's slot: the NodeDyn
+ * summaries and the bitmap columns of its nodes) the slots are laid back out as the arrays the sweep reads.
+ * Slot q covers super-tiles [q*S, (q+1)*S): S*256 summaries, then rows x S*4 bitmap words.
+ */
+__global__ void unpack_slots_kernel(const uint4* __restrict__ xchg, int ws, int S, int n_super, int rows, int W,
+                                    uint4* __restrict__ dyn, uint64_t* __restrict__ bitmaps)
+{
+    const size_t slot16 = (size_t)S * 2 * (SUPER_NODES + rows);           /* 16-byte units per slot */
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slot16 * (size_t)ws) return;
+    const int q = (int)(i / slot16);
+    const size_t r = i % slot16;
+    const int lo = q * S, hi = lo + S < n_super ? lo + S : n_super;
+    if (lo >= hi) return;
+    const size_t dyn16 = (size_t)S * SUPER_NODES * 2;
+    if (r < dyn16) {
+        if (r < (size_t)(hi - lo) * SUPER_NODES * 2) dyn[(size_t)lo * SUPER_NODES * 2 + r] = xchg[i];
+    } else {
+        const size_t b = r - dyn16;                                          /* 16 bytes = two words of one row */
+        const int row = (int)(b / ((size_t)S * 2)), k2 = (int)(b % ((size_t)S * 2));
+        if (k2 * 2 < (hi - lo) * 4) {
+            const uint4 v = xchg[i];
+            uint64_t* dst = bitmaps + (size_t)row * W + (size_t)lo * 4 + (size_t)k2 * 2;
+            dst[0] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            dst[1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
         }
     }
 }

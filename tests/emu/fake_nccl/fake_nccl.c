@@ -1,12 +1,12 @@
 /*
  * fake_nccl.c — TEST INFRASTRUCTURE.  The five NCCL entry points the library resolves at run time
- * (nhd_b200/csrc/nhd_api.cu: ncclGetUniqueId, ncclCommInitRank, ncclCommDestroy, ncclAllReduce,
+ * (nhd_b200/csrc/nhd_api.cu: ncclGetUniqueId, ncclCommInitRank, ncclCommDestroy, ncclAllGather,
  * ncclGetErrorString) for ranks that are ordinary processes on one machine without GPUs: the
- * communicator is a POSIX shared-memory segment named by the unique id, the all-reduce copies every
- * rank's buffer into its slot, meets at a barrier, sums the slots, meets again.  Built as libnccl.so.2
+ * communicator is a POSIX shared-memory segment named by the unique id, the all-gather copies every
+ * rank's buffer into its slot, meets at a barrier, copies all slots out, meets again.  Built as libnccl.so.2
  * (that soname is what the library looks for) and loaded by the test processes before the emulated
- * library; lets the world_size > 1 path of nhd_solve_batch (sharded filter + one all-reduce + identical
- * sweeps) run in the CPU suite.  Only what that path uses: sum over uint64.
+ * library; lets the world_size > 1 path of nhd_solve_batch (sharded filter + one all-gather + identical
+ * sweeps) run in the CPU suite.  Only what that path uses: bytes.
  */
 #define _GNU_SOURCE
 #include <fcntl.h>
@@ -91,19 +91,15 @@ ncclResult_t ncclCommDestroy(comm_t* c)
     return 0;
 }
 
-ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int op, comm_t* c, void* stream)
+ncclResult_t ncclAllGather(const void* send, void* recv, size_t count, int dtype, comm_t* c, void* stream)
 {
     (void)stream;
-    if (dtype != 5 || op != 0) return 4;                       /* ncclUint64, ncclSum */
-    if (count * 8 > FAKE_SLOT_BYTES) return 4;
-    memcpy(c->sh->slots + (size_t)c->rank * FAKE_SLOT_BYTES, send, count * 8);
+    if (dtype != 0) return 4;                                  /* ncclInt8 */
+    if (count > FAKE_SLOT_BYTES) return 4;
+    memcpy(c->sh->slots + (size_t)c->rank * FAKE_SLOT_BYTES, send, count);
     if (barrier(c)) return 1;
-    uint64_t* out = (uint64_t*)recv;
-    for (size_t i = 0; i < count; i++) {
-        uint64_t acc = 0;
-        for (int r = 0; r < c->n; r++) acc += ((const uint64_t*)(c->sh->slots + (size_t)r * FAKE_SLOT_BYTES))[i];
-        out[i] = acc;
-    }
+    for (int r = 0; r < c->n; r++)
+        memmove((unsigned char*)recv + (size_t)r * count, c->sh->slots + (size_t)r * FAKE_SLOT_BYTES, count);
     return barrier(c);                                         /* nobody overwrites a slot somebody still reads */
 }
 

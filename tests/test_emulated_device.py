@@ -129,7 +129,7 @@ s.close()
 @pytest.mark.parametrize('world,config', [(2, 3), (4, 5)])
 def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path, world, config):
     """SURVEY 8e on the CPU: ``world`` processes, each with an emulated device and the full cluster, compute
-    their shard of the bitmaps, exchange them with one all-reduce (tests/emu/fake_nccl: shared memory instead
+    their shard of the bitmaps, exchange them with one all-gather (tests/emu/fake_nccl: shared memory instead
     of NVLink) and run the identical sweep — every rank must return the oracle's bindings and records."""
     import numpy as np
     import workload

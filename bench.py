@@ -143,6 +143,40 @@ def pick_threads(ob, recs, speed, pods, now, single_per_pod=None):
     return best
 
 
+def quick_value(Solver, recs, speed, pods, now, steps=3, **kw):
+    """decisions/s (device-timed total, batch resident) of a side workload: `steps` solves from the same snapshot."""
+    s = Solver(speed, **kw)
+    try:
+        s.load_nodes(recs)
+        s.snapshot()
+        s.stage_batch(pods, now)
+        best = None
+        for _ in range(steps + 1):
+            s.restore()
+            s.solve_staged()
+            s.sync()
+            t = s.timing()
+            best = t if best is None or t['total_ms'] < best['total_ms'] else best
+        return {'value': len(pods) / (best['total_ms'] / 1e3), 'unit': UNIT, 'ms': best['total_ms'],
+                'filter_ms': best['filter_ms'], 'sweep_ms': best['sweep_ms'], 'pod_types': best['n_types']}
+    finally:
+        s.close()
+
+
+def python_reference_baseline(recs, speed, pods, now, n_pods=8):
+    """The reference's own Python path (unmodified nhd/Matcher.py + Node.py through oracle/ref_loader) on the first
+    pods of the stream at full N, one thread — only where the reference is reachable (NHD_REFERENCE_ROOT or
+    /root/reference; never on the GPU box).  Returns None otherwise."""
+    root = os.environ.get('NHD_REFERENCE_ROOT', '/root/reference')
+    if not os.path.isfile(os.path.join(root, 'nhd', 'Matcher.py')):
+        return None
+    try:
+        from tests import pyref
+        return pyref.time_reference(recs, speed, pods[:n_pods], now[:n_pods])
+    except Exception as e:                      # never let the optional leg take the bench down
+        return {'error': str(e)[:200]}
+
+
 def run_reference_arm(args, rank):
     """CPU arm: the oracle port of the reference path on the host cores.  The reference itself is one
     Python thread (NHDScheduler.py:43); its per-pod walk over all nodes is independent per node, so the
@@ -184,6 +218,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='nhd_b200', choices=['nhd_b200', 'reference'])
     ap.add_argument('--cpu-sample-pods', type=int, default=128)
+    ap.add_argument('--no-extra', action='store_true', help='skip the side workloads (config 5, heterogeneous, moving clock)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
 
@@ -375,7 +410,7 @@ def main():
         'dtype': 'u64', 'data': 'synthetic',
         'config': {'workload': f'BASELINE config {CONFIG}: {N} nodes x {P} pods, 16 pod types (50% GPU/PCI), '
                                f'30% nodes pre-occupied, constant clock',
-                   'parallelism': f'node-sharded filter x{world} + one NCCL all-reduce + replicated sweep' if world > 1
+                   'parallelism': f'node-sharded filter x{world} + one NCCL all-gather + replicated sweep' if world > 1
                    else 'single GPU',
                    'l2': 'flushed between steps (256 MiB memset)', 'pods_placed': placed, 'pod_types': n_types},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -396,7 +431,33 @@ def main():
                              'latency of the dependent chain on one SM, not by HBM'},
         'clocks': clocks,
     }
+    # ---------------- side workloads (not the headline; a few solves each) -------------------
+    extra = {}
+    if world == 1 and not args.no_extra:
+        try:
+            r5, s5, p5, n5 = workload.make_workload(5)
+            extra['config5_262144x8192_1gpu'] = quick_value(Solver, r5, s5, p5, n5, device=local_rank)
+            del r5, p5
+            rw, sw, pw, nw = workload.make_workload(CONFIG, wild=True)
+            extra['heterogeneous_65536x4096'] = dict(quick_value(Solver, rw, sw, pw, nw, device=local_rank),
+                                                     note='1-4 NICs per NUMA node at 25/40/100G in any mix: hundreds of '
+                                                          'hardware classes, most outside the direct-path tables')
+            del rw
+            mv = now + 0.001 * np.arange(P)
+            extra['moving_clock_65536x4096'] = dict(quick_value(Solver, recs, speed, pods, mv, device=local_rank),
+                                                    note='per-pod clocks: the general one-warp sweep with busy-list upkeep')
+        except Exception as e:
+            extra['error'] = str(e)[:200]
+    total_ms = float(np.mean(phase['total_ms']))
+    line['amdahl'] = {'filter_share': filter_ms / total_ms,
+                      'limit_if_filter_were_free': total_ms / max(total_ms - filter_ms, 1e-9),
+                      'note': 'only the filter shards over GPUs; the sweep (sequential first-fit) is replicated'}
+    if extra:
+        line['extra'] = extra
     if cpu is not None:
+        pyb = python_reference_baseline(recs, speed, pods, now)
+        if pyb is not None:
+            cpu['python_reference'] = pyb
         line['cpu_baseline'] = cpu
     if parity_vs_oracle is not None:
         line['parity_vs_oracle'] = parity_vs_oracle

@@ -295,7 +295,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
         SweepArgs sa;
         memset(&sa, 0, sizeof(sa));
         const size_t smem = (size_t)SMEMO_SLOTS * 16 + (size_t)DMEMO_SLOTS * 48 + (size_t)DCACHE_SLOTS * 36 + 16 +
-                            (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16 + 4096;
+                            (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16 + ((MAPT_BYTES + 15) & ~15) + 4096;
         sweep_kernel<true><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
         sweep_kernel<false><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);
         CK(cudaGetLastError());

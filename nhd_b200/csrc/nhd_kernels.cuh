@@ -947,8 +947,10 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     const int k = lane >> 4, S = lane & 15;
     const uint32_t mk = k ? m1 : m0;
     const uint32_t inuse = du.d.nic_inuse;
-    bool feas = false;
+    bool feas = false, s_miss = false;
     uint32_t r_idx = 0, r_li = 0;                      /* one byte per member of S, in group order */
+    uint4* se = cx.spmemo;
+    uint4 s_new = make_uint4(0, 0, 0, 0);
     if (S <= gmask) {
       /* the sub-problem depends on (type, S) and on the NICs of this NUMA node only: their count,
        * speeds and which are taken, in NUMA-local order — memo keyed by exactly that */
@@ -964,15 +966,24 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
       const uint32_t skey2 = wide ? (uint32_t)du.d.hw_class : (k ? spk1 : spk0);
       uint32_t sh = skey * 0x9E3779B1u ^ inuse_k * 0x85EBCA77u ^ skey2 * 0xC2B2AE3Du;
       sh ^= sh >> 15;
-      uint4* se = &cx.spmemo[sh & cx.spmemo_mask];
+      se = &cx.spmemo[sh & cx.spmemo_mask];
       const uint4 sv = *se;
       if (sv.x == skey && sv.y == inuse_k && sv.z == skey2) {
         feas = (sv.w >> 31) != 0; r_idx = sv.w & 0x7FFFFFFFu;
       } else {
         const uint32_t rr = nic_sub_solve(a.cap, t, S, mk, inuse, sp0, sp1);
         feas = (rr >> 31) != 0; r_idx = rr & 0x7FFFFFFFu;
-        *se = make_uint4(skey, inuse_k, skey2, r_idx | (feas ? 0x80000000u : 0u));
+        s_new = make_uint4(skey, inuse_k, skey2, r_idx | (feas ? 0x80000000u : 0u));
+        s_miss = true;
       }
+    }
+    {
+        /* a miss is stored once every lane has read the table, one lane at a time (lanes may share a slot) */
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, s_miss);
+        for (uint32_t m = mm; m; m &= m - 1) {
+            if (lane == ctz32(m)) *se = s_new;
+            __syncwarp();
+        }
     }
     PROF2(1);   /* per-NUMA sub-problems */
     /* ---- tuple lanes combine their two halves ---- */
@@ -1081,6 +1092,7 @@ __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepC
     }
     pm = pm2;
     }
+    __syncwarp();                                        /* every lane has read the entry */
     if (memoable && cx.lane == 0) {
         eu.e.a = key; eu.e.nic_inuse = du.d.nic_inuse;
         eu.e.state = (uint8_t)state; eu.e.ms = (uint8_t)pm.ms; eu.e.ncl = (uint8_t)pk.ncl; eu.e.ng = (uint8_t)pk.ng;
@@ -1995,7 +2007,11 @@ sweep_kernel(const SweepArgs a)
                 }
                 c = found;
             }
-            if (c != c_in) cursors[ti * 3 + pass] = c;
+            if (c != c_in) {
+                __syncwarp();
+                if (lane == 0) cursors[ti * 3 + pass] = c;
+                __syncwarp();
+            }
             if (c >= W) continue;
             /* (2) candidates from there on, skipping busy nodes for GPU pods */
             int cb = c;
@@ -2017,7 +2033,11 @@ sweep_kernel(const SweepArgs a)
                         if (nz) { found = base + ctz32(nz); break; }
                     }
                     cb = found;
-                    if (skip_busy && !multi) cursors[ti * 3 + 2] = cb;
+                    if (skip_busy && !multi) {
+                        __syncwarp();
+                        if (lane == 0) cursors[ti * 3 + 2] = cb;
+                        __syncwarp();
+                    }
                     continue;
                 }
                 const int node = cb * 64 + ctz64(word);

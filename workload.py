@@ -42,8 +42,11 @@ def _range_mask(lo, hi):
     return np.where(b > a, low_bits(b) & ~low_bits(a), np.uint64(0))
 
 
-def make_cluster(config: int, n_nodes: int = None, seed: int = None):
-    """Returns (records[NODE_DTYPE], speed_table[16]) for a BASELINE config."""
+def make_cluster(config: int, n_nodes: int = None, seed: int = None, wild: bool = False):
+    """Returns (records[NODE_DTYPE], speed_table[16]) for a BASELINE config.
+    ``wild``: a heterogeneous variant of configs 1-4 (sensitivity runs, not a BASELINE config): one to four NICs per
+    NUMA node at 25 / 40 / 100 G in any mix — hundreds of hardware classes and more NIC signatures than the sweep's
+    direct-path tables hold, so a large share of the decisions takes the general path."""
     N = CONFIGS[config][0] if n_nodes is None else n_nodes
     rng = np.random.default_rng(SEED0 + config if seed is None else seed)
     recs = np.zeros(N, dtype=wire.NODE_DTYPE)
@@ -87,6 +90,24 @@ def make_cluster(config: int, n_nodes: int = None, seed: int = None):
             pick = rng.integers(0, N_GROUP_NAMES, size=N).astype(np.uint64)
             gm |= np.where(j < n_names, np.uint64(1) << pick, np.uint64(0))
         recs['group_mask'] = gm
+    elif wild:
+        speeds = [100.0, 40.0, 25.0]
+        n0 = rng.integers(1, 5, size=N)
+        n1 = rng.integers(1, 5, size=N)
+        recs['n_nics'] = n0 + n1
+        recs['nic_numa_mask'][:, 0] = (1 << n0) - 1
+        recs['nic_numa_mask'][:, 1] = ((1 << n1) - 1) << n0
+        sw = np.zeros(N, dtype=np.uint64)
+        sp = np.zeros(N, dtype=np.uint64)
+        for j in range(8):
+            on1 = j >= n0                                     # NIC j sits on NUMA 1 (list order numa0.., numa1..)
+            live = j < n0 + n1
+            swj = np.where(on1, 2 + ((j - n0) % 2), j % 2).astype(np.uint64)
+            sw |= np.where(live, swj << np.uint64(4 * j), np.uint64(0))
+            sp |= np.where(live, rng.integers(0, 3, size=N).astype(np.uint64) << np.uint64(4 * j), np.uint64(0))
+        recs['nic_sw'][:, 0] = sw
+        recs['nic_speed'][:, 0] = sp
+        recs['group_mask'] = 1
     else:
         # one or two 100G NICs per NUMA node, list order numa0.., numa1..; NIC j of NUMA k on switch 2k + j
         speeds = [100.0]
@@ -173,7 +194,7 @@ def make_pods(config: int, n_pods: int = None, seed: int = None):
     return pods, now
 
 
-def make_workload(config: int, n_nodes: int = None, n_pods: int = None):
-    recs, speed = make_cluster(config, n_nodes)
+def make_workload(config: int, n_nodes: int = None, n_pods: int = None, wild: bool = False):
+    recs, speed = make_cluster(config, n_nodes, wild=wild)
     pods, now = make_pods(config, n_pods)
     return recs, speed, pods, now

@@ -294,6 +294,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
          * real batch instead of inside it (a first sweep used to take tens of milliseconds) */
         SweepArgs sa;
         memset(&sa, 0, sizeof(sa));
+        sa.prof = h->d_prof;                               /* (profile builds flush their counters) */
         const size_t smem = (size_t)SMEMO_SLOTS * 16 + (size_t)DMEMO_SLOTS * 48 + (size_t)DCACHE_SLOTS * 36 + 16 +
                             (size_t)CLSNIC_SLOTS * 48 + (size_t)SPMEMO_SLOTS * 16 + ((MAPT_BYTES + 15) & ~15) + 4096;
         sweep_kernel<true><<<1, SWEEP_THREADS, smem, h->stream>>>(sa);

@@ -980,6 +980,7 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     {
         /* a miss is stored once every lane has read the table, one lane at a time (lanes may share a slot) */
         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, s_miss);
+        __syncwarp();
         for (uint32_t m = mm; m; m &= m - 1) {
             if (lane == ctz32(m)) *se = s_new;
             __syncwarp();

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Developer script for `gpurun --gpus N`: multi-rank parity against the oracle, then the bench at 1 and N ranks.
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_multirank.py -m gpu -x -q > gpurun_out/pytest_multirank_$N.log 2>&1
+timeout 600 python bench.py --no-extra > gpurun_out/bench_n1.log 2>&1
+for n in 2 4 8; do
+  if [ $n -le $N ]; then
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n > gpurun_out/bench_n$n.log 2>&1
+  fi
+done
+tail -n 5 gpurun_out/pytest_multirank_$N.log; for f in gpurun_out/bench_n*.log; do tail -n 1 $f | cut -c1-700; echo; done

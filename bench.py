@@ -280,6 +280,8 @@ def main():
         solver.sync()
         flush.zero_()                      # L2 flush between timed iterations
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                 # ranks enter the step together (the collective would otherwise time their skew)
         solver.solve_staged()
         solver.sync()
         t = solver.timing()

@@ -23,13 +23,14 @@ def main():
     rank, local, world = int(os.environ['RANK']), int(os.environ['LOCAL_RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    nccl_id = bytes(idt.cpu().numpy().tobytes())
     failures = []
     for cfg, n_nodes, n_pods in ((3, 4096, 384), (5, 8192, 512), (4, None, None)):
+        # one communicator per solver handle: a fresh NCCL unique id each time (they are single-use)
+        idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
         recs, speed, pods, now = workload.make_workload(cfg, n_nodes, n_pods)
         s = Solver(speed, device=local, rank=rank, world_size=world, nccl_id=nccl_id)
         try:

@@ -409,10 +409,15 @@ extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx
     if (!h || n < 0 || (n > 0 && (!idx || !recs))) return NHD_ERR_INVALID;
     if (!h->loaded) return fail(h, NHD_ERR_STATE, "nhd_update_nodes before nhd_load_nodes");
     CK(cudaSetDevice(h->params.device));
-    for (int i = 0; i < n; i++) {
-        if (idx[i] < 0 || idx[i] >= h->n_nodes) return fail(h, NHD_ERR_INVALID, "node index %d out of range", idx[i]);
-        int32_t v = nhd_validate_node(&recs[i]);      /* before anything is written: an update must not half-apply */
-        if (v != NHD_OK) return fail(h, v, "update %d: record rejected", i);
+    {
+        std::vector<uint8_t> seen((size_t)h->n_nodes, 0);            /* the device applies the records in parallel: one per node */
+        for (int i = 0; i < n; i++) {
+            if (idx[i] < 0 || idx[i] >= h->n_nodes) return fail(h, NHD_ERR_INVALID, "node index %d out of range", idx[i]);
+            if (seen[idx[i]]) return fail(h, NHD_ERR_INVALID, "node index %d appears twice in one update", idx[i]);
+            seen[idx[i]] = 1;
+            int32_t v = nhd_validate_node(&recs[i]);      /* before anything is written: an update must not half-apply */
+            if (v != NHD_OK) return fail(h, v, "update %d: record rejected", i);
+        }
     }
     if (n == 0) return NHD_OK;
     int mx = 1;
@@ -424,7 +429,7 @@ extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx
 extern "C" int32_t nhd_read_nodes(nhd_handle* h, int32_t first, int32_t n, nhd_node_rec* out)
 {
     if (!h || first < 0 || n < 0 || (n > 0 && !out)) return NHD_ERR_INVALID;
-    if (!h->loaded || first + n > h->n_nodes) return fail(h, NHD_ERR_STATE, "range outside the loaded cluster");
+    if (!h->loaded || (long long)first + (long long)n > (long long)h->n_nodes) return fail(h, NHD_ERR_STATE, "range outside the loaded cluster");
     if (n == 0) return NHD_OK;
     CK(cudaSetDevice(h->params.device));
     const size_t bytes = (size_t)n * sizeof(nhd_node_rec);

@@ -359,9 +359,11 @@ __global__ void unpack_slots_kernel(const uint4* __restrict__ xchg, int ws, int 
 #define PROF2_DECL long long p2_t0 = clock64();
 #define PROF2(i) do { long long t_ = clock64(); if (cx.lane == 0) atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - p2_t0)); p2_t0 = t_; } while (0)
 #define PROF_FLUSH(buf) do { if (lane == 0) for (int i_ = 0; i_ < 16; i_++) { (buf)[i_] = (unsigned long long)prof_acc[i_]; (buf)[32 + i_] = (unsigned long long)prof_cnt[i_]; } } while (0)
+#define PROF_ADD(i, n) do { if (cx.lane == 0) atomicAdd(&a.prof[48 + (i)], (unsigned long long)(n)); } while (0)
 #define PROFL_DECL long long pl_t0 = clock64();
 #define PROFL(i) do { long long t_ = clock64(); atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - pl_t0)); atomicAdd(&a.prof[48 + (i)], 1ULL); pl_t0 = clock64(); } while (0)
 #else
+#define PROF_ADD(i, n)
 #define PROFL_DECL
 #define PROFL(i)
 #define PROF2_DECL
@@ -1435,6 +1437,8 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
         sl.w &= ldw<SMEM_BITMAPS>(&F[sl.c]);
     for (;;) {
         if (__any_sync(0xFFFFFFFFu, need)) {
+            PROF_ADD(0, 1);                                  /* evaluation passes */
+            PROF_ADD(1, __popc(__ballot_sync(0xFFFFFFFFu, need)));      /* lanes evaluating */
             uint32_t dec = 0, iu2 = 0;
             DynU da;
             const bool feas = fast_eval(ft, tl, ty, cur, cax, now, dec, da, iu2);
@@ -1454,6 +1458,8 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
             need = false;
         }
         if (!__any_sync(0xFFFFFFFFu, dead)) break;
+        PROF_ADD(2, 1);                                      /* passes with lanes moving on */
+        PROF_ADD(3, __popc(__ballot_sync(0xFFFFFFFFu, dead)));          /* lanes moving on */
         if (dead) {
             /* next candidate of the GPU-less pass (Matcher.py:412-416) */
             if (sl.c < W)

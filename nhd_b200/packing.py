@@ -159,7 +159,8 @@ def pack_node(node, layout: ClusterLayout, out=None):
 
 def stub_record(out):
     """Inactive place-holder record: keeps a node's position in the order, is never a candidate."""
-    out[()] = np.zeros((), dtype=wire.NODE_DTYPE)
+    for name in wire.NODE_DTYPE.names:                  # `out` may be a record of an array (numpy.void): field by field
+        out[name] = 0
     out['n_numa'] = 1
     out['phys_cores'] = 1
     return out

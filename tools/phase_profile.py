@@ -19,7 +19,6 @@ print(f'cfg{cfg}: sweep {t["sweep_ms"]:.3f} ms, {len(pods)} pods, warp-0 cycles 
 for i, n in enumerate(names):
     print(f'  {n:34s} cycles {int(c[i]):10d} ({100*int(c[i])/max(tot,1):5.1f}%)  count {int(c[32+i]):7d}  avg {int(c[i])/max(int(c[32+i]),1):8.1f}')
 print('  stale candidates (ordinary path)', int(c[32 + 8]), ' direct commits', int(c[32 + 13]), ' deferred GPU commits', int(c[32 + 12]))
-# lane-level, inside the refresh (summed over lanes = pod types)
-for i, n in enumerate(['refresh: candidate scan', 'refresh: summary load', 'refresh: evaluation', 'refresh: slot store']):
-    print(f'  {n:34s} lane-cycles {int(c[16+i]):10d}  count {int(c[48+i]):7d}  avg {int(c[16+i])/max(int(c[48+i]),1):8.1f}')
+print('  refresh: evaluation passes', int(c[48]), ' lanes evaluating', int(c[49]), ' passes with lanes moving on', int(c[50]),
+      ' lanes moving on', int(c[51]))
 s.close()

@@ -99,6 +99,7 @@ struct nhd_handle {
     int* d_vresult = nullptr;
     uint64_t* d_memo = nullptr;
     uint8_t* d_xchg = nullptr;  size_t xchg_cap = 0;     /* node-sharded ranks: one slot per rank (summaries + bitmap columns) */
+    uint8_t* d_ftab = nullptr;            /* direct-path tables of the staged batch's pod types */
     uint8_t* d_mapt = nullptr;            /* GetNumaGroupIdx table of the direct path */
     uint32_t* d_sigs = nullptr;           /* per-NUMA NIC signatures */
     ClsFast* d_cls_fast = nullptr;        /* per hardware class */
@@ -224,7 +225,7 @@ extern "C" int32_t nhd_destroy(nhd_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_nodes); cudaFree(h->d_snapshot); cudaFree(h->d_stage); cudaFree(h->d_idx);
     cudaFree(h->d_types); cudaFree(h->d_pod_type); cudaFree(h->d_now); cudaFree(h->d_out);
-    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_mapt); cudaFree(h->d_xchg); cudaFree(h->d_sigs); cudaFree(h->d_cls_fast); 
+    cudaFree(h->d_bitmaps); cudaFree(h->d_cursors); cudaFree(h->d_busy_list); cudaFree(h->d_memo); cudaFree(h->d_dyn); cudaFree(h->d_class); cudaFree(h->d_class_slots); cudaFree(h->d_mapt); cudaFree(h->d_ftab); cudaFree(h->d_xchg); cudaFree(h->d_sigs); cudaFree(h->d_cls_fast); 
 #ifdef NHD_CHECKS
     cudaFreeHost(h->d_prof);
 #else
@@ -279,6 +280,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     CK(cudaMalloc((void**)&h->d_class_slots, (size_t)CLASS_SLOTS * sizeof(ClassSlot)));
     CK(cudaMemsetAsync(h->d_class_slots, 0, (size_t)CLASS_SLOTS * sizeof(ClassSlot), h->stream));
     CK(cudaMalloc((void**)&h->d_mapt, (size_t)((MAPT_BYTES + 15) & ~15)));
+    CK(cudaMalloc((void**)&h->d_ftab, ftab_bytes(FAST_MAX_TYPES)));
     CK(cudaMalloc((void**)&h->d_sigs, (size_t)FAST_NSIG * 4));
     CK(cudaMemsetAsync(h->d_sigs, 0, (size_t)FAST_NSIG * 4, h->stream));
     CK(cudaMalloc((void**)&h->d_cls_fast, (size_t)CLASS_SLOTS * sizeof(ClsFast)));
@@ -619,8 +621,19 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     const int super_hi = sharded ? std::min(super_lo + S, h->n_super) : h->n_super;
     const size_t slot_bytes = (size_t)S * 32 * (SUPER_NODES + rows);
     if (sharded) CK(grow_dev(h->d_xchg, h->xchg_cap, slot_bytes * ws));
+    const bool have_ftab = T > 0 && T <= FAST_MAX_TYPES;
+    if (h->n_pods > 0 && have_ftab) {
+        /* 0. the direct-path tables of this batch's pod types (filter and sweep both read them) */
+        TablesArgs ta;
+        ta.types = h->d_types; ta.n_types = T; ta.sigs = h->d_sigs; ta.out = h->d_ftab;
+        memcpy(ta.cap, h->cap, sizeof(ta.cap));
+        fast_tables_kernel<<<T, 256, 0, h->stream>>>(ta);
+        CK(cudaGetLastError());
+        launches++;
+    }
     if (h->n_pods > 0 && super_hi > super_lo) {
         FilterArgs fa;
+        fa.ftab = have_ftab ? h->d_ftab : nullptr; fa.mapt = h->d_mapt; fa.cls = h->d_cls_fast;
         fa.nodes = h->d_nodes; fa.types = h->d_types; fa.n_types = T; fa.n_nodes = h->n_nodes;
         fa.super_lo = super_lo; fa.super_hi = super_hi;
         if (sharded) {
@@ -676,6 +689,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
         sa.mapt = h->d_mapt; sa.sigs = h->d_sigs; sa.cls_fast = h->d_cls_fast;
+        sa.ftab = (T > 0 && T <= FAST_MAX_TYPES) ? h->d_ftab : nullptr;
         sa.min_busy = h->params.min_busy_secs;
         memcpy(sa.cap, h->cap, sizeof(sa.cap));
         /* shared memory: memo front | pod types | cursors | (bitmaps when they fit) */

@@ -177,6 +177,187 @@ __global__ void classify_verify_kernel(const uint8_t* __restrict__ nodes, const 
     if (!same) class_id[node] = NHD_NO_CLASS;
 }
 
+/* ------------------------------------------------------------------ direct-path tables */
+
+#define NHD_SLOT_SLOW   0
+#define NHD_SLOT_FAST   1
+#define NHD_SLOT_DEFER  2
+#define NHD_SLOT_NONE   3
+
+#define NHD_PENDING_FAST 101          /* internal binding status: node and packed mapping known, header not formatted yet */
+
+constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
+constexpr int FAST_NSIG = 4;          /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
+constexpr int MAPT_BYTES = 4096 + 64;
+
+struct ClsFast {             /* per hardware class, 16 bytes */
+    uint32_t li0, li1;       /* byte j = index in Node.nics of the j-th NIC of NUMA 0 / 1 */
+    uint8_t sig0, sig1;      /* signature ids of the two NUMA nodes */
+    uint8_t n0, n1;          /* NICs per NUMA node */
+    uint32_t ok;             /* 1: covered by the direct path */
+};
+
+struct TyFast {              /* per pod type, 16 bytes */
+    uint8_t G, n_misc, misc_smt, nic_groups;
+    uint8_t direct;          /* CPU-only, NUMA mode, G <= 2 */
+    uint8_t pad_[3];
+    int32_t hugepages_gb;
+    uint32_t pad2_;
+};
+
+struct FastTables {
+    const uint8_t* tb;       /* [T][2][2][64] */
+    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p */
+    const uint32_t* sub1;
+    const uint8_t* mapt;     /* MAPT_BYTES */
+    const uint16_t* gd;      /* [T][2][4] */
+    const TyFast* ty;        /* [T] */
+    const ClsFast* cls;      /* global, [CLASS_SLOTS] */
+};
+
+/* GetNumaGroupIdx for CPU-only pods on 2-NUMA nodes as a table (every GPU tuple passes the GPU stage):
+ * [0, 4096): G = 2, index = CPU mask (8 bits, q = 2p + m) << 4 | NIC mask (4 bits, p); [4096, 4160): G = 1,
+ * index = CPU mask (4 bits) << 2 | NIC mask (2 bits).  Value: 0x80 | tuple | misc NUMA << 2, or 0. */
+__global__ void mapt_kernel(uint8_t* mapt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MAPT_BYTES) return;
+    const int G = i < 4096 ? 2 : 1;
+    const int j = i < 4096 ? i : i - 4096;
+    TMask ma = tm_zero(), mb = tm_zero(), mc = tm_zero();
+    ma.w[0] = (1u << (1 << G)) - 1;
+    mb.w[0] = G == 2 ? (uint32_t)(j >> 4) : (uint32_t)(j >> 2);
+    mc.w[0] = G == 2 ? (uint32_t)(j & 15) : (uint32_t)(j & 3);
+    int ps = 0, ms = 0;
+    mapt[i] = choose_mapping(2, G, ma, mb, mc, &ps, &ms) ? (uint8_t)(0x80 | ps | (ms << 2)) : (uint8_t)0;
+}
+
+/*
+ * Per hardware class (ClassSlot key = the static description of its nodes): the NIC list indices of each NUMA
+ * node in NodeNic.idx order and the signature ids (NIC count + speed classes in that order) of the two NUMA
+ * nodes.  Runs after classification (load / update); signatures are only ever added.
+ */
+__global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cls, uint32_t* sigs)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= CLASS_SLOTS) return;
+    ClsFast cf;
+    cf.li0 = cf.li1 = 0; cf.sig0 = cf.sig1 = 0; cf.n0 = cf.n1 = 0; cf.ok = 0;
+    if (slots[s].hash != 0ULL) {
+        const uint32_t* key = slots[s].key;
+        const int n_numa = (int)((key[16] >> 16) & 0xFF);
+        const uint32_t m[2] = {key[4], key[5]};
+        const unsigned long long sp0 = (unsigned long long)key[12] | ((unsigned long long)key[13] << 32);
+        const unsigned long long sp1 = (unsigned long long)key[14] | ((unsigned long long)key[15] << 32);
+        const int n0 = popc32(m[0]), n1 = popc32(m[1]);
+        bool ok = n_numa == 2 && n0 <= 4 && n1 <= 4;
+        uint32_t li[2] = {0, 0};
+        uint8_t sg[2] = {0, 0};
+        for (int k = 0; k < 2 && ok; k++) {
+            uint32_t sv = 0x80000000u | (uint32_t)(k ? n1 : n0);
+            int j = 0;
+            for (uint32_t f = m[k]; f; f &= f - 1, j++) {
+                const int l = ctz32(f);
+                li[k] |= (uint32_t)l << (8 * j);
+                sv |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 + 4 * j);
+            }
+            int id = -1;
+            for (int q = 0; q < FAST_NSIG; q++) {
+                const uint32_t old = atomicCAS(&sigs[q], 0u, sv);
+                if (old == 0u || old == sv) { id = q; break; }
+            }
+            if (id < 0) ok = false; else sg[k] = (uint8_t)id;
+        }
+        if (ok) { cf.li0 = li[0]; cf.li1 = li[1]; cf.sig0 = sg[0]; cf.sig1 = sg[1]; cf.n0 = (uint8_t)n0; cf.n1 = (uint8_t)n1; cf.ok = 1; }
+    }
+    cls[s] = cf;
+}
+
+/* byte offsets of the direct-path tables of T pod types inside one buffer (global: fast_tables_kernel writes it,
+ * the filter reads it through L1, the sweep copies it to shared memory): TB | SUB0 | SUB1 | GD | TyFast */
+__host__ __device__ __forceinline__ size_t ftab_off_tb(int) { return 0; }
+__host__ __device__ __forceinline__ size_t ftab_off_sub0(int T) { return (size_t)T * 256; }
+__host__ __device__ __forceinline__ size_t ftab_off_sub1(int T) { return (size_t)T * 512; }
+__host__ __device__ __forceinline__ size_t ftab_off_gd(int T) { return (size_t)T * 768; }
+__host__ __device__ __forceinline__ size_t ftab_off_ty(int T) { return (size_t)T * 784; }
+__host__ __device__ __forceinline__ size_t ftab_bytes(int T) { return (size_t)T * 800; }
+
+__device__ __noinline__ uint32_t nic_sub_solve(const double* cap, const PodType& t, int S, uint32_t mk, uint32_t inuse,
+                                               unsigned long long sp0, unsigned long long sp1);
+
+struct TablesArgs {
+    const PodType* types;
+    int n_types;
+    const uint32_t* sigs;
+    uint8_t* out;
+    double cap[NHD_MAX_SPEED_CLASSES];
+};
+
+/* the direct-path tables of a batch's pod types (one CTA per type, 256 threads): see the comment above */
+__global__ void fast_tables_kernel(const TablesArgs a)
+{
+    const int T = a.n_types, tt = blockIdx.x, i = threadIdx.x;
+    if (tt >= T) return;
+    const PodType& ty = a.types[tt];
+    const bool direct = ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2;
+    {
+        /* CPU stage per socket (Matcher.py:203-212 with K = 2): which tuples q = 2p + m fit c free cores on NUMA k */
+        const int f = (i >> 7) & 1, k = (i >> 6) & 1, c = i & 63;
+        const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+        const int L = ty.G + 1;
+        uint32_t m = 0;
+        for (int q = 0; q < (1 << L) && L <= 3; q++) {
+            int n = 0;
+            for (int g = 0; g < L; g++) if (((q >> (L - 1 - g)) & 1) == k) n += cl[g];
+            if (n <= c || (c == 63 && n <= 255)) m |= 1u << q;       /* the free count saturates at 63 in the index */
+        }
+        a.out[ftab_off_tb(T) + (size_t)tt * 256 + i] = (uint8_t)m;
+    }
+    if (i < FAST_NSIG * 16) {
+        /* NIC stage per NUMA node (Matcher.py:242-268): per (type, NIC signature, NICs in use) and tuple p, whether
+         * the groups p puts on NUMA 0 (SUB0) / NUMA 1 (SUB1) get NICs there, and which */
+        const int sg = i >> 4, iu = i & 15;
+        const uint32_t sv = a.sigs[sg];
+        uint32_t w0 = 0, w1 = 0;
+        const int n_k = (int)(sv & 15);
+        if ((sv >> 31) && direct && iu < (1 << n_k)) {
+            const uint32_t mk = (1u << n_k) - 1;
+            const unsigned long long sp = (sv >> 4) & 0xFFFFu;
+            const int G = ty.G, gmask = (1 << G) - 1;
+            for (int p = 0; p <= gmask; p++) {
+                const int S1 = (int)(__brev((unsigned)p) >> (32 - G)), S0 = gmask & ~S1;
+                const uint32_t r0 = nic_sub_solve(a.cap, ty, S0, mk, (uint32_t)iu, sp, 0ULL);
+                const uint32_t r1 = nic_sub_solve(a.cap, ty, S1, mk, (uint32_t)iu, sp, 0ULL);
+                w0 |= (((r0 >> 31) << 7) | (r0 & 3) | (((r0 >> 8) & 3) << 2)) << (8 * p);
+                w1 |= (((r1 >> 31) << 7) | (r1 & 3) | (((r1 >> 8) & 3) << 2)) << (8 * p);
+            }
+        }
+        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub0(T))[tt * FAST_NSIG * 16 + i] = w0;
+        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub1(T))[tt * FAST_NSIG * 16 + i] = w1;
+    }
+    if (i < 8) {
+        /* cores the groups of tuple p take from each socket */
+        const int f = (i >> 2) & 1, p = i & 3;
+        const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+        int n0 = 0, n1 = 0;
+        for (int g = 0; g < ty.G && ty.G <= 2; g++) { if ((p >> (ty.G - 1 - g)) & 1) n1 += cl[g]; else n0 += cl[g]; }
+        reinterpret_cast<uint16_t*>(a.out + ftab_off_gd(T))[tt * 8 + i] = (uint16_t)((n0 & 0xFF) | ((n1 & 0xFF) << 8));
+    }
+    if (i == 0) {
+        TyFast f;
+        f.G = ty.G; f.n_misc = ty.pod.n_misc; f.misc_smt = (ty.pod.flags & NHD_POD_MISC_SMT) ? 1 : 0; f.nic_groups = ty.nic_groups;
+        f.direct = direct ? 1 : 0;
+        f.pad_[0] = f.pad_[1] = f.pad_[2] = 0; f.hugepages_gb = ty.pod.hugepages_gb; f.pad2_ = 0;
+        reinterpret_cast<TyFast*>(a.out + ftab_off_ty(T))[tt] = f;
+    }
+}
+
+/* bit 7 of each byte of x -> bits 0..3 */
+__device__ __forceinline__ uint32_t gather_b7(uint32_t x)
+{
+    return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+}
+
 /* ------------------------------------------------------------------ TMA / mbarrier helpers */
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -223,6 +404,9 @@ struct FilterArgs {
     uint64_t names_used;         /* node-group names some pod of the batch asks for (0: gate folded into the types) */
     uint4* dyn;                  /* [window nodes][2]: NodeDyn summaries; entry 0 = node 64 * word_base */
     const uint16_t* class_id;    /* hardware class of every node */
+    const uint8_t* ftab;         /* direct-path tables (fast_tables_kernel) or null */
+    const uint8_t* mapt;
+    const ClsFast* cls;
     double now0;                 /* clock of the first pod, for the BUSY snapshot */
     double min_busy;
     double cap[NHD_MAX_SPEED_CLASSES];
@@ -288,18 +472,48 @@ filter_kernel(const FilterArgs a)
         const bool valid = node < a.n_nodes;
 
         /* per-node summary for the sweep */
+        union { NodeDyn d; uint4 q[2]; } du;
+        if (valid) { make_dyn(u.r, du.d); du.d.hw_class = a.class_id[node]; }
+        else { du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0]; }
         if (tch == 0) {
-            union { NodeDyn d; uint4 q[2]; } du;
-            if (valid) { make_dyn(u.r, du.d); du.d.hw_class = a.class_id[node]; }
-            else { du.q[0] = make_uint4(0, 0, 0, 0); du.q[1] = du.q[0]; }
             const size_t dn = (size_t)node - (size_t)a.word_base * 64;
             a.dyn[dn * 2] = du.q[0];
             a.dyn[dn * 2 + 1] = du.q[1];
         }
+        /* direct path (CPU-only NUMA-mode types with <= 2 groups on 2-NUMA nodes whose class the tables cover): the
+         * node's part of the table indices, once for all types.  Same tables and the same answer as the sweep's
+         * fast_eval: feasible <=> MAPT holds a mapping for (CPU mask, NIC mask) (Matcher.py:203-276, :349) */
+        bool shape_ok = false;
+        uint32_t d_i0 = 0, d_i1 = 0, d_c0 = 0, d_c1 = 0, d_smt = 0;
+        if (valid && a.ftab && u.r.n_numa == 2 && du.d.hw_class != NHD_NO_CLASS) {
+            const ClsFast cf = a.cls[du.d.hw_class];
+            if (cf.ok) {
+                shape_ok = true;
+                uint32_t iu0 = 0, iu1 = 0;
+                for (int j = 0; j < cf.n0; j++) iu0 |= ((u.r.nic_inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;
+                for (int j = 0; j < cf.n1; j++) iu1 |= ((u.r.nic_inuse >> ((cf.li1 >> (8 * j)) & 31)) & 1u) << j;
+                d_i0 = (uint32_t)cf.sig0 * 16 + iu0; d_i1 = (uint32_t)cf.sig1 * 16 + iu1;
+                d_c0 = du.d.fc[0] < 63 ? du.d.fc[0] : 63; d_c1 = du.d.fc[1] < 63 ? du.d.fc[1] : 63;
+                d_smt = rec_smt(u.r) ? 1 : 0;
+            }
+        }
+        const int T_ = a.n_types;
+        const uint8_t* f_tb = a.ftab;
+        const uint32_t* f_sub0 = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T_));
+        const uint32_t* f_sub1 = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T_));
+        const TyFast* f_ty = reinterpret_cast<const TyFast*>(a.ftab + ftab_off_ty(T_));
 
         const size_t w32 = ((size_t)node >> 5) - (size_t)a.word_base * 2;
         for (int t = tch; t < a.n_types; t += TS) {
-            bool f = valid && node_feasible(u.r, types[t], a.cap);
+            bool f;
+            if (shape_ok && f_ty[t].direct) {
+                const uint32_t w0 = __ldg(&f_sub0[t * FAST_NSIG * 16 + d_i0]), w1 = __ldg(&f_sub1[t * FAST_NSIG * 16 + d_i1]);
+                const uint32_t mC = gather_b7(w0 & w1);
+                const uint32_t mB = __ldg(&f_tb[((t * 2 + d_smt) * 2 + 0) * 64 + d_c0]) & __ldg(&f_tb[((t * 2 + d_smt) * 2 + 1) * 64 + d_c1]);
+                const uint32_t mi = f_ty[t].G == 2 ? ((mB << 4) | mC) : (4096 + (((mB & 15) << 2) | (mC & 3)));
+                f = node_gates(u.r, types[t]) && (__ldg(&a.mapt[mi]) & 0x80) != 0;
+            } else
+                f = valid && node_feasible(u.r, types[t], a.cap);
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, f);
             if (lane == 0) out32[(size_t)t * words32 + w32] = bal;
         }
@@ -416,6 +630,7 @@ struct SweepArgs {
     uint64_t* memo;              /* MEMO_SLOTS x 2 words (global, persists across batches) */
     const uint8_t* mapt;         /* MAPT_BYTES: GetNumaGroupIdx table of the direct path (mapt_kernel, once per handle) */
     const uint32_t* sigs;        /* FAST_NSIG per-NUMA NIC signatures (cls_fast_kernel, at load / update time) */
+    const uint8_t* ftab;         /* direct-path tables of the batch's pod types (fast_tables_kernel), null when T > FAST_MAX_TYPES */
     const struct ClsFast* cls_fast;   /* [CLASS_SLOTS] */
     unsigned long long* prof;    /* debug counters (NHD_PROFILE builds) */
     double min_busy;
@@ -1208,106 +1423,6 @@ __device__ __noinline__ void resolve_pending(const SweepArgs& a, const SweepCtx&
  * order: no inter-warp hand-off exists.  The binding of a directly decided pod is written out in packed form
  * (NHD_PENDING_FAST) and formatted by resolve_kernel, off the sequential chain.
  */
-#define NHD_SLOT_SLOW   0
-#define NHD_SLOT_FAST   1
-#define NHD_SLOT_DEFER  2
-#define NHD_SLOT_NONE   3
-
-#define NHD_PENDING_FAST 101          /* internal binding status: node and packed mapping known, header not formatted yet */
-
-constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
-constexpr int FAST_NSIG = 4;          /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
-constexpr int MAPT_BYTES = 4096 + 64;
-
-struct ClsFast {             /* per hardware class, 16 bytes */
-    uint32_t li0, li1;       /* byte j = index in Node.nics of the j-th NIC of NUMA 0 / 1 */
-    uint8_t sig0, sig1;      /* signature ids of the two NUMA nodes */
-    uint8_t n0, n1;          /* NICs per NUMA node */
-    uint32_t ok;             /* 1: covered by the direct path */
-};
-
-struct TyFast {              /* per pod type, 16 bytes */
-    uint8_t G, n_misc, misc_smt, nic_groups;
-    uint8_t direct;          /* CPU-only, NUMA mode, G <= 2 */
-    uint8_t pad_[3];
-    int32_t hugepages_gb;
-    uint32_t pad2_;
-};
-
-struct FastTables {
-    const uint8_t* tb;       /* [T][2][2][64] */
-    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p */
-    const uint32_t* sub1;
-    const uint8_t* mapt;     /* MAPT_BYTES */
-    const uint16_t* gd;      /* [T][2][4] */
-    const TyFast* ty;        /* [T] */
-    const ClsFast* cls;      /* global, [CLASS_SLOTS] */
-};
-
-/* GetNumaGroupIdx for CPU-only pods on 2-NUMA nodes as a table (every GPU tuple passes the GPU stage):
- * [0, 4096): G = 2, index = CPU mask (8 bits, q = 2p + m) << 4 | NIC mask (4 bits, p); [4096, 4160): G = 1,
- * index = CPU mask (4 bits) << 2 | NIC mask (2 bits).  Value: 0x80 | tuple | misc NUMA << 2, or 0. */
-__global__ void mapt_kernel(uint8_t* mapt)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= MAPT_BYTES) return;
-    const int G = i < 4096 ? 2 : 1;
-    const int j = i < 4096 ? i : i - 4096;
-    TMask ma = tm_zero(), mb = tm_zero(), mc = tm_zero();
-    ma.w[0] = (1u << (1 << G)) - 1;
-    mb.w[0] = G == 2 ? (uint32_t)(j >> 4) : (uint32_t)(j >> 2);
-    mc.w[0] = G == 2 ? (uint32_t)(j & 15) : (uint32_t)(j & 3);
-    int ps = 0, ms = 0;
-    mapt[i] = choose_mapping(2, G, ma, mb, mc, &ps, &ms) ? (uint8_t)(0x80 | ps | (ms << 2)) : (uint8_t)0;
-}
-
-/*
- * Per hardware class (ClassSlot key = the static description of its nodes): the NIC list indices of each NUMA
- * node in NodeNic.idx order and the signature ids (NIC count + speed classes in that order) of the two NUMA
- * nodes.  Runs after classification (load / update); signatures are only ever added.
- */
-__global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cls, uint32_t* sigs)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= CLASS_SLOTS) return;
-    ClsFast cf;
-    cf.li0 = cf.li1 = 0; cf.sig0 = cf.sig1 = 0; cf.n0 = cf.n1 = 0; cf.ok = 0;
-    if (slots[s].hash != 0ULL) {
-        const uint32_t* key = slots[s].key;
-        const int n_numa = (int)((key[16] >> 16) & 0xFF);
-        const uint32_t m[2] = {key[4], key[5]};
-        const unsigned long long sp0 = (unsigned long long)key[12] | ((unsigned long long)key[13] << 32);
-        const unsigned long long sp1 = (unsigned long long)key[14] | ((unsigned long long)key[15] << 32);
-        const int n0 = popc32(m[0]), n1 = popc32(m[1]);
-        bool ok = n_numa == 2 && n0 <= 4 && n1 <= 4;
-        uint32_t li[2] = {0, 0};
-        uint8_t sg[2] = {0, 0};
-        for (int k = 0; k < 2 && ok; k++) {
-            uint32_t sv = 0x80000000u | (uint32_t)(k ? n1 : n0);
-            int j = 0;
-            for (uint32_t f = m[k]; f; f &= f - 1, j++) {
-                const int l = ctz32(f);
-                li[k] |= (uint32_t)l << (8 * j);
-                sv |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 + 4 * j);
-            }
-            int id = -1;
-            for (int q = 0; q < FAST_NSIG; q++) {
-                const uint32_t old = atomicCAS(&sigs[q], 0u, sv);
-                if (old == 0u || old == sv) { id = q; break; }
-            }
-            if (id < 0) ok = false; else sg[k] = (uint8_t)id;
-        }
-        if (ok) { cf.li0 = li[0]; cf.li1 = li[1]; cf.sig0 = sg[0]; cf.sig1 = sg[1]; cf.n0 = (uint8_t)n0; cf.n1 = (uint8_t)n1; cf.ok = 1; }
-    }
-    cls[s] = cf;
-}
-
-/* bit 7 of each byte of x -> bits 0..3 */
-__device__ __forceinline__ uint32_t gather_b7(uint32_t x)
-{
-    return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-}
-
 /* what a lane knows about the node it evaluates besides the summary: the NICs in use in NodeNic.idx order
  * (NUMA 0 in bits 0-3, NUMA 1 in bits 4-7) and the class entry (li0, li1, sig0 | sig1 << 8 | n0 << 16 | n1 << 24) */
 struct NodeAux { uint32_t iu, li0, li1, sig; };
@@ -1577,63 +1692,14 @@ sweep_kernel(const SweepArgs a)
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) misc[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
-    const bool fast = fast_cap && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
+    const bool fast = fast_cap && a.ftab != nullptr && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
     if (fast) {
         for (int i = tid; i < (MAPT_BYTES + 15) / 16; i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_mapt)[i] = reinterpret_cast<const uint4*>(a.mapt)[i];
-        for (int tt = tid; tt < T; tt += SWEEP_THREADS) {
-            const PodType& ty = a.types[tt];
-            TyFast f;
-            f.G = ty.G; f.n_misc = ty.pod.n_misc; f.misc_smt = (ty.pod.flags & NHD_POD_MISC_SMT) ? 1 : 0; f.nic_groups = ty.nic_groups;
-            f.direct = (ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2) ? 1 : 0;
-            f.pad_[0] = f.pad_[1] = f.pad_[2] = 0; f.hugepages_gb = ty.pod.hugepages_gb; f.pad2_ = 0;
-            s_ty[tt] = f;
-        }
-        /* CPU stage per socket (Matcher.py:203-212 with K = 2): which tuples q = 2p + m fit c free cores on NUMA k */
-        for (int i = tid; i < T * 256; i += SWEEP_THREADS) {
-            const int tt = i >> 8, f = (i >> 7) & 1, k = (i >> 6) & 1, c = i & 63;
-            const PodType& ty = a.types[tt];
-            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
-            const int L = ty.G + 1;
-            uint32_t m = 0;
-            for (int q = 0; q < (1 << L) && L <= 3; q++) {
-                int n = 0;
-                for (int g = 0; g < L; g++) if (((q >> (L - 1 - g)) & 1) == k) n += cl[g];
-                if (n <= c || (c == 63 && n <= 255)) m |= 1u << q;       /* the free count saturates at 63 in the index */
-            }
-            s_tb[i] = (uint8_t)m;
-        }
-        /* cores the groups of tuple p take from each socket */
-        for (int i = tid; i < T * 8; i += SWEEP_THREADS) {
-            const int tt = i >> 3, f = (i >> 2) & 1, p = i & 3;
-            const PodType& ty = a.types[tt];
-            const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
-            int n0 = 0, n1 = 0;
-            for (int g = 0; g < ty.G && ty.G <= 2; g++) { if ((p >> (ty.G - 1 - g)) & 1) n1 += cl[g]; else n0 += cl[g]; }
-            s_gd[i] = (uint16_t)((n0 & 0xFF) | ((n1 & 0xFF) << 8));
-        }
-        /* NIC stage per NUMA node (Matcher.py:242-268): per (type, NIC signature, NICs in use) and tuple p, whether
-         * the groups p puts on NUMA 0 (SUB0) / NUMA 1 (SUB1) get NICs there, and which */
-        for (int i = tid; i < T * FAST_NSIG * 16; i += SWEEP_THREADS) {
-            const int tt = i / (FAST_NSIG * 16), sg = (i >> 4) % FAST_NSIG, iu = i & 15;
-            const PodType& ty = a.types[tt];
-            const uint32_t sv = a.sigs[sg];
-            uint32_t w0 = 0, w1 = 0;
-            const int n_k = (int)(sv & 15);
-            if ((sv >> 31) && ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2 && iu < (1 << n_k)) {
-                const uint32_t mk = (1u << n_k) - 1;
-                const unsigned long long sp = (sv >> 4) & 0xFFFFu;
-                const int G = ty.G, gmask = (1 << G) - 1;
-                for (int p = 0; p <= gmask; p++) {
-                    const int S1 = (int)(__brev((unsigned)p) >> (32 - G)), S0 = gmask & ~S1;
-                    const uint32_t r0 = nic_sub_solve(a.cap, ty, S0, mk, (uint32_t)iu, sp, 0ULL);
-                    const uint32_t r1 = nic_sub_solve(a.cap, ty, S1, mk, (uint32_t)iu, sp, 0ULL);
-                    w0 |= (((r0 >> 31) << 7) | (r0 & 3) | (((r0 >> 8) & 3) << 2)) << (8 * p);
-                    w1 |= (((r1 >> 31) << 7) | (r1 & 3) | (((r1 >> 8) & 3) << 2)) << (8 * p);
-                }
-            }
-            s_sub0[i] = w0; s_sub1[i] = w1;
-        }
+        /* the direct-path tables of this batch's pod types (fast_tables_kernel): one contiguous copy; the
+         * shared-memory areas s_tb | s_sub0 | s_sub1 | s_gd | s_ty are laid out like the buffer */
+        for (int i = tid; i < (int)(ftab_bytes(T) / 16); i += SWEEP_THREADS)
+            reinterpret_cast<uint4*>(s_tb)[i] = reinterpret_cast<const uint4*>(a.ftab)[i];
         /* "no CPU-only pod can spill" certificate: a CPU-only pod touches one node, and a node no pod of the batch
          * was bound to keeps its exact snapshot bit; a type with more GPU-less candidates than there are CPU-only
          * pods therefore never runs out of them (or it has no candidate anywhere).  Then CPU-only pods only ever
@@ -1833,6 +1899,7 @@ sweep_kernel(const SweepArgs a)
     }
     __syncwarp();
     double cur_now = a.n_pods > 0 ? a.now[0] : 0.0;
+    double busy_oldest = -1e300;          /* oldest stamp on the busy list; unknown for the snapshot's list: first clock step scans */
     PROF_DECL
 
     for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
@@ -1935,7 +2002,11 @@ sweep_kernel(const SweepArgs a)
         if (!handled) do {
 
         /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
-        if (now != cur_now) {
+        if (now > cur_now && now - busy_oldest < a.min_busy) {
+            /* forwards, and not even the oldest stamp on the list has left the window: nothing changes */
+            cur_now = now;
+        } else if (now != cur_now) {
+            double oldest = 1e300;
             if (now < cur_now) {
                 /* clock went backwards: rebuild from the summaries */
                 n_busy = 0;
@@ -1945,6 +2016,7 @@ sweep_kernel(const SweepArgs a)
                     if (n < a.n_nodes) {
                         double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
                         b = (now - bt) < a.min_busy;
+                        if (b && bt < oldest) oldest = bt;
                     }
                     uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
                     if (lane == 0) reinterpret_cast<uint32_t*>(BUSY)[n0 >> 5] = bal;
@@ -1961,6 +2033,7 @@ sweep_kernel(const SweepArgs a)
                         n = a.busy_list[e];
                         double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
                         b = (now - bt) < a.min_busy;
+                        if (b && bt < oldest) oldest = bt;
                         if (!b) atomicAnd(reinterpret_cast<unsigned long long*>(&BUSY[n >> 6]), ~(1ULL << (n & 63)));
                     }
                     uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
@@ -1972,6 +2045,12 @@ sweep_kernel(const SweepArgs a)
                 n_busy = kept;
             }
             for (int tt = lane; tt < T; tt += 32) cursors[tt * 3 + 2] = 0;   /* busy bits may have cleared */
+            /* the oldest stamp still inside the window (stamps added from here on are newer) */
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double o = __shfl_sync(0xFFFFFFFFu, oldest, lane ^ d);
+                oldest = o < oldest ? o : oldest;
+            }
+            busy_oldest = oldest;
             __syncwarp();
             cur_now = now;
         }
@@ -2117,6 +2196,7 @@ sweep_kernel(const SweepArgs a)
                     if (!cclock) a.busy_list[n_busy] = chosen;
                 }
                 n_busy++;
+                if (now < busy_oldest) busy_oldest = now;
             }
         }
         /* eager invalidation: pod types that can no longer fit here lose their bit now, so later

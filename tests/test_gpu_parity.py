@@ -106,7 +106,7 @@ def test_baseline_configs_match_oracle(oracle_lib, solver_mod, config, n_nodes, 
     cb, crecs, timing = _run_cuda(solver_mod, recs, speed, pods, now, extra_cpu_warps=ALL_CPU_WARPS)
     assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
     assert orecs.tobytes() == crecs.tobytes()
-    assert timing['n_launches'] == 5      # filter, sweep, resolve, core ids, commit
+    assert timing['n_launches'] == 6      # direct-path tables, filter, sweep, resolve, core ids, commit
 
 
 def test_clock_changes_and_busy_window(oracle_lib, solver_mod):

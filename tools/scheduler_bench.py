@@ -70,8 +70,24 @@ dev_ms = None
 if not use_oracle and sched.cluster._solver is not None:
     t = sched.cluster._solver.timing()
     dev_ms = t['total_ms']
+first = {'pods_per_s': n_pods / total_s, 'seconds': {k: round(v, 4) for k, v in acc.items()}, 'seconds_total': round(total_s, 4),
+         'note': 'first batch after start-up: every node record is packed from its Python object and uploaded once'}
+# steady state: the cluster mirror is resident, the solver's own placements need no upload; a second pending set arrives
+acc.clear()
+pods2, _ = workload.make_pods(4, n_pods, seed=workload.SEED0 + 77)
+for i, p in enumerate(pods2):
+    k8s.add_pod('ns', f'late{i:05d}', pyref.pod_dict_from_record(p))
+t0 = time.perf_counter()
+sched.CheckPendingPods()
+total_s = time.perf_counter() - t0
+bound = sum(1 for p in k8s.pods.values() if p['node'])
+other = total_s - sum(acc.values())
+if not use_oracle and sched.cluster._solver is not None:
+    dev_ms = sched.cluster._solver.timing()['total_ms']
 line = {'metric': 'scheduler-level pods/s (NHDScheduler.CheckPendingPods, one batch, in-memory K8s stand-in)',
-        'value': n_pods / total_s, 'unit': 'pods/s', 'n_nodes': n_nodes, 'n_pods': n_pods, 'bound': bound,
+        'first_batch': first,
+        'value': n_pods / total_s, 'unit': 'pods/s', 'n_nodes': n_nodes, 'n_pods': n_pods, 'bound_total': bound,
+        'what': 'second pending set (steady state: device-resident cluster, only host-side changes are re-sent)',
         'seconds': {k: round(v, 4) for k, v in acc.items()}, 'seconds_other': round(other, 4), 'seconds_total': round(total_s, 4),
         'device_ms_last_batch': dev_ms, 'batches': sched.cluster.batches, 'full_loads': sched.cluster.full_loads,
         'startup_s (ParseLabels per node, once)': round(startup_s, 2), 'setup_s (bench only)': round(setup_s, 2),

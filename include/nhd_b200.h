@@ -171,7 +171,8 @@ typedef struct nhd_params {
     int32_t  device;                 /* CUDA device ordinal                                    */
     int32_t  rank;                   /* node-shard rank, 0 when single GPU                     */
     int32_t  world_size;             /* number of GPUs sharing the node set                    */
-    int32_t  reserved_;              /* 0.  Test hook: low byte 1 = one-warp sweep, 2..8 = 1..7 CPU-only-class warps;
+    int32_t  reserved_;              /* 0.  Test hook: low byte 1 = the general one-warp sweep only, 2 = never sweep the two pod
+                                      * classes side by side; bit 8 = no standing decisions, bit 9 = same as 2;
                                       * all settings produce identical bindings (tests/test_gpu_parity.py)      */
     uint8_t  nccl_unique_id[128];    /* from nhd_nccl_unique_id() on rank 0; unused if world_size==1 */
 } nhd_params;
@@ -179,7 +180,7 @@ typedef struct nhd_params {
 /* per-call device timings of the last nhd_solve_batch (CUDA events, ms) */
 typedef struct nhd_timing {
     float filter_ms;             /* snapshot predicate kernel                                  */
-    float exchange_ms;           /* NCCL collective (0 when world_size == 1)                   */
+    float exchange_ms;           /* NCCL all-gather + slot unpack (0 when world_size == 1)     */
     float sweep_ms;              /* select + assign sweep kernel                               */
     float total_ms;              /* first launch to last kernel end                            */
     int32_t n_types;             /* distinct pod descriptors in the batch                      */

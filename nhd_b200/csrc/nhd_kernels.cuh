@@ -573,7 +573,7 @@ __global__ void unpack_slots_kernel(const uint4* __restrict__ xchg, int ws, int 
 #define PROF2_DECL long long p2_t0 = clock64();
 #define PROF2(i) do { long long t_ = clock64(); if (cx.lane == 0) atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - p2_t0)); p2_t0 = t_; } while (0)
 #define PROF_FLUSH(buf) do { if (lane == 0) for (int i_ = 0; i_ < 16; i_++) { (buf)[i_] = (unsigned long long)prof_acc[i_]; (buf)[32 + i_] = (unsigned long long)prof_cnt[i_]; } } while (0)
-#define PROF_ADD(i, n) do { if (cx.lane == 0) atomicAdd(&a.prof[48 + (i)], (unsigned long long)(n)); } while (0)
+#define PROF_ADD(i, n) do { const unsigned long long n_ = (unsigned long long)(n); if (cx.lane == 0) atomicAdd(&a.prof[48 + (i)], n_); } while (0)
 #define PROFL_DECL long long pl_t0 = clock64();
 #define PROFL(i) do { long long t_ = clock64(); atomicAdd(&a.prof[16 + (i)], (unsigned long long)(t_ - pl_t0)); atomicAdd(&a.prof[48 + (i)], 1ULL); pl_t0 = clock64(); } while (0)
 #else

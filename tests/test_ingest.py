@@ -249,3 +249,48 @@ def test_node_stats_match_reference_getters_after_scheduling():
         order = list(nodes.values())
         recs = packing.pack_nodes(order, packing.ClusterLayout())
         _check_stats(recs, _stats_of_objects(order))
+
+
+@pytest.mark.parametrize('config,wild', [(4, False), (5, False), (4, True)])
+def test_bench_clusters_are_what_the_ingest_makes_of_nfd_labels(config, wild):
+    """the synthetic clusters of workload.py (bench.py, the full-size parity tests) are packed records
+    written with numpy for speed; every one of them is exactly what the native label ingest produces from the NFD
+    label dictionary of that node (tests/pyref.node_def_from_record writes the labels), plus the occupancy the
+    record carries (cores / GPUs / NICs in use, hugepages) — i.e. a state the reference reaches from those labels."""
+    import workload
+    from tests import pyref
+    recs, speed = workload.make_cluster(config, n_nodes=600, wild=wild)
+    ing = LabelIngest()
+    for s in speed:                                   # same speed classes in the same order as the workload's table
+        if s:
+            pass
+    got = np.zeros(len(recs), dtype=wire.NODE_DTYPE)
+    for i, r in enumerate(recs):
+        nd = pyref.node_def_from_record(i, r, speed, group_names=[f'g{b}' for b in range(64)] if config == 5 else None)
+        rec, _ = ing.node(nd['labels'], nd['active'], nd['hp_alloc'], nd['hp_free'], name=nd['name'])
+        got[i] = rec
+    # static description: everything but the occupancy words
+    for f in ('n_numa', 'phys_cores', 'n_gpus', 'n_nics', 'gpu_numa_mask', 'nic_numa_mask'):
+        assert np.array_equal(got[f], recs[f]), f
+
+    def switch_classes(r):
+        # switch ids are node-local aliases (only equality is ever tested, Matcher.py:316-320, Node.py:651): compare the
+        # partition of the GPUs and NICs into switches, numbered by first use
+        ids = [(int(r['gpu_sw']) >> (4 * g)) & 0xF for g in range(int(r['n_gpus']))] + \
+              [(int(r['nic_sw'][j >> 4]) >> (4 * (j & 15))) & 0xF for j in range(int(r['n_nics']))]
+        first = {}
+        return [first.setdefault(x, len(first)) for x in ids]
+    for i in range(len(recs)):
+        assert switch_classes(got[i]) == switch_classes(recs[i]), i
+    assert np.array_equal(got['flags'] & (wire.NODE_SMT | wire.NODE_ACTIVE), recs['flags'] & (wire.NODE_SMT | wire.NODE_ACTIVE))
+    # speed classes: the ingest numbers them in order of first appearance, the workload by its table
+    tbl = ing.speed_table()
+    for i in range(len(recs)):
+        for j in range(int(recs[i]['n_nics'])):
+            a = (int(got[i]['nic_speed'][j >> 4]) >> (4 * (j & 15))) & 0xF
+            b = (int(recs[i]['nic_speed'][j >> 4]) >> (4 * (j & 15))) & 0xF
+            assert tbl[a] == speed[b], (i, j)
+    # occupancy only ever adds to what the labels give: reserved cores stay reserved, free hugepages as given
+    assert np.array_equal(got['used'] & recs['used'], got['used'])
+    assert np.array_equal(got['free_hugepages_gb'], recs['free_hugepages_gb'])
+    assert (got['gpu_used'] == 0).all() and (got['nic_inuse'] == 0).all()

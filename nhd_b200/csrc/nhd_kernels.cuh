@@ -1519,12 +1519,6 @@ struct LaneSlot {
     NodeAux ax;              /* FAST: class entry of the node, NICs in use once the pod is placed */
     int c;                   /* CPU-only types: word of F[t] & NOGPU the lane is at, and what is left of it */
     uint64_t w;
-    /* FAST: the candidate after `node` with its current summary and class entry, kept exact like the bits, so that
-     * the day `node` stops taking the type the lane has its next decision without another pass:
-     * nx_node >= 0 valid, -1 none (evaluate the slow way), -2 to be looked up again */
-    int nx_node;
-    DynU nx_st;
-    NodeAux nx_ax;
 };
 
 /*
@@ -1534,22 +1528,19 @@ struct LaneSlot {
  *                been bound to stay exact; lanes whose decision was for node0 take the result as their new decision.
  *                A lane whose type no longer fits clears the bit (resources only shrink inside a batch) and, if node0
  *                was its candidate, moves on to its next one;
- *   rescan_cpu / rescan_gpu   lanes that must look their candidate up again (after the ordinary path, which
- *                changed `changed_node`).
- * Every lane also keeps the candidate AFTER its node with that node's current summary (nx_*), evaluated in the same
- * straight-line block as the committed node, so a lane that has to move on usually has its decision at once; lanes
- * only part ways to scan and load.
+ *   rescan_cpu / rescan_gpu   lanes that must look their candidate up again (after the ordinary path).
+ * Every pass of the loop evaluates all lanes that need it side by side; lanes only part ways to scan and load.
  */
 template <bool SMEM_BITMAPS>
 __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx& cx, const FastTables& ft, const TyFast& ty, int tl,
                                               bool l_direct, bool l_cpu, bool l_gpu, LaneSlot& sl, uint64_t* BM, const uint64_t* NOGPU,
                                               const uint64_t* BUSY, const uint64_t* touched, int W, int32_t* cursors, double now,
                                               bool eval_first, int node0, const DynU& st0, const NodeAux& ax0,
-                                              uint32_t rescan_cpu, uint32_t rescan_gpu, int changed_node)
+                                              uint32_t rescan_cpu, uint32_t rescan_gpu)
 {
     const int lane = cx.lane;
     uint64_t* F = BM + (size_t)tl * W;
-    bool need = false;
+    bool need = eval_first && l_direct;
     bool pointing = sl.node == node0;
     bool dead = !eval_first && l_cpu && ((rescan_cpu >> lane) & 1);
     int cur_node = node0;
@@ -1557,69 +1548,33 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
     cur.q[0] = st0.q[0]; cur.q[1] = st0.q[1];
     NodeAux cax = ax0;
     __syncwarp();
-    if (dead) {
-        if (sl.c >= 0 && sl.c < W) sl.w &= ldw<SMEM_BITMAPS>(&F[sl.c]);     /* the ordinary path may have cleared bits of this word */
-        sl.nx_node = -1;
-    }
-    if (!eval_first && changed_node >= 0 && sl.nx_node == changed_node) sl.nx_node = -2;      /* the ordinary path changed my next candidate */
-    if (eval_first) {
-        /* One straight-line block, two independent evaluations the scheduler interleaves: (A) this lane's type on the
-         * committed node's new summary — every directly evaluable type, so the bits of bound-to nodes stay exact;
-         * (B) this lane's type on its NEXT candidate, which is what it needs if (A) says the node no longer takes it. */
-        PROF_ADD(0, 1);
-        uint32_t decA = 0, iuA = 0, decB = 0, iuB = 0;
-        DynU daA, daB;
-        const bool feasA = fast_eval(ft, tl, ty, cur, cax, now, decA, daA, iuA);
-        const bool haveB = sl.nx_node >= 0 && sl.nx_node != node0;
-        const bool feasB = fast_eval(ft, tl, ty, sl.nx_st, sl.nx_ax, now, decB, daB, iuB) && haveB;
-        if (l_direct) {
-            if (feasA) {
-                if (pointing) {
-                    sl.kind = NHD_SLOT_FAST; sl.dec = decA; sl.w14 = cur.q[0].y;
-                    sl.after.q[0] = daA.q[0]; sl.after.q[1] = daA.q[1];
-                    sl.ax = cax; sl.ax.iu = iuA;
-                } else if (sl.nx_node == node0) {               /* my next candidate just changed: keep its summary exact */
-                    sl.nx_st.q[0] = cur.q[0]; sl.nx_st.q[1] = cur.q[1]; sl.nx_ax = cax;
-                }
-            } else {
-                bit_clear(F, node0);
-                if (sl.c == (node0 >> 6)) sl.w &= ~(1ULL << (node0 & 63));
-                if (pointing) {
-                    if (feasB) {
-                        /* move on to the next candidate: its decision is ready */
-                        const int n2 = sl.nx_node;
-                        if ((n2 >> 6) != sl.c) { sl.c = n2 >> 6; sl.w = ldw<SMEM_BITMAPS>(&F[sl.c]) & ldw<SMEM_BITMAPS>(&NOGPU[sl.c]); }
-                        sl.node = n2; sl.kind = NHD_SLOT_FAST; sl.dec = decB; sl.w14 = sl.nx_st.q[0].y;
-                        sl.after.q[0] = daB.q[0]; sl.after.q[1] = daB.q[1];
-                        sl.ax = sl.nx_ax; sl.ax.iu = iuB;
-                        sl.nx_node = -2;
-                    } else dead = true;
-                } else if (sl.nx_node == node0) sl.nx_node = -2;   /* my next candidate is gone */
-            }
-        }
-    }
+    if (dead && sl.c >= 0 && sl.c < W)                       /* the ordinary path may have cleared bits of this word */
+        sl.w &= ldw<SMEM_BITMAPS>(&F[sl.c]);
     for (;;) {
         if (__any_sync(0xFFFFFFFFu, need)) {
-            PROF_ADD(1, 1);                                  /* extra evaluation passes */
+            PROF_ADD(0, 1);                                  /* evaluation passes */
+            PROF_ADD(1, __popc(__ballot_sync(0xFFFFFFFFu, need)));      /* lanes evaluating */
             uint32_t dec = 0, iu2 = 0;
             DynU da;
             const bool feas = fast_eval(ft, tl, ty, cur, cax, now, dec, da, iu2);
             if (need) {
                 if (feas) {
-                    sl.node = cur_node; sl.kind = NHD_SLOT_FAST; sl.dec = dec; sl.w14 = cur.q[0].y;
-                    sl.after.q[0] = da.q[0]; sl.after.q[1] = da.q[1];
-                    sl.ax = cax; sl.ax.iu = iu2;
-                    sl.nx_node = -2;
+                    if (pointing) {
+                        sl.node = cur_node; sl.kind = NHD_SLOT_FAST; sl.dec = dec; sl.w14 = cur.q[0].y;
+                        sl.after.q[0] = da.q[0]; sl.after.q[1] = da.q[1];
+                        sl.ax = cax; sl.ax.iu = iu2;
+                    }
                 } else {
                     bit_clear(F, cur_node);
                     if (sl.c == (cur_node >> 6)) sl.w &= ~(1ULL << (cur_node & 63));
-                    dead = true;
+                    dead = pointing;
                 }
             }
             need = false;
         }
         if (!__any_sync(0xFFFFFFFFu, dead)) break;
-        PROF_ADD(2, 1);                                      /* passes with lanes looking their candidate up */
+        PROF_ADD(2, 1);                                      /* passes with lanes moving on */
+        PROF_ADD(3, __popc(__ballot_sync(0xFFFFFFFFu, dead)));          /* lanes moving on */
         if (dead) {
             /* next candidate of the GPU-less pass (Matcher.py:412-416) */
             if (sl.c < W)
@@ -1628,35 +1583,14 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
                     if (sl.c >= W) break;
                     sl.w = ldw<SMEM_BITMAPS>(&F[sl.c]) & ldw<SMEM_BITMAPS>(&NOGPU[sl.c]);
                 }
-            sl.nx_node = -1;
             if (sl.c >= W) { sl.node = -1; sl.kind = NHD_SLOT_SLOW; }        /* the pod will spill: ordinary path */
             else {
                 cur_node = sl.c * 64 + ctz64(sl.w);
                 fast_load_dyn(a, cx, touched, cur_node, cur);
-                if (l_direct && fast_node_aux(ft, cur, cax)) need = true;
+                if (l_direct && fast_node_aux(ft, cur, cax)) { need = true; pointing = true; }
                 else { sl.node = cur_node; sl.kind = NHD_SLOT_SLOW; }         /* a shape the tables do not cover */
             }
             dead = false;
-        }
-    }
-    /* lanes that settled on a new node look up the candidate after it (summary through L1, class entry): no evaluation */
-    const bool want_nx = l_direct && sl.kind == NHD_SLOT_FAST && sl.nx_node == -2;
-    if (__any_sync(0xFFFFFFFFu, want_nx)) {
-        PROF_ADD(3, 1);
-        if (want_nx) {
-            uint64_t w2 = sl.w & ~(1ULL << (sl.node & 63));
-            int c2 = sl.c;
-            while (w2 == 0) {
-                c2++;
-                if (c2 >= W) break;
-                w2 = ldw<SMEM_BITMAPS>(&F[c2]) & ldw<SMEM_BITMAPS>(&NOGPU[c2]);
-            }
-            sl.nx_node = -1;
-            if (c2 < W) {
-                const int n3 = c2 * 64 + ctz64(w2);
-                fast_load_dyn(a, cx, touched, n3, sl.nx_st);
-                if (fast_node_aux(ft, sl.nx_st, sl.nx_ax)) sl.nx_node = n3;
-            }
         }
     }
     if (l_gpu && ((rescan_gpu >> lane) & 1)) {
@@ -1930,7 +1864,6 @@ sweep_kernel(const SweepArgs a)
     LaneSlot sl;
     sl.node = -1; sl.kind = NHD_SLOT_SLOW; sl.dec = sl.w14 = 0; sl.after.q[0] = st_none.q[0]; sl.after.q[1] = st_none.q[0];
     sl.ax = ax_none; sl.c = -1; sl.w = 0;
-    sl.nx_node = -1; sl.nx_st.q[0] = st_none.q[0]; sl.nx_st.q[1] = st_none.q[0]; sl.nx_ax = ax_none;
     const double now0 = a.n_pods > 0 ? a.now[0] : 0.0;
     if (fast) {
         for (int tt = 0; tt < T; tt++) {
@@ -1944,7 +1877,7 @@ sweep_kernel(const SweepArgs a)
         l_cpu = (cpu_mask >> lane) & 1; l_gpu = (gpu_mask >> lane) & 1;
         l_direct = l_cpu && myty.direct;
         lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now0,
-                                    false, -1, st_none, ax_none, cpu_mask, gpu_mask, -1);
+                                    false, -1, st_none, ax_none, cpu_mask, gpu_mask);
     }
 
     /* busy list from the BUSY snapshot (filter_kernel evaluated it for now[0]) */
@@ -2291,16 +2224,15 @@ sweep_kernel(const SweepArgs a)
         if (fast) {
             if (fast_commit) {
                 lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now,
-                                            true, commit_node, da, dax, 0u, 0u, -1);
+                                            true, commit_node, da, dax, 0u, 0u);
             } else {
                 /* every standing decision made for the node this pod changed is out of date; after the ordinary path
                  * the pod's own type as well (it may have given up the node its slot names) */
                 uint32_t st = handled ? 0u : (1u << ti);
                 if (commit_node >= 0) st |= __ballot_sync(0xFFFFFFFFu, sl.node == commit_node);
-                const bool nx_hit = __any_sync(0xFFFFFFFFu, commit_node >= 0 && sl.nx_node == commit_node);
-                if ((st & (cpu_mask | gpu_mask)) || nx_hit)
+                if (st & (cpu_mask | gpu_mask))
                     lanes_refresh<SMEM_BITMAPS>(a, cx, ft, myty, tl, l_direct, l_cpu, l_gpu, sl, BM, NOGPU, BUSY, s_touched, W, cursors, now,
-                                                false, -1, st_none, ax_none, st & cpu_mask, st & gpu_mask, commit_node);
+                                                false, -1, st_none, ax_none, st & cpu_mask, st & gpu_mask);
             }
         }
         PROF_MARK(6);      /* write-back + refresh */

@@ -527,7 +527,23 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
     index.reserve(64);
     std::vector<PodType> types;
     h->pod_type_host.resize(n_pods);
+    /* pending sets repeat a few descriptors thousands of times: a descriptor seen before (byte for byte) skips
+     * validation, normalisation and the map */
+    struct RawSlot { uint64_t hash; int32_t type; nhd_pod raw; };
+    static thread_local std::vector<RawSlot> raw_cache;
+    raw_cache.assign(256, RawSlot{0, -1, {}});
     for (int i = 0; i < n_pods; i++) {
+        uint64_t rh = 0x9E3779B97F4A7C15ULL;
+        {
+            const uint64_t* w = reinterpret_cast<const uint64_t*>(&pods[i]);
+            for (size_t q = 0; q < sizeof(nhd_pod) / 8; q++) { rh ^= w[q]; rh *= 0xff51afd7ed558ccdULL; rh ^= rh >> 29; }
+        }
+        RawSlot& rs = raw_cache[rh & 255];
+        if (rs.type >= 0 && rs.hash == rh && memcmp(&rs.raw, &pods[i], sizeof(nhd_pod)) == 0) {
+            if (!std::isfinite(now[i])) return fail(h, NHD_ERR_INVALID, "pod %d: non-finite clock", i);
+            h->pod_type_host[i] = rs.type;
+            continue;
+        }
         int32_t v = nhd_validate_pod(&pods[i]);
         if (v != NHD_OK) return fail(h, v, "pod %d: descriptor rejected by nhd_validate_pod", i);
         if (!std::isfinite(now[i])) return fail(h, NHD_ERR_INVALID, "pod %d: non-finite clock", i);
@@ -545,6 +561,7 @@ extern "C" int32_t nhd_stage_batch(nhd_handle* h, int32_t n_pods, const nhd_pod*
             types.push_back(t);
         }
         h->pod_type_host[i] = it->second;
+        rs.hash = rh; rs.type = it->second; rs.raw = pods[i];
     }
     const int T = (int)types.size();
     const size_t types_bytes = (size_t)T * sizeof(PodType);

@@ -109,6 +109,28 @@ def test_baseline_configs_match_oracle(oracle_lib, solver_mod, config, n_nodes, 
     assert timing['n_launches'] == 6      # direct-path tables, filter, sweep, resolve, core ids, commit
 
 
+@pytest.mark.parametrize('wild', [False, True], ids=['regular', 'heterogeneous'])
+def test_many_pod_type_catalogues_match_oracle(oracle_lib, solver_mod, wild):
+    """The table-driven direct path over many different pod-type catalogues (group counts, SMT flags, misc cores,
+    NIC demands, hugepages), on clusters big enough for the no-spill certificate to hold (the two pod classes on two
+    CTAs) — and on a heterogeneous cluster where most hardware classes fall outside the tables."""
+    placed = 0
+    for seed in range(10):
+        recs, speed = workload.make_cluster(3 + seed % 2, n_nodes=900, seed=4200 + seed, wild=wild)
+        types = workload.make_pod_types(3 + seed % 2, seed=9000 + seed)
+        rng = np.random.default_rng(seed)
+        # skew the stream so that some types fill their nodes quickly
+        pick = rng.choice(len(types), size=220, p=rng.dirichlet(np.ones(len(types)) * 0.7))
+        pods = types[pick].copy()
+        now = np.full(len(pods), 777.0)
+        ob, orecs = oracle_lib.solve(recs, speed, pods, now)
+        cb, crecs, _ = _run_cuda(solver_mod, recs, speed, pods, now, extra_cpu_warps=ALL_CPU_WARPS)
+        assert helpers.binding_bytes_equal(ob, cb), (seed, helpers.first_binding_diff(ob, cb))
+        assert orecs.tobytes() == crecs.tobytes(), seed
+        placed += int((ob['status'] == 0).sum())
+    assert placed > 1500
+
+
 def test_clock_changes_and_busy_window(oracle_lib, solver_mod):
     """Per-pod clocks that move forwards, stall and jump backwards exercise the busy list."""
     recs, speed, pods, _ = workload.make_workload(3, n_nodes=512, n_pods=200)

@@ -158,7 +158,8 @@ def quick_value(Solver, recs, speed, pods, now, steps=3, **kw):
             t = s.timing()
             best = t if best is None or t['total_ms'] < best['total_ms'] else best
         return {'value': len(pods) / (best['total_ms'] / 1e3), 'unit': UNIT, 'ms': best['total_ms'],
-                'filter_ms': best['filter_ms'], 'sweep_ms': best['sweep_ms'], 'pod_types': best['n_types']}
+                'filter_ms': best['filter_ms'], 'exchange_ms': best['exchange_ms'], 'sweep_ms': best['sweep_ms'],
+                'pod_types': best['n_types']}
     finally:
         s.close()
 
@@ -328,6 +329,22 @@ def main():
     h2d = N * wire.NODE_DTYPE.itemsize + n_types * 176 + P * 12
     d2h = P * wire.BINDING_DTYPE.itemsize
 
+    # BASELINE config 5 (262 144 x 8 192, SR-IOV VFs + node groups) on all ranks: a side number, a few solves
+    cfg5_multi = None
+    if world > 1 and not args.no_extra:
+        idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))     # a fresh id: one per handle
+        dist.broadcast(idt, 0)
+        r5, s5, p5, n5 = workload.make_workload(5)
+        cfg5_multi = quick_value(Solver, r5, s5, p5, n5, device=local_rank, rank=rank, world_size=world,
+                                 nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        tt = torch.tensor([cfg5_multi['ms']], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cfg5_multi['ms'] = float(tt.item())
+        cfg5_multi['value'] = len(p5) / (cfg5_multi['ms'] / 1e3)
+        del r5, p5
+
     # every rank ran the identical replicated sweep: their bindings must be byte-identical (digest vs rank 0)
     ranks_agree = True
     if world > 1:
@@ -450,6 +467,8 @@ def main():
                                                     note='per-pod clocks: the general one-warp sweep with busy-list upkeep')
         except Exception as e:
             extra['error'] = str(e)[:200]
+    if cfg5_multi is not None:
+        extra[f'config5_262144x8192_{world}gpu'] = cfg5_multi
     total_ms = float(np.mean(phase['total_ms']))
     line['amdahl'] = {'filter_share': filter_ms / total_ms,
                       'limit_if_filter_were_free': total_ms / max(total_ms - filter_ms, 1e-9),

@@ -644,7 +644,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         TablesArgs ta;
         ta.types = h->d_types; ta.n_types = T; ta.sigs = h->d_sigs; ta.out = h->d_ftab;
         memcpy(ta.cap, h->cap, sizeof(ta.cap));
-        fast_tables_kernel<<<T, 256, 0, h->stream>>>(ta);
+        fast_tables_kernel<<<dim3(T, FAST_NSIG * 16 / 256), 256, 0, h->stream>>>(ta);
         CK(cudaGetLastError());
         launches++;
     }
@@ -715,7 +715,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
         if (T <= FAST_MAX_TYPES)                /* standing decisions + their tables */
-            smem += (size_t)T * (256 + 2 * FAST_NSIG * 64 + 16 + sizeof(TyFast)) + ((MAPT_BYTES + 15) & ~15) +
+            smem += ftab_small_bytes(T) + ((MAPT_BYTES + 15) & ~15) +
                     (((size_t)(T + 2) * 4 + 15) & ~(size_t)15);
         const size_t with_bitmaps = smem + bm_bytes;
         /* a second CTA takes the GPU pods when the two pod classes cannot meet (decided on the device, see sweep_kernel) */

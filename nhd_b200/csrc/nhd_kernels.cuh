@@ -187,7 +187,7 @@ __global__ void classify_verify_kernel(const uint8_t* __restrict__ nodes, const 
 #define NHD_PENDING_FAST 101          /* internal binding status: node and packed mapping known, header not formatted yet */
 
 constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
-constexpr int FAST_NSIG = 4;          /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
+constexpr int FAST_NSIG = 128;        /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
 constexpr int MAPT_BYTES = 4096 + 64;
 
 struct ClsFast {             /* per hardware class, 16 bytes */
@@ -207,7 +207,7 @@ struct TyFast {              /* per pod type, 16 bytes */
 
 struct FastTables {
     const uint8_t* tb;       /* [T][2][2][64] */
-    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p */
+    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p; global memory, read through L1 */
     const uint32_t* sub1;
     const uint8_t* mapt;     /* MAPT_BYTES */
     const uint16_t* gd;      /* [T][2][4] */
@@ -262,7 +262,9 @@ __global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cl
                 sv |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 + 4 * j);
             }
             int id = -1;
-            for (int q = 0; q < FAST_NSIG; q++) {
+            const uint32_t h0 = (sv * 0x9E3779B1u) >> 16;
+            for (int pr = 0; pr < FAST_NSIG; pr++) {
+                const int q = (int)((h0 + (uint32_t)pr) % FAST_NSIG);
                 const uint32_t old = atomicCAS(&sigs[q], 0u, sv);
                 if (old == 0u || old == sv) { id = q; break; }
             }
@@ -276,11 +278,12 @@ __global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cl
 /* byte offsets of the direct-path tables of T pod types inside one buffer (global: fast_tables_kernel writes it,
  * the filter reads it through L1, the sweep copies it to shared memory): TB | SUB0 | SUB1 | GD | TyFast */
 __host__ __device__ __forceinline__ size_t ftab_off_tb(int) { return 0; }
-__host__ __device__ __forceinline__ size_t ftab_off_sub0(int T) { return (size_t)T * 256; }
-__host__ __device__ __forceinline__ size_t ftab_off_sub1(int T) { return (size_t)T * 512; }
-__host__ __device__ __forceinline__ size_t ftab_off_gd(int T) { return (size_t)T * 768; }
-__host__ __device__ __forceinline__ size_t ftab_off_ty(int T) { return (size_t)T * 784; }
-__host__ __device__ __forceinline__ size_t ftab_bytes(int T) { return (size_t)T * 800; }
+__host__ __device__ __forceinline__ size_t ftab_off_gd(int T) { return (size_t)T * 256; }
+__host__ __device__ __forceinline__ size_t ftab_off_ty(int T) { return (size_t)T * 272; }
+__host__ __device__ __forceinline__ size_t ftab_small_bytes(int T) { return (size_t)T * 288; }       /* TB | GD | TyFast: copied to shared memory */
+__host__ __device__ __forceinline__ size_t ftab_off_sub0(int T) { return ftab_small_bytes(T); }
+__host__ __device__ __forceinline__ size_t ftab_off_sub1(int T) { return ftab_small_bytes(T) + (size_t)T * FAST_NSIG * 64; }
+__host__ __device__ __forceinline__ size_t ftab_bytes(int T) { return ftab_small_bytes(T) + (size_t)T * FAST_NSIG * 128; }
 
 __device__ __noinline__ uint32_t nic_sub_solve(const double* cap, const PodType& t, int S, uint32_t mk, uint32_t inuse,
                                                unsigned long long sp0, unsigned long long sp1);
@@ -301,22 +304,10 @@ __global__ void fast_tables_kernel(const TablesArgs a)
     const PodType& ty = a.types[tt];
     const bool direct = ty.valid_map && !ty.needs_gpu && !ty.pci && ty.G <= 2;
     {
-        /* CPU stage per socket (Matcher.py:203-212 with K = 2): which tuples q = 2p + m fit c free cores on NUMA k */
-        const int f = (i >> 7) & 1, k = (i >> 6) & 1, c = i & 63;
-        const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
-        const int L = ty.G + 1;
-        uint32_t m = 0;
-        for (int q = 0; q < (1 << L) && L <= 3; q++) {
-            int n = 0;
-            for (int g = 0; g < L; g++) if (((q >> (L - 1 - g)) & 1) == k) n += cl[g];
-            if (n <= c || (c == 63 && n <= 255)) m |= 1u << q;       /* the free count saturates at 63 in the index */
-        }
-        a.out[ftab_off_tb(T) + (size_t)tt * 256 + i] = (uint8_t)m;
-    }
-    if (i < FAST_NSIG * 16) {
         /* NIC stage per NUMA node (Matcher.py:242-268): per (type, NIC signature, NICs in use) and tuple p, whether
-         * the groups p puts on NUMA 0 (SUB0) / NUMA 1 (SUB1) get NICs there, and which */
-        const int sg = i >> 4, iu = i & 15;
+         * the groups p puts on NUMA 0 (SUB0) / NUMA 1 (SUB1) get NICs there, and which; blockIdx.y walks the signatures */
+        const int e = blockIdx.y * 256 + i;                       /* (signature, NICs in use) */
+        const int sg = e >> 4, iu = e & 15;
         const uint32_t sv = a.sigs[sg];
         uint32_t w0 = 0, w1 = 0;
         const int n_k = (int)(sv & 15);
@@ -332,8 +323,22 @@ __global__ void fast_tables_kernel(const TablesArgs a)
                 w1 |= (((r1 >> 31) << 7) | (r1 & 3) | (((r1 >> 8) & 3) << 2)) << (8 * p);
             }
         }
-        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub0(T))[tt * FAST_NSIG * 16 + i] = w0;
-        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub1(T))[tt * FAST_NSIG * 16 + i] = w1;
+        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub0(T))[tt * FAST_NSIG * 16 + e] = w0;
+        reinterpret_cast<uint32_t*>(a.out + ftab_off_sub1(T))[tt * FAST_NSIG * 16 + e] = w1;
+    }
+    if (blockIdx.y != 0) return;
+    {
+        /* CPU stage per socket (Matcher.py:203-212 with K = 2): which tuples q = 2p + m fit c free cores on NUMA k */
+        const int f = (i >> 7) & 1, k = (i >> 6) & 1, c = i & 63;
+        const uint8_t* cl = f ? ty.cl_smt : ty.cl_nosmt;
+        const int L = ty.G + 1;
+        uint32_t m = 0;
+        for (int q = 0; q < (1 << L) && L <= 3; q++) {
+            int n = 0;
+            for (int g = 0; g < L; g++) if (((q >> (L - 1 - g)) & 1) == k) n += cl[g];
+            if (n <= c || (c == 63 && n <= 255)) m |= 1u << q;       /* the free count saturates at 63 in the index */
+        }
+        a.out[ftab_off_tb(T) + (size_t)tt * 256 + i] = (uint8_t)m;
     }
     if (i < 8) {
         /* cores the groups of tuple p take from each socket */
@@ -1438,8 +1443,8 @@ __device__ __forceinline__ bool fast_eval(const FastTables& ft, int tl, const Ty
                                           double now, uint32_t& dec, DynU& da, uint32_t& iu_after)
 {
     const int smt = (du.d.info >> 1) & 1;                                     /* NHD_DYN_SMT */
-    const uint32_t w0 = ft.sub0[(tl * FAST_NSIG + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)];
-    const uint32_t w1 = ft.sub1[(tl * FAST_NSIG + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)];
+    const uint32_t w0 = __ldg(&ft.sub0[(tl * FAST_NSIG + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)]);
+    const uint32_t w1 = __ldg(&ft.sub1[(tl * FAST_NSIG + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)]);
     const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
     const uint32_t fc0 = du.q[0].x & 0xFF, fc1 = (du.q[0].x >> 8) & 0xFF;
     const uint32_t mB = ft.tb[((tl * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
@@ -1675,9 +1680,7 @@ sweep_kernel(const SweepArgs a)
     /* standing decisions and their tables (constant clock, one lane per type) */
     const bool fast_cap = cx.types_in_smem && T <= FAST_MAX_TYPES;
     uint8_t* s_tb = p3;                                                         /* [T][2][2][64] */
-    uint32_t* s_sub0 = reinterpret_cast<uint32_t*>(s_tb + (fast_cap ? (size_t)T * 256 : 0));      /* [T][FAST_NSIG][16] */
-    uint32_t* s_sub1 = s_sub0 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0);
-    uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_sub1 + (fast_cap ? (size_t)T * FAST_NSIG * 16 : 0));   /* [T][2][4] */
+    uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_tb + (fast_cap ? (size_t)T * 256 : 0));               /* [T][2][4] */
     TyFast* s_ty = reinterpret_cast<TyFast*>(s_gd + (fast_cap ? (size_t)T * 8 : 0));                       /* [T] */
     uint8_t* s_mapt = reinterpret_cast<uint8_t*>(s_ty + (fast_cap ? T : 0));                               /* MAPT_BYTES (+ pad) */
     int* s_cnt = reinterpret_cast<int*>(s_mapt + (fast_cap ? ((MAPT_BYTES + 15) & ~15) : 0));              /* [T + 2] candidate counts, CPU-only pods, flag */
@@ -1697,8 +1700,9 @@ sweep_kernel(const SweepArgs a)
         for (int i = tid; i < (MAPT_BYTES + 15) / 16; i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_mapt)[i] = reinterpret_cast<const uint4*>(a.mapt)[i];
         /* the direct-path tables of this batch's pod types (fast_tables_kernel): one contiguous copy; the
-         * shared-memory areas s_tb | s_sub0 | s_sub1 | s_gd | s_ty are laid out like the buffer */
-        for (int i = tid; i < (int)(ftab_bytes(T) / 16); i += SWEEP_THREADS)
+         * shared-memory areas s_tb | s_gd | s_ty are laid out like the head of the buffer; the NIC-stage tables
+         * (SUB0 / SUB1: one row per NIC signature, up to FAST_NSIG of them) stay in global memory, read through L1 */
+        for (int i = tid; i < (int)(ftab_small_bytes(T) / 16); i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_tb)[i] = reinterpret_cast<const uint4*>(a.ftab)[i];
         /* "no CPU-only pod can spill" certificate: a CPU-only pod touches one node, and a node no pod of the batch
          * was bound to keeps its exact snapshot bit; a type with more GPU-less candidates than there are CPU-only
@@ -1852,7 +1856,9 @@ sweep_kernel(const SweepArgs a)
     uint32_t cpu_mask = 0, gpu_mask = 0;
     unsigned long long gpu_pods_mask = 0;                   /* (side by side) types whose pods CTA 1 sweeps */
     FastTables ft;
-    ft.tb = s_tb; ft.sub0 = s_sub0; ft.sub1 = s_sub1; ft.mapt = s_mapt; ft.gd = s_gd; ft.ty = s_ty; ft.cls = a.cls_fast;
+    ft.tb = s_tb; ft.mapt = s_mapt; ft.gd = s_gd; ft.ty = s_ty; ft.cls = a.cls_fast;
+    ft.sub0 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T)) : nullptr;
+    ft.sub1 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T)) : nullptr;
     DynU st_none;
     st_none.q[0] = make_uint4(0, 0, 0, 0); st_none.q[1] = st_none.q[0];
     NodeAux ax_none = {0, 0, 0, 0};

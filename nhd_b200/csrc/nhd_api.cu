@@ -715,7 +715,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         if (T <= SWEEP_TYPES_SMEM_MAX) smem += (((size_t)T * sizeof(PodType) + 15) & ~(size_t)15) + (size_t)T * 256;
         smem += (((size_t)T * 3 * 4 + 15) & ~(size_t)15) + (size_t)W * 8;
         if (T <= FAST_MAX_TYPES)                /* standing decisions + their tables */
-            smem += ftab_small_bytes(T) + ((MAPT_BYTES + 15) & ~15) +
+            smem += ftab_small_bytes(T) + (size_t)T * FAST_NSIG_SMEM * 128 + ((MAPT_BYTES + 15) & ~15) +
                     (((size_t)(T + 2) * 4 + 15) & ~(size_t)15);
         const size_t with_bitmaps = smem + bm_bytes;
         /* a second CTA takes the GPU pods when the two pod classes cannot meet (decided on the device, see sweep_kernel) */

@@ -188,6 +188,7 @@ __global__ void classify_verify_kernel(const uint8_t* __restrict__ nodes, const 
 
 constexpr int FAST_MAX_TYPES = 32;    /* one lane per type */
 constexpr int FAST_NSIG = 128;        /* distinct per-NUMA NIC signatures (count + speeds) the tables hold */
+constexpr int FAST_NSIG_SMEM = 4;     /* ... of which the first few (ids are handed out in order of appearance) sit in shared memory */
 constexpr int MAPT_BYTES = 4096 + 64;
 
 struct ClsFast {             /* per hardware class, 16 bytes */
@@ -208,6 +209,8 @@ struct TyFast {              /* per pod type, 16 bytes */
 struct FastTables {
     const uint8_t* tb;       /* [T][2][2][64] */
     const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p; global memory, read through L1 */
+    const uint32_t* sub0s;   /* [T][FAST_NSIG_SMEM][16]: the rows of the first signatures, in shared memory */
+    const uint32_t* sub1s;
     const uint32_t* sub1;
     const uint8_t* mapt;     /* MAPT_BYTES */
     const uint16_t* gd;      /* [T][2][4] */
@@ -262,9 +265,7 @@ __global__ void cls_fast_kernel(const ClassSlot* __restrict__ slots, ClsFast* cl
                 sv |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 + 4 * j);
             }
             int id = -1;
-            const uint32_t h0 = (sv * 0x9E3779B1u) >> 16;
-            for (int pr = 0; pr < FAST_NSIG; pr++) {
-                const int q = (int)((h0 + (uint32_t)pr) % FAST_NSIG);
+            for (int q = 0; q < FAST_NSIG; q++) {                    /* ids in order of appearance: the common ones are low */
                 const uint32_t old = atomicCAS(&sigs[q], 0u, sv);
                 if (old == 0u || old == sv) { id = q; break; }
             }
@@ -1443,8 +1444,12 @@ __device__ __forceinline__ bool fast_eval(const FastTables& ft, int tl, const Ty
                                           double now, uint32_t& dec, DynU& da, uint32_t& iu_after)
 {
     const int smt = (du.d.info >> 1) & 1;                                     /* NHD_DYN_SMT */
-    const uint32_t w0 = __ldg(&ft.sub0[(tl * FAST_NSIG + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)]);
-    const uint32_t w1 = __ldg(&ft.sub1[(tl * FAST_NSIG + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)]);
+    const uint32_t sg0 = ax.sig & 0xFF, sg1 = (ax.sig >> 8) & 0xFF;
+    const uint32_t* p0 = sg0 < FAST_NSIG_SMEM ? &ft.sub0s[(tl * FAST_NSIG_SMEM + sg0) * 16 + (ax.iu & 15)]
+                                              : &ft.sub0[(tl * FAST_NSIG + sg0) * 16 + (ax.iu & 15)];
+    const uint32_t* p1 = sg1 < FAST_NSIG_SMEM ? &ft.sub1s[(tl * FAST_NSIG_SMEM + sg1) * 16 + ((ax.iu >> 4) & 15)]
+                                              : &ft.sub1[(tl * FAST_NSIG + sg1) * 16 + ((ax.iu >> 4) & 15)];
+    const uint32_t w0 = *p0, w1 = *p1;                                        /* (generic loads: either address space) */
     const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
     const uint32_t fc0 = du.q[0].x & 0xFF, fc1 = (du.q[0].x >> 8) & 0xFF;
     const uint32_t mB = ft.tb[((tl * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
@@ -1682,7 +1687,9 @@ sweep_kernel(const SweepArgs a)
     uint8_t* s_tb = p3;                                                         /* [T][2][2][64] */
     uint16_t* s_gd = reinterpret_cast<uint16_t*>(s_tb + (fast_cap ? (size_t)T * 256 : 0));               /* [T][2][4] */
     TyFast* s_ty = reinterpret_cast<TyFast*>(s_gd + (fast_cap ? (size_t)T * 8 : 0));                       /* [T] */
-    uint8_t* s_mapt = reinterpret_cast<uint8_t*>(s_ty + (fast_cap ? T : 0));                               /* MAPT_BYTES (+ pad) */
+    uint32_t* s_sub0s = reinterpret_cast<uint32_t*>(s_ty + (fast_cap ? T : 0));                            /* [T][FAST_NSIG_SMEM][16] */
+    uint32_t* s_sub1s = s_sub0s + (fast_cap ? (size_t)T * FAST_NSIG_SMEM * 16 : 0);
+    uint8_t* s_mapt = reinterpret_cast<uint8_t*>(s_sub1s + (fast_cap ? (size_t)T * FAST_NSIG_SMEM * 16 : 0));   /* MAPT_BYTES (+ pad) */
     int* s_cnt = reinterpret_cast<int*>(s_mapt + (fast_cap ? ((MAPT_BYTES + 15) & ~15) : 0));              /* [T + 2] candidate counts, CPU-only pods, flag */
     uint64_t* s_touched = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_cnt) + (fast_cap ? (((size_t)(T + 2) * 4 + 15) & ~(size_t)15) : 0));   /* [W] */
     uint64_t* s_bitmaps = s_touched + W;
@@ -1704,6 +1711,11 @@ sweep_kernel(const SweepArgs a)
          * (SUB0 / SUB1: one row per NIC signature, up to FAST_NSIG of them) stay in global memory, read through L1 */
         for (int i = tid; i < (int)(ftab_small_bytes(T) / 16); i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_tb)[i] = reinterpret_cast<const uint4*>(a.ftab)[i];
+        for (int i = tid; i < T * FAST_NSIG_SMEM * 16; i += SWEEP_THREADS) {        /* rows of the first signatures */
+            const int tt = i / (FAST_NSIG_SMEM * 16), r = i % (FAST_NSIG_SMEM * 16);
+            s_sub0s[i] = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T))[tt * FAST_NSIG * 16 + r];
+            s_sub1s[i] = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T))[tt * FAST_NSIG * 16 + r];
+        }
         /* "no CPU-only pod can spill" certificate: a CPU-only pod touches one node, and a node no pod of the batch
          * was bound to keeps its exact snapshot bit; a type with more GPU-less candidates than there are CPU-only
          * pods therefore never runs out of them (or it has no candidate anywhere).  Then CPU-only pods only ever
@@ -1857,6 +1869,7 @@ sweep_kernel(const SweepArgs a)
     unsigned long long gpu_pods_mask = 0;                   /* (side by side) types whose pods CTA 1 sweeps */
     FastTables ft;
     ft.tb = s_tb; ft.mapt = s_mapt; ft.gd = s_gd; ft.ty = s_ty; ft.cls = a.cls_fast;
+    ft.sub0s = s_sub0s; ft.sub1s = s_sub1s;
     ft.sub0 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T)) : nullptr;
     ft.sub1 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T)) : nullptr;
     DynU st_none;

@@ -208,8 +208,8 @@ struct TyFast {              /* per pod type, 16 bytes */
 
 struct FastTables {
     const uint8_t* tb;       /* [T][2][2][64] */
-    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p; global memory, read through L1 */
-    const uint32_t* sub0s;   /* [T][FAST_NSIG_SMEM][16]: the rows of the first signatures, in shared memory */
+    const uint32_t* sub0;    /* [T][FAST_NSIG][16], byte p = tuple p; global memory, read through L1 (filter) */
+    const uint32_t* sub0s;   /* [T][FAST_NSIG_SMEM][16]: the rows of the first signatures, in shared memory (sweep) */
     const uint32_t* sub1s;
     const uint32_t* sub1;
     const uint8_t* mapt;     /* MAPT_BYTES */
@@ -1444,12 +1444,9 @@ __device__ __forceinline__ bool fast_eval(const FastTables& ft, int tl, const Ty
                                           double now, uint32_t& dec, DynU& da, uint32_t& iu_after)
 {
     const int smt = (du.d.info >> 1) & 1;                                     /* NHD_DYN_SMT */
-    const uint32_t sg0 = ax.sig & 0xFF, sg1 = (ax.sig >> 8) & 0xFF;
-    const uint32_t* p0 = sg0 < FAST_NSIG_SMEM ? &ft.sub0s[(tl * FAST_NSIG_SMEM + sg0) * 16 + (ax.iu & 15)]
-                                              : &ft.sub0[(tl * FAST_NSIG + sg0) * 16 + (ax.iu & 15)];
-    const uint32_t* p1 = sg1 < FAST_NSIG_SMEM ? &ft.sub1s[(tl * FAST_NSIG_SMEM + sg1) * 16 + ((ax.iu >> 4) & 15)]
-                                              : &ft.sub1[(tl * FAST_NSIG + sg1) * 16 + ((ax.iu >> 4) & 15)];
-    const uint32_t w0 = *p0, w1 = *p1;                                        /* (generic loads: either address space) */
+    /* (the sweep's rows are in shared memory: fast_node_aux admits only the first FAST_NSIG_SMEM signatures) */
+    const uint32_t w0 = ft.sub0s[(tl * FAST_NSIG_SMEM + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)];
+    const uint32_t w1 = ft.sub1s[(tl * FAST_NSIG_SMEM + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)];
     const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
     const uint32_t fc0 = du.q[0].x & 0xFF, fc1 = (du.q[0].x >> 8) & 0xFF;
     const uint32_t mB = ft.tb[((tl * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
@@ -1511,7 +1508,9 @@ __device__ __forceinline__ bool fast_node_aux(const FastTables& ft, const DynU& 
     ax.iu = ax.li0 = ax.li1 = ax.sig = 0;
     if (((du.d.info >> 2) & 7) != 2 || du.d.hw_class == NHD_NO_CLASS) return false;
     const ClsFast cf = ft.cls[du.d.hw_class];
-    if (!cf.ok) return false;
+    /* the sweep keeps the table rows of the first few NIC signatures in shared memory (a generic or global load on
+     * this chain costs 3-5 % of the whole sweep, measured); rarer signatures take the general path */
+    if (!cf.ok || cf.sig0 >= FAST_NSIG_SMEM || cf.sig1 >= FAST_NSIG_SMEM) return false;
     const uint32_t inuse = du.d.nic_inuse;
     uint32_t iu = 0;
     for (int j = 0; j < cf.n0; j++) iu |= ((inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;

@@ -1625,6 +1625,270 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
 }
 
 /*
+ * One pod on the general path (see sweep_kernel): first fit over the bitmaps, live re-validation on the node's summary,
+ * assignment, eager invalidation.  Kept out of line so that the short loop of the standing decisions is compiled on
+ * its own (registers, scheduling).  Returns the node whose summary / BUSY / touched state the pod changed, or -1.
+ */
+struct OrdState {
+    uint64_t* BM; uint64_t* NOGPU; uint64_t* BUSY; const uint64_t* GB; uint64_t* s_touched;
+    int32_t* cursors; const PodType* types;
+    int W, T;
+    bool multi, eager, cclock, fast;
+    int all_need, all_big, all_hp, all_gpus;
+    int n_busy;                       /* entries of the busy list */
+    double cur_now, busy_oldest;      /* clock the BUSY bitmap stands at; oldest stamp on the busy list */
+};
+
+template <bool SMEM_BITMAPS>
+__device__ __noinline__ int ordinary_pod(const SweepArgs& a, const SweepCtx& cx, OrdState& os, int i, int ti, double now,
+                                         unsigned long long gm)
+{
+    const int lane = cx.lane, W = os.W, T = os.T;
+    uint64_t* const BM = os.BM;
+    uint64_t* const NOGPU = os.NOGPU;
+    uint64_t* const BUSY = os.BUSY;
+    const uint64_t* const GB = os.GB;
+    uint64_t* const s_touched = os.s_touched;
+    int32_t* const cursors = os.cursors;
+    const PodType* const types = os.types;
+    const bool multi = os.multi, eager = os.eager, cclock = os.cclock, fast = os.fast;
+    const int all_need = os.all_need, all_big = os.all_big, all_hp = os.all_hp, all_gpus = os.all_gpus;
+    int& n_busy = os.n_busy;
+    double& cur_now = os.cur_now;
+    double& busy_oldest = os.busy_oldest;
+    const PodType& t = types[ti];
+    nhd_binding* bout = &a.out[i];
+    uint64_t* F = BM + (size_t)ti * W;
+    int commit_node = -1;
+    const int wid = 0;                /* (check builds name the sweeping warp) */
+    (void)wid;
+    PROF_DECL
+    do {
+
+        /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
+        if (now > cur_now && now - busy_oldest < a.min_busy) {
+            /* forwards, and not even the oldest stamp on the list has left the window: nothing changes */
+            cur_now = now;
+        } else if (now != cur_now) {
+            double oldest = 1e300;
+            if (now < cur_now) {
+                /* clock went backwards: rebuild from the summaries */
+                n_busy = 0;
+                for (int n0 = 0; n0 < W * 64; n0 += 32) {
+                    int n = n0 + lane;
+                    bool b = false;
+                    if (n < a.n_nodes) {
+                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
+                        b = (now - bt) < a.min_busy;
+                        if (b && bt < oldest) oldest = bt;
+                    }
+                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
+                    if (lane == 0) reinterpret_cast<uint32_t*>(BUSY)[n0 >> 5] = bal;
+                    if (b) a.busy_list[n_busy + popc32(bal & ((1u << lane) - 1))] = n;
+                    n_busy += popc32(bal);
+                }
+            } else {
+                int kept = 0;
+                for (int e0 = 0; e0 < n_busy; e0 += 32) {
+                    int e = e0 + lane;
+                    int n = -1;
+                    bool b = false;
+                    if (e < n_busy) {
+                        n = a.busy_list[e];
+                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
+                        b = (now - bt) < a.min_busy;
+                        if (b && bt < oldest) oldest = bt;
+                        if (!b) atomicAnd(reinterpret_cast<unsigned long long*>(&BUSY[n >> 6]), ~(1ULL << (n & 63)));
+                    }
+                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
+                    __syncwarp();
+                    if (b) a.busy_list[kept + popc32(bal & ((1u << lane) - 1))] = n;   /* kept <= e0 */
+                    __syncwarp();
+                    kept += popc32(bal);
+                }
+                n_busy = kept;
+            }
+            for (int tt = lane; tt < T; tt += 32) cursors[tt * 3 + 2] = 0;   /* busy bits may have cleared */
+            /* the oldest stamp still inside the window (stamps added from here on are newer) */
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double o = __shfl_sync(0xFFFFFFFFu, oldest, lane ^ d);
+                oldest = o < oldest ? o : oldest;
+            }
+            busy_oldest = oldest;
+            __syncwarp();
+            cur_now = now;
+        }
+
+        if (!t.valid_map) {
+            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_BAD_MAP_TYPE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
+            break;
+        }
+
+        /* ---- first fit ---- */
+        int chosen = -1;
+        bool deferred = false;
+        DynU du;
+        PMap pm = {0, 0, 0, 0};
+        Picks pk;
+        pk.fail_status = 0;
+        const bool skip_busy = t.needs_gpu != 0;                         /* Matcher.py:107-111 */
+        /* nodes whose groups intersect the pod's (NHDScheduler.py:241); all ones when the gate is in F */
+        auto elig = [&](int w) -> uint64_t {
+            if (!multi) return ~0ULL;
+            uint64_t e = 0;
+            for (unsigned long long g = gm; g; g &= g - 1)
+                e |= ldw<SMEM_BITMAPS>(&GB[(size_t)popc64(a.names_used & ((1ULL << ctz64(g)) - 1)) * W + w]);
+            return e;
+        };
+        for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
+            /* (1) the cursor: first word with any candidate of this pass */
+            int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* warps working ahead advance it too: one read for all lanes */
+            const int c_in = c;
+            uint64_t raw = 0;
+            while (c < W) {
+                raw = ldw<SMEM_BITMAPS>(&F[c]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[c]) : ~0ULL);
+                if (raw) break;
+                int found = W;
+                for (int base = c + 1; base < W; base += 32) {
+                    const int w = base + lane;
+                    const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL)) : 0;
+                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                    if (nz) { found = base + ctz32(nz); break; }
+                }
+                c = found;
+            }
+            if (c != c_in) {
+                __syncwarp();
+                if (lane == 0) cursors[ti * 3 + pass] = c;
+                __syncwarp();
+            }
+            if (c >= W) continue;
+            /* (2) candidates from there on, skipping busy nodes for GPU pods */
+            int cb = c;
+            if (skip_busy && !multi) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
+            bool first = true;
+            while (cb < W) {
+                /* first look: the cursor word was just read */
+                uint64_t word = (first && cb == c) ? raw : (ldw<SMEM_BITMAPS>(&F[cb]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[cb]) : ~0ULL));
+                first = false;
+                if (multi) word &= elig(cb);
+                if (skip_busy) word &= ~ldw<SMEM_BITMAPS>(&BUSY[cb]);
+                if (!word) {
+                    int found = W;
+                    for (int base = cb + 1; base < W; base += 32) {
+                        const int w = base + lane;
+                        uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL) & elig(w)) : 0;
+                        if (skip_busy && w < W) r &= ~ldw<SMEM_BITMAPS>(&BUSY[w]);
+                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
+                        if (nz) { found = base + ctz32(nz); break; }
+                    }
+                    cb = found;
+                    if (skip_busy && !multi) {
+                        __syncwarp();
+                        if (lane == 0) cursors[ti * 3 + 2] = cb;
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                const int node = cb * 64 + ctz64(word);
+                const uint64_t nbit = 1ULL << (node & 63);
+                PROF_MARK(1);      /* bitmap scan */
+
+                if (skip_busy && !(s_touched[cb] & nbit)) {
+                    /* no pod of this batch was bound here: the snapshot bit is exact (and the node is not
+                     * busy), so the pod is placed; what it takes is resolved later */
+                    chosen = node;
+                    deferred = true;
+                    break;
+                }
+                load_dyn(a, cx, node, du);
+                CHK_SANE(du, node, 6);
+                if (du.d.info & NHD_DYN_PENDING) {
+                    /* the pod that took this node first is still unresolved: do it now, in order */
+                    const int pj = a.pend_pod[node];
+                    const int tj = a.pod_type[pj];
+                    DynU dtmp;
+                    dtmp.q[0] = du.q[0]; dtmp.q[1] = du.q[1];
+                    resolve_pending(a, cx, tj, types[tj], node, dtmp, &a.out[pj]);
+                    du.q[0] = dtmp.q[0]; du.q[1] = dtmp.q[1];
+                    PROF_COUNT(12);
+                }
+                /* active / maintenance / node group are static inside a batch and already part of F */
+                bool missed;
+                const int state = resolve_decision(a, cx, ti, t, node, du, pm, pk, missed);
+                if (missed) { PROF_MARK(3); } else { PROF_MARK(2); }      /* summary + decision: memo miss / hit */
+                if (state >= 2) { chosen = node; break; }
+                PROF_COUNT(8);     /* stale candidate */
+                /* resources only shrink inside a batch: the node stays infeasible for this type */
+                __syncwarp();                            /* every lane has read the word */
+                if (lane == 0) bit_clear(F, node);
+                __syncwarp();
+            }
+        }
+        if (chosen < 0) {
+            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_NO_CANDIDATE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
+            break;
+        }
+        PROF_MARK(4);      /* loop exit */
+        commit_node = chosen;
+
+        bool placed = false;
+        if (deferred) {
+            /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
+            __syncwarp();                                /* every lane has read the touched word */
+            if (lane == 0) {
+                NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + chosen;
+                gd->busy_time = now;
+                atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
+                a.pend_pod[chosen] = i;
+                reinterpret_cast<uint2*>(bout)[0] = make_uint2(NHD_PENDING, (uint32_t)chosen);
+                bit_set(s_touched, chosen);
+            }
+        } else {
+            placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
+            store_dyn(a, cx, chosen, du);
+            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
+            if (lane == 0 && (du.d.n_gpus || fast)) bit_set(s_touched, chosen);
+        }
+        PROF_MARK(5);      /* assignment */
+        if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
+            const uint64_t bit = 1ULL << (chosen & 63);
+            if (!(ldw<SMEM_BITMAPS>(&BUSY[chosen >> 6]) & bit)) {
+                __syncwarp();
+                if (lane == 0) {
+                    bit_set(BUSY, chosen);
+                    if (!cclock) a.busy_list[n_busy] = chosen;
+                }
+                n_busy++;
+                if (now < busy_oldest) busy_oldest = now;
+            }
+        }
+        /* eager invalidation: pod types that can no longer fit here lose their bit now, so later
+         * pods of those types never stop at this node (exact: summary_infeasible is a necessary condition) */
+        bool roomy = false;
+        if (eager && placed) {
+            const NodeDyn& nd = du.d;
+            const int sum = nd.fc[0] + nd.fc[1] + nd.fc[2] + nd.fc[3];
+            int mx = nd.fc[0] > nd.fc[1] ? nd.fc[0] : nd.fc[1];
+            const int mx2 = nd.fc[2] > nd.fc[3] ? nd.fc[2] : nd.fc[3];
+            mx = mx > mx2 ? mx : mx2;
+            const uint32_t alln = nd.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << nd.n_nics) - 1);
+            roomy = sum >= all_need && mx >= all_big && nd.free_hugepages_gb >= all_hp && (nd.nic_inuse & alln) != alln &&
+                    (nd.n_gpus == 0 || popc32(~(uint32_t)nd.gpu_used & ((1u << nd.n_gpus) - 1)) >= all_gpus);
+        }
+        if (eager && placed && !roomy) {
+            for (int tb = 0; tb < T; tb += 32) {
+                const int tt = tb + lane;
+                if (tt < T && summary_infeasible(types[tt], du.d))
+                    bit_clear(BM + (size_t)tt * W, chosen);
+            }
+        }
+    } while (0);
+    __syncwarp();
+    return commit_node;
+}
+
+/*
  * Decision sweep.  One CTA; warp 0 walks the pods in order (all lanes execute the scalar parts
  * redundantly, so there is no intra-warp hand-off), the other warps only help to stage tables
  * into shared memory.  Per pod:
@@ -1916,8 +2180,13 @@ sweep_kernel(const SweepArgs a)
         n_busy += __shfl_sync(0xFFFFFFFFu, pre, 31);
     }
     __syncwarp();
-    double cur_now = a.n_pods > 0 ? a.now[0] : 0.0;
-    double busy_oldest = -1e300;          /* oldest stamp on the busy list; unknown for the snapshot's list: first clock step scans */
+    OrdState os;
+    os.BM = BM; os.NOGPU = NOGPU; os.BUSY = BUSY; os.GB = GB; os.s_touched = s_touched; os.cursors = cursors; os.types = types;
+    os.W = W; os.T = T; os.multi = multi; os.eager = eager; os.cclock = cclock; os.fast = fast;
+    os.all_need = all_need; os.all_big = all_big; os.all_hp = all_hp; os.all_gpus = all_gpus;
+    os.n_busy = n_busy;
+    os.cur_now = a.n_pods > 0 ? a.now[0] : 0.0;
+    os.busy_oldest = -1e300;              /* oldest stamp on the busy list; unknown for the snapshot's list: first clock step scans */
     PROF_DECL
 
     for (int i0 = 0; i0 < a.n_pods; i0 += 32) {
@@ -2017,227 +2286,7 @@ sweep_kernel(const SweepArgs a)
             }
         }
         PROF_MARK(0);      /* pod header / standing decision */
-        if (!handled) do {
-
-        /* ---- busy window bookkeeping when the clock moved (Node.py:847-850) ---- */
-        if (now > cur_now && now - busy_oldest < a.min_busy) {
-            /* forwards, and not even the oldest stamp on the list has left the window: nothing changes */
-            cur_now = now;
-        } else if (now != cur_now) {
-            double oldest = 1e300;
-            if (now < cur_now) {
-                /* clock went backwards: rebuild from the summaries */
-                n_busy = 0;
-                for (int n0 = 0; n0 < W * 64; n0 += 32) {
-                    int n = n0 + lane;
-                    bool b = false;
-                    if (n < a.n_nodes) {
-                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
-                        b = (now - bt) < a.min_busy;
-                        if (b && bt < oldest) oldest = bt;
-                    }
-                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
-                    if (lane == 0) reinterpret_cast<uint32_t*>(BUSY)[n0 >> 5] = bal;
-                    if (b) a.busy_list[n_busy + popc32(bal & ((1u << lane) - 1))] = n;
-                    n_busy += popc32(bal);
-                }
-            } else {
-                int kept = 0;
-                for (int e0 = 0; e0 < n_busy; e0 += 32) {
-                    int e = e0 + lane;
-                    int n = -1;
-                    bool b = false;
-                    if (e < n_busy) {
-                        n = a.busy_list[e];
-                        double bt = __ldcg(&reinterpret_cast<const NodeDyn*>(a.dyn)[n].busy_time);
-                        b = (now - bt) < a.min_busy;
-                        if (b && bt < oldest) oldest = bt;
-                        if (!b) atomicAnd(reinterpret_cast<unsigned long long*>(&BUSY[n >> 6]), ~(1ULL << (n & 63)));
-                    }
-                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, b);
-                    __syncwarp();
-                    if (b) a.busy_list[kept + popc32(bal & ((1u << lane) - 1))] = n;   /* kept <= e0 */
-                    __syncwarp();
-                    kept += popc32(bal);
-                }
-                n_busy = kept;
-            }
-            for (int tt = lane; tt < T; tt += 32) cursors[tt * 3 + 2] = 0;   /* busy bits may have cleared */
-            /* the oldest stamp still inside the window (stamps added from here on are newer) */
-            for (int d = 16; d >= 1; d >>= 1) {
-                const double o = __shfl_sync(0xFFFFFFFFu, oldest, lane ^ d);
-                oldest = o < oldest ? o : oldest;
-            }
-            busy_oldest = oldest;
-            __syncwarp();
-            cur_now = now;
-        }
-
-        if (!t.valid_map) {
-            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_BAD_MAP_TYPE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
-            break;
-        }
-
-        /* ---- first fit ---- */
-        int chosen = -1;
-        bool deferred = false;
-        DynU du;
-        PMap pm = {0, 0, 0, 0};
-        Picks pk;
-        pk.fail_status = 0;
-        const bool skip_busy = t.needs_gpu != 0;                         /* Matcher.py:107-111 */
-        /* nodes whose groups intersect the pod's (NHDScheduler.py:241); all ones when the gate is in F */
-        auto elig = [&](int w) -> uint64_t {
-            if (!multi) return ~0ULL;
-            uint64_t e = 0;
-            for (unsigned long long g = gm; g; g &= g - 1)
-                e |= ldw<SMEM_BITMAPS>(&GB[(size_t)popc64(a.names_used & ((1ULL << ctz64(g)) - 1)) * W + w]);
-            return e;
-        };
-        for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
-            /* (1) the cursor: first word with any candidate of this pass */
-            int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* warps working ahead advance it too: one read for all lanes */
-            const int c_in = c;
-            uint64_t raw = 0;
-            while (c < W) {
-                raw = ldw<SMEM_BITMAPS>(&F[c]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[c]) : ~0ULL);
-                if (raw) break;
-                int found = W;
-                for (int base = c + 1; base < W; base += 32) {
-                    const int w = base + lane;
-                    const uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL)) : 0;
-                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
-                    if (nz) { found = base + ctz32(nz); break; }
-                }
-                c = found;
-            }
-            if (c != c_in) {
-                __syncwarp();
-                if (lane == 0) cursors[ti * 3 + pass] = c;
-                __syncwarp();
-            }
-            if (c >= W) continue;
-            /* (2) candidates from there on, skipping busy nodes for GPU pods */
-            int cb = c;
-            if (skip_busy && !multi) { const int c2 = cursors[ti * 3 + 2]; cb = c2 > c ? c2 : c; }
-            bool first = true;
-            while (cb < W) {
-                /* first look: the cursor word was just read */
-                uint64_t word = (first && cb == c) ? raw : (ldw<SMEM_BITMAPS>(&F[cb]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[cb]) : ~0ULL));
-                first = false;
-                if (multi) word &= elig(cb);
-                if (skip_busy) word &= ~ldw<SMEM_BITMAPS>(&BUSY[cb]);
-                if (!word) {
-                    int found = W;
-                    for (int base = cb + 1; base < W; base += 32) {
-                        const int w = base + lane;
-                        uint64_t r = (w < W) ? (ldw<SMEM_BITMAPS>(&F[w]) & (pass == 0 ? ldw<SMEM_BITMAPS>(&NOGPU[w]) : ~0ULL) & elig(w)) : 0;
-                        if (skip_busy && w < W) r &= ~ldw<SMEM_BITMAPS>(&BUSY[w]);
-                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, r != 0);
-                        if (nz) { found = base + ctz32(nz); break; }
-                    }
-                    cb = found;
-                    if (skip_busy && !multi) {
-                        __syncwarp();
-                        if (lane == 0) cursors[ti * 3 + 2] = cb;
-                        __syncwarp();
-                    }
-                    continue;
-                }
-                const int node = cb * 64 + ctz64(word);
-                const uint64_t nbit = 1ULL << (node & 63);
-                PROF_MARK(1);      /* bitmap scan */
-
-                if (skip_busy && !(s_touched[cb] & nbit)) {
-                    /* no pod of this batch was bound here: the snapshot bit is exact (and the node is not
-                     * busy), so the pod is placed; what it takes is resolved later */
-                    chosen = node;
-                    deferred = true;
-                    break;
-                }
-                load_dyn(a, cx, node, du);
-                CHK_SANE(du, node, 6);
-                if (du.d.info & NHD_DYN_PENDING) {
-                    /* the pod that took this node first is still unresolved: do it now, in order */
-                    const int pj = a.pend_pod[node];
-                    const int tj = a.pod_type[pj];
-                    DynU dtmp;
-                    dtmp.q[0] = du.q[0]; dtmp.q[1] = du.q[1];
-                    resolve_pending(a, cx, tj, types[tj], node, dtmp, &a.out[pj]);
-                    du.q[0] = dtmp.q[0]; du.q[1] = dtmp.q[1];
-                    PROF_COUNT(12);
-                }
-                /* active / maintenance / node group are static inside a batch and already part of F */
-                bool missed;
-                const int state = resolve_decision(a, cx, ti, t, node, du, pm, pk, missed);
-                if (missed) { PROF_MARK(3); } else { PROF_MARK(2); }      /* summary + decision: memo miss / hit */
-                if (state >= 2) { chosen = node; break; }
-                PROF_COUNT(8);     /* stale candidate */
-                /* resources only shrink inside a batch: the node stays infeasible for this type */
-                __syncwarp();                            /* every lane has read the word */
-                if (lane == 0) bit_clear(F, node);
-                __syncwarp();
-            }
-        }
-        if (chosen < 0) {
-            if (lane < 8) reinterpret_cast<uint4*>(bout)[lane] = make_uint4(lane == 0 ? NHD_NO_CANDIDATE : 0, lane == 0 ? 0xFFFFFFFFu : 0, lane == 0 ? t.G : 0, 0);
-            break;
-        }
-        PROF_MARK(4);      /* loop exit */
-        commit_node = chosen;
-
-        bool placed = false;
-        if (deferred) {
-            /* stamp the node (NHDScheduler.py:289) and leave a note for resolve_kernel / a later visitor */
-            __syncwarp();                                /* every lane has read the touched word */
-            if (lane == 0) {
-                NodeDyn* gd = reinterpret_cast<NodeDyn*>(a.dyn) + chosen;
-                gd->busy_time = now;
-                atomicOr(reinterpret_cast<unsigned int*>(&gd->gpu_used), (unsigned int)(NHD_DYN_TOUCHED | NHD_DYN_PENDING) << 16);
-                a.pend_pod[chosen] = i;
-                reinterpret_cast<uint2*>(bout)[0] = make_uint2(NHD_PENDING, (uint32_t)chosen);
-                bit_set(s_touched, chosen);
-            }
-        } else {
-            placed = apply_decision(cx, t, chosen, du.d, pm, pk, now, bout);
-            store_dyn(a, cx, chosen, du);
-            /* the touched / BUSY bitmaps are only ever consulted for GPU pods, which cannot fit a GPU-less node */
-            if (lane == 0 && (du.d.n_gpus || fast)) bit_set(s_touched, chosen);
-        }
-        PROF_MARK(5);      /* assignment */
-        if (a.min_busy > 0.0 && (deferred || du.d.n_gpus)) {             /* now - busy_time == 0 < MIN_BUSY_SECS */
-            const uint64_t bit = 1ULL << (chosen & 63);
-            if (!(ldw<SMEM_BITMAPS>(&BUSY[chosen >> 6]) & bit)) {
-                __syncwarp();
-                if (lane == 0) {
-                    bit_set(BUSY, chosen);
-                    if (!cclock) a.busy_list[n_busy] = chosen;
-                }
-                n_busy++;
-                if (now < busy_oldest) busy_oldest = now;
-            }
-        }
-        /* eager invalidation: pod types that can no longer fit here lose their bit now, so later
-         * pods of those types never stop at this node (exact: summary_infeasible is a necessary condition) */
-        bool roomy = false;
-        if (eager && placed) {
-            const NodeDyn& nd = du.d;
-            const int sum = nd.fc[0] + nd.fc[1] + nd.fc[2] + nd.fc[3];
-            int mx = nd.fc[0] > nd.fc[1] ? nd.fc[0] : nd.fc[1];
-            const int mx2 = nd.fc[2] > nd.fc[3] ? nd.fc[2] : nd.fc[3];
-            mx = mx > mx2 ? mx : mx2;
-            const uint32_t alln = nd.n_nics >= 32 ? 0xFFFFFFFFu : ((1u << nd.n_nics) - 1);
-            roomy = sum >= all_need && mx >= all_big && nd.free_hugepages_gb >= all_hp && (nd.nic_inuse & alln) != alln &&
-                    (nd.n_gpus == 0 || popc32(~(uint32_t)nd.gpu_used & ((1u << nd.n_gpus) - 1)) >= all_gpus);
-        }
-        if (eager && placed && !roomy) {
-            for (int tb = 0; tb < T; tb += 32) {
-                const int tt = tb + lane;
-                if (tt < T && summary_infeasible(types[tt], du.d))
-                    bit_clear(BM + (size_t)tt * W, chosen);
-            }
-        }
-        } while (0);
+        if (!handled) commit_node = ordinary_pod<SMEM_BITMAPS>(a, cx, os, i, ti, now, gm);
         __syncwarp();
         if (fast) {
             if (fast_commit) {

@@ -172,7 +172,7 @@ typedef struct nhd_params {
     int32_t  rank;                   /* node-shard rank, 0 when single GPU                     */
     int32_t  world_size;             /* number of GPUs sharing the node set                    */
     int32_t  reserved_;              /* 0.  Test hook: low byte 1 = the general one-warp sweep only, 2 = never sweep the two pod
-                                      * classes side by side; bit 8 = no standing decisions, bit 9 = same as 2;
+                                      * classes side by side; bit 8 = no standing decisions, bit 9 = same as 2, bit 10 = no direct-path tables;
                                       * all settings produce identical bindings (tests/test_gpu_parity.py)      */
     uint8_t  nccl_unique_id[128];    /* from nhd_nccl_unique_id() on rank 0; unused if world_size==1 */
 } nhd_params;

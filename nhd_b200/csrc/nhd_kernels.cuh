@@ -893,6 +893,7 @@ struct SweepCtx {
     struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 48 B: static NIC layout per hardware class */
     int* clsnic_lock;
     uint4* spmemo;           /* SPMEMO_SLOTS x 16 B: first surviving NIC assignment of (type, groups S, NUMA k, NICs in use there) */
+    const FastTables* ft;    /* direct-path tables (null when the batch has too many pod types) */
 };
 
 union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
@@ -1259,11 +1260,19 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
  * Returns 1 (FindNode would not offer the node), 2 (placed) or 3 (SetPhysicalIdsFromMapping
  * fails) plus the mapping and the resource picks.  Decision memo first, full evaluation on a miss.
  */
+__device__ __forceinline__ int direct_single(const SweepCtx& cx, int ti, const DynU& du, PMap& pm, Picks& pk);
+
 __device__ __forceinline__ int resolve_decision(const SweepArgs& a, const SweepCtx& cx, int ti, const PodType& t, int node,
                                                 const DynU& du, PMap& pm, Picks& pk, bool& missed)
 {
     missed = false;
     if (summary_infeasible(t, du.d)) return 1;
+    if (cx.ft) {
+        /* CPU-only NUMA-mode type with <= 2 groups on a classed 2-NUMA node: the table-driven evaluation of the
+         * standing decisions, for this one (type, node) — every lane computes the same */
+        const int st = direct_single(cx, ti, du, pm, pk);
+        if (st) return st;
+    }
     const bool fast2 = cx.s_needb && t.total_gpus == 0 && !t.pci && ((du.d.info >> 2) & 7) == 2 && du.d.hw_class != NHD_NO_CLASS && ti < 4096;
     if (fast2) return resolve_cpu2(a, cx, ti, t, node, du, pm, pk, missed);    /* CPU-only pod on a 2-NUMA node: direct */
     const bool smt = (du.d.info & NHD_DYN_SMT) != 0;
@@ -1440,13 +1449,17 @@ struct NodeAux { uint32_t iu, li0, li1, sig; };
  * (SetBusy + the bookkeeping of SetPhysicalIdsFromMapping, Node.py:663-841, + ClaimPodNICResources) and the NICs
  * in use afterwards.
  */
+template <bool SUB_SMEM>
 __device__ __forceinline__ bool fast_eval(const FastTables& ft, int tl, const TyFast& ty, const DynU& du, const NodeAux& ax,
                                           double now, uint32_t& dec, DynU& da, uint32_t& iu_after)
 {
     const int smt = (du.d.info >> 1) & 1;                                     /* NHD_DYN_SMT */
-    /* (the sweep's rows are in shared memory: fast_node_aux admits only the first FAST_NSIG_SMEM signatures) */
-    const uint32_t w0 = ft.sub0s[(tl * FAST_NSIG_SMEM + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)];
-    const uint32_t w1 = ft.sub1s[(tl * FAST_NSIG_SMEM + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)];
+    /* the standing decisions read the rows in shared memory (fast_node_aux admits only the first FAST_NSIG_SMEM
+     * signatures there); the general path reads any signature's row from global memory */
+    const uint32_t w0 = SUB_SMEM ? ft.sub0s[(tl * FAST_NSIG_SMEM + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)]
+                                 : __ldg(&ft.sub0[(tl * FAST_NSIG + (ax.sig & 0xFF)) * 16 + (ax.iu & 15)]);
+    const uint32_t w1 = SUB_SMEM ? ft.sub1s[(tl * FAST_NSIG_SMEM + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)]
+                                 : __ldg(&ft.sub1[(tl * FAST_NSIG + ((ax.sig >> 8) & 0xFF)) * 16 + ((ax.iu >> 4) & 15)]);
     const uint32_t mC = gather_b7(w0 & w1);                                   /* Matcher.py:242-276 */
     const uint32_t fc0 = du.q[0].x & 0xFF, fc1 = (du.q[0].x >> 8) & 0xFF;
     const uint32_t mB = ft.tb[((tl * 2 + smt) * 2 + 0) * 64 + (fc0 < 63 ? fc0 : 63)] &
@@ -1503,14 +1516,14 @@ __device__ __forceinline__ void fast_load_dyn(const SweepArgs& a, const SweepCtx
 }
 
 /* class entry and compact in-use bits of a node with summary du; false when the direct path does not cover it */
-__device__ __forceinline__ bool fast_node_aux(const FastTables& ft, const DynU& du, NodeAux& ax)
+__device__ __forceinline__ bool fast_node_aux(const FastTables& ft, const DynU& du, NodeAux& ax, bool smem_rows = true)
 {
     ax.iu = ax.li0 = ax.li1 = ax.sig = 0;
     if (((du.d.info >> 2) & 7) != 2 || du.d.hw_class == NHD_NO_CLASS) return false;
     const ClsFast cf = ft.cls[du.d.hw_class];
     /* the sweep keeps the table rows of the first few NIC signatures in shared memory (a generic or global load on
      * this chain costs 3-5 % of the whole sweep, measured); rarer signatures take the general path */
-    if (!cf.ok || cf.sig0 >= FAST_NSIG_SMEM || cf.sig1 >= FAST_NSIG_SMEM) return false;
+    if (!cf.ok || (smem_rows && (cf.sig0 >= FAST_NSIG_SMEM || cf.sig1 >= FAST_NSIG_SMEM))) return false;
     const uint32_t inuse = du.d.nic_inuse;
     uint32_t iu = 0;
     for (int j = 0; j < cf.n0; j++) iu |= ((inuse >> ((cf.li0 >> (8 * j)) & 31)) & 1u) << j;
@@ -1518,6 +1531,36 @@ __device__ __forceinline__ bool fast_node_aux(const FastTables& ft, const DynU& 
     ax.iu = iu; ax.li0 = cf.li0; ax.li1 = cf.li1;
     ax.sig = (uint32_t)cf.sig0 | ((uint32_t)cf.sig1 << 8) | ((uint32_t)cf.n0 << 16) | ((uint32_t)cf.n1 << 24);
     return true;
+}
+
+/* resolve_decision's direct case: 0 = not covered by the tables, 1 = FindNode would not offer the node, 2 = placed
+ * (mapping and picks filled in like resolve_cpu2 does) */
+__device__ __forceinline__ int direct_single(const SweepCtx& cx, int ti, const DynU& du, PMap& pm, Picks& pk)
+{
+    const FastTables& ft = *cx.ft;
+    const TyFast ty = ft.ty[ti];
+    if (!ty.direct) return 0;
+    NodeAux ax;
+    if (!fast_node_aux(ft, du, ax, false)) return 0;
+    uint32_t dec = 0, iu2 = 0;
+    DynU da;
+    if (!fast_eval<false>(ft, ti, ty, du, ax, 0.0, dec, da, iu2)) return 1;
+    const int G = ty.G, ps = dec & 3;
+    const uint32_t e0 = (dec >> 8) & 0xFF, e1 = (dec >> 16) & 0xFF;
+    uint32_t pn = 0, idx = 0, li = 0, rec = 0;
+    int n_rec = 0, k0 = 0, k1 = 0;
+    for (int g = 0; g < G; g++) {
+        const int numa = (ps >> (G - 1 - g)) & 1;
+        const uint32_t x = numa ? (e1 >> (2 * k1++)) & 3 : (e0 >> (2 * k0++)) & 3;
+        const uint32_t l = ((numa ? ax.li1 : ax.li0) >> (8 * x)) & 31;             /* NodeNic.idx -> index in Node.nics */
+        pn |= (uint32_t)numa << (8 * g); idx |= x << (8 * g); li |= l << (8 * g);
+        if ((ty.nic_groups >> g) & 1) { rec |= l << (8 * n_rec); n_rec++; }
+    }
+    pm.pn = pn; pm.idx = idx; pm.li = li; pm.ms = (dec >> 2) & 1;
+    pk.claimed = claimed_order_packed(rec, n_rec, pk.ncl);                          /* NHDScheduler.py:302 */
+    pk.gi_lo = pk.gi_hi = 0; pk.ng = 0; pk.fail_status = 0;
+    pk.gpu_used_new = du.d.gpu_used;
+    return 2;
 }
 
 /* per-lane standing decision (lane t = pod type t), kept in registers */
@@ -1565,7 +1608,7 @@ __device__ __forceinline__ void lanes_refresh(const SweepArgs& a, const SweepCtx
             PROF_ADD(1, __popc(__ballot_sync(0xFFFFFFFFu, need)));      /* lanes evaluating */
             uint32_t dec = 0, iu2 = 0;
             DynU da;
-            const bool feas = fast_eval(ft, tl, ty, cur, cax, now, dec, da, iu2);
+            const bool feas = fast_eval<true>(ft, tl, ty, cur, cax, now, dec, da, iu2);
             if (need) {
                 if (feas) {
                     if (pointing) {
@@ -1915,6 +1958,7 @@ sweep_kernel(const SweepArgs a)
     const int dbg = a.n_cpu_warps >> 8;       /* debug switch: 1 = no standing decisions (ordinary path for every pod) */
     SweepCtx cx;
     cx.lane = lane;
+    cx.ft = nullptr;
     cx.smemo_mask = SMEMO_SLOTS - 1;
     cx.dmemo_mask = DMEMO_SLOTS - 1;
     cx.spmemo_mask = SPMEMO_SLOTS - 1;
@@ -1965,8 +2009,9 @@ sweep_kernel(const SweepArgs a)
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
     if (tid < 4) misc[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
-    const bool fast = fast_cap && a.ftab != nullptr && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
-    if (fast) {
+    const bool have_tables = fast_cap && a.ftab != nullptr && !(dbg & 4);
+    const bool fast = have_tables && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
+    if (have_tables) {
         for (int i = tid; i < (MAPT_BYTES + 15) / 16; i += SWEEP_THREADS)
             reinterpret_cast<uint4*>(s_mapt)[i] = reinterpret_cast<const uint4*>(a.mapt)[i];
         /* the direct-path tables of this batch's pod types (fast_tables_kernel): one contiguous copy; the
@@ -1979,6 +2024,8 @@ sweep_kernel(const SweepArgs a)
             s_sub0s[i] = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T))[tt * FAST_NSIG * 16 + r];
             s_sub1s[i] = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T))[tt * FAST_NSIG * 16 + r];
         }
+    }
+    if (fast) {
         /* "no CPU-only pod can spill" certificate: a CPU-only pod touches one node, and a node no pod of the batch
          * was bound to keeps its exact snapshot bit; a type with more GPU-less candidates than there are CPU-only
          * pods therefore never runs out of them (or it has no candidate anywhere).  Then CPU-only pods only ever
@@ -2135,6 +2182,11 @@ sweep_kernel(const SweepArgs a)
     ft.sub0s = s_sub0s; ft.sub1s = s_sub1s;
     ft.sub0 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub0(T)) : nullptr;
     ft.sub1 = a.ftab ? reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T)) : nullptr;
+#ifdef NHD_CHECKS
+    cx.ft = nullptr;                 /* check builds re-derive the standing decisions with the independent warp-wide evaluation */
+#else
+    cx.ft = have_tables ? &ft : nullptr;
+#endif
     DynU st_none;
     st_none.q[0] = make_uint4(0, 0, 0, 0); st_none.q[1] = st_none.q[0];
     NodeAux ax_none = {0, 0, 0, 0};

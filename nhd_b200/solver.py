@@ -64,7 +64,7 @@ class Solver:
         p.device, p.rank, p.world_size = device, rank, world_size
         # test knobs (all settings produce identical bindings): single_warp = the general one-warp sweep only;
         # cpu_warps = 1: never sweep the two pod classes side by side; sweep_debug bit 0: no standing decisions,
-        # bit 1: same as cpu_warps = 1
+        # bit 1: same as cpu_warps = 1, bit 2: no direct-path tables in the sweep (warp-wide evaluation everywhere)
         p.reserved_ = (1 if single_warp else (cpu_warps + 1 if cpu_warps else 0)) | \
             ((int(sweep_debug) | int(os.environ.get('NHD_SWEEP_DEBUG', '0'))) << 8)
         if world_size > 1:

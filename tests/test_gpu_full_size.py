@@ -23,7 +23,7 @@ pytestmark = [pytest.mark.gpu,
                                         '(tools/emu_full_size.py does them)')]
 
 THREADS = max(1, os.cpu_count() or 1)
-MODES = (dict(), dict(single_warp=True), dict(cpu_warps=1), dict(sweep_debug=1))
+MODES = (dict(), dict(single_warp=True), dict(cpu_warps=1), dict(sweep_debug=1), dict(sweep_debug=5))
 
 
 def _cuda(recs, speed, pods, now, **mode):

@@ -26,7 +26,8 @@ def _run_cuda(solver_mod, recs, speed, pods, now, min_busy=30.0, extra_cpu_warps
     outs = []
     modes = ((False, 0, 0), (True, 0, 0)) + tuple((False, c, 0) for c in extra_cpu_warps)
     if extra_cpu_warps:
-        modes += ((False, 0, 1),)              # constant-clock sweep without standing decisions
+        modes += ((False, 0, 1),               # constant-clock sweep without standing decisions (general path, table-driven evaluation)
+                  (False, 0, 5))               # ... and without the direct-path tables (warp-wide evaluation)
     for single, cw, dbg in modes:
         s = solver_mod.Solver(speed, min_busy_secs=min_busy, single_warp=single, cpu_warps=cw, sweep_debug=dbg)
         try:

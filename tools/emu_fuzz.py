@@ -25,7 +25,7 @@ from nhd_b200.solver import Solver                      # noqa: E402
 from oracle import binding                              # noqa: E402
 from tests import helpers, ref_compare, scenarios       # noqa: E402
 
-MODES = [dict(), dict(single_warp=True), dict(cpu_warps=1), dict(sweep_debug=1), dict(), dict(cpu_warps=1), dict()]
+MODES = [dict(), dict(single_warp=True), dict(cpu_warps=1), dict(sweep_debug=1), dict(sweep_debug=5), dict(cpu_warps=1), dict()]
 if os.environ.get('EMU_FUZZ_MODES'):                    # e.g. "1,2": only the one-warp sweep and one CPU-class warp
     MODES = [MODES[int(i)] for i in os.environ['EMU_FUZZ_MODES'].split(',')]
 

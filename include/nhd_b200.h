@@ -31,7 +31,8 @@ extern "C" {
 /* ---- limits of the packed layout (checked by nhd_validate_*) -------------- */
 #define NHD_MAX_NUMA           4    /* Node.numa_nodes (== sockets, Node.py:336)      */
 #define NHD_MAX_GROUPS         4    /* len(CfgTopology.proc_groups)                   */
-#define NHD_MAX_TUPLES         256  /* numa^(groups+1) must not exceed this           */
+#define NHD_MAX_TUPLES         256  /* numa^(groups+1) must not exceed this; numa = the largest NUMA count among the
+                                        nodes the filter could accept (active, not in maintenance) at staging time */
 #define NHD_MAX_GPUS           16   /* len(Node.gpus)                                 */
 #define NHD_MAX_NICS           32   /* len(Node.nics) (schedulable NICs / VFs)        */
 #define NHD_MAX_LCORES         256  /* len(Node.cores) (logical cores)                */

@@ -71,6 +71,10 @@ struct nhd_handle {
 
     /* cluster mirror */
     int n_nodes = 0, n_super = 0, words = 0, max_numa = 1;
+    /* NUMA count of every node the filter could accept (active, not in maintenance; 0 otherwise): the mapping stage's
+       tuple limits are judged against the largest of these, and follow updates in both directions */
+    std::vector<uint8_t> node_numa;
+    int numa_hist[NHD_MAX_NUMA + 1] = {0, 0, 0, 0, 0};
     uint8_t* d_nodes = nullptr;
     uint8_t* d_snapshot = nullptr;
     size_t nodes_bytes = 0;
@@ -193,6 +197,24 @@ static bool tuple_limits_ok(int K, int G)
     for (int i = 0; i < G + 1; i++) nq *= K;
     for (int i = 0; i < G; i++) np *= K;
     return nq <= NHD_MAX_TUPLES && np <= 64;
+}
+
+static inline uint8_t schedulable_numa(const nhd_node_rec& r)
+{
+    return ((r.flags & NHD_NODE_ACTIVE) && !(r.flags & NHD_NODE_MAINTENANCE)) ? (uint8_t)r.n_numa : (uint8_t)0;
+}
+
+static void track_numa(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx)
+{
+    for (int i = 0; i < n; i++) {
+        const int node = idx ? idx[i] : i;
+        const uint8_t k = schedulable_numa(recs[i]);
+        h->numa_hist[h->node_numa[node]]--;
+        h->numa_hist[k]++;
+        h->node_numa[node] = k;
+    }
+    h->max_numa = 1;
+    for (int k = 2; k <= NHD_MAX_NUMA; k++) if (h->numa_hist[k] > 0) h->max_numa = k;
 }
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -398,11 +420,14 @@ extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node
     h->have_snapshot = false;
     h->staged = h->solved = false;
     h->max_numa = 1;
+    h->node_numa.assign((size_t)n_nodes, 0);
+    for (int k = 0; k <= NHD_MAX_NUMA; k++) h->numa_hist[k] = 0;
+    h->numa_hist[0] = n_nodes;
     if (n_nodes == 0) { CK(cudaStreamSynchronize(h->stream)); return NHD_OK; }
     int mx = 1;
     const int32_t rc = upload_records(h, n_nodes, recs, nullptr, &mx);
     if (rc != NHD_OK) { h->loaded = false; return rc; }
-    h->max_numa = mx;
+    track_numa(h, n_nodes, recs, nullptr);
     return NHD_OK;
 }
 
@@ -424,7 +449,7 @@ extern "C" int32_t nhd_update_nodes(nhd_handle* h, int32_t n, const int32_t* idx
     if (n == 0) return NHD_OK;
     int mx = 1;
     const int32_t rc = upload_records(h, n, recs, idx, &mx);
-    if (rc == NHD_OK) h->max_numa = std::max(h->max_numa, mx);
+    if (rc == NHD_OK) track_numa(h, n, recs, idx);
     return rc;
 }
 

@@ -285,3 +285,48 @@ def test_edge_cases_empty_and_rejected_inputs(oracle_lib, solver_mod):
         assert helpers.binding_bytes_equal(ob, cb) and s.read_nodes().tobytes() == orecs.tobytes()
     finally:
         s.close()
+
+
+def test_tuple_limit_follows_the_schedulable_nodes(oracle_lib, solver_mod):
+    """numa^(groups+1) <= NHD_MAX_TUPLES is judged against the nodes the filter could accept: a 4-socket node that is
+    inactive (or in maintenance) does not make 4-group pods unsupported cluster-wide, and the limit follows updates in
+    both directions (Matcher.py:73-75 never looks at such a node either)."""
+    from nhd_b200 import wire
+    def nics(sockets):
+        return [(f'vf{i}', 100000, i % sockets, 0x10 * (i % sockets + 1)) for i in range(2 * sockets)]
+    nodes = [scenarios.make_node('a', sockets=2, phys_cores=32, nics=nics(2)),
+             scenarios.make_node('b', sockets=4, phys_cores=64, nics=nics(4)),
+             scenarios.make_node('c', sockets=2, phys_cores=32, nics=nics(2))]
+    pod4 = scenarios.make_pod([scenarios.make_group(pairs=((5, 5),), workers=1) for _ in range(4)], misc=1)
+    pod2 = scenarios.make_pod([scenarios.make_group(pairs=((5, 5),), workers=2) for _ in range(2)], misc=1)
+    scn = {'nodes': nodes, 'pods': [pod4, pod2, pod4, pod2], 'now': [1000.0] * 4, 'min_busy_secs': 0.0}
+    recs, pods, now, layout = ref_compare.pack_scenario(scn)
+    speed = layout.speed_table()
+    off = recs.copy()
+    off['flags'][1] &= 0xFF ^ wire.NODE_ACTIVE
+    maint = recs.copy()
+    maint['flags'][1] |= wire.NODE_MAINTENANCE
+    s = solver_mod.Solver(speed, min_busy_secs=0.0)
+    try:
+        for variant in (off, maint):
+            s.load_nodes(variant)
+            ob, orecs = oracle_lib.solve(variant, speed, pods, now, min_busy_secs=0.0)
+            cb = s.solve_batch(pods, now)
+            assert helpers.binding_bytes_equal(ob, cb), helpers.first_binding_diff(ob, cb)
+            assert s.read_nodes().tobytes() == orecs.tobytes()
+            assert (cb['status'] == 0).all() and (cb['node'] != 1).all()
+        s.load_nodes(off)
+        s.update_nodes(np.array([1], dtype=np.int32), recs[1:2])              # the 4-socket node comes back
+        with pytest.raises(solver_mod.SolverError) as ei:
+            s.solve_batch(pods, now)
+        assert ei.value.code == -2
+        two = s.solve_batch(pods[1::2], now[1::2])                            # 2-group pods: 4^3 = 64 tuples, fine
+        ob, _ = oracle_lib.solve(recs, speed, pods[1::2], now[1::2], min_busy_secs=0.0)
+        assert helpers.binding_bytes_equal(ob, two)
+        s.load_nodes(recs)
+        s.update_nodes(np.array([1], dtype=np.int32), off[1:2])               # ... and leaves again: the limit shrinks
+        ob, orecs = oracle_lib.solve(off, speed, pods, now, min_busy_secs=0.0)
+        cb = s.solve_batch(pods, now)
+        assert helpers.binding_bytes_equal(ob, cb) and s.read_nodes().tobytes() == orecs.tobytes()
+    finally:
+        s.close()

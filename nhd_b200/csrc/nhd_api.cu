@@ -718,16 +718,11 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.nodes = h->d_nodes; sa.types = h->d_types; sa.pod_type = h->d_pod_type; sa.now = h->d_now; sa.out = h->d_out;
         sa.n_pods = h->n_pods; sa.n_types = T; sa.n_nodes = h->n_nodes; sa.words = W;
         sa.n_names = h->n_names; sa.names_used = h->names_used; sa.pod_groups = h->d_pod_groups;
-        /* reserved_: 0 default (NHD_DEFAULT_CPU_WARPS speculating CPU-class warps + 1 GPU-class warp on a constant
-         * clock), 1 forces the single-warp sweep, 2..8 select 1..7 CPU-class warps (tests compare them byte for byte) */
+        /* reserved_ (test knobs; every setting gives the same bindings): low byte 0 = default, 1 = the general one-warp
+         * sweep only (no standing decisions), 2 = standing decisions but never the two pod classes side by side;
+         * bits 8.. = debug switches of sweep_kernel */
         sa.dual = (h->const_clock && (h->params.reserved_ & 0xFF) != 1) ? 1 : 0;
-        {
-            const int r = h->params.reserved_ & 0xFF, flags = h->params.reserved_ >> 8;
-            /* working ahead needs the node-group gate folded into the pod types (one distinct group list in the
-             * batch); otherwise the CPU-only class stays on one warp */
-            const int dflt = h->n_names > 0 ? 1 : NHD_DEFAULT_CPU_WARPS;
-            sa.n_cpu_warps = ((r >= 2 && r <= 8) ? r - 1 : dflt) | (flags << 8);
-        }
+        sa.sweep_flags = ((h->params.reserved_ & 0xFF) == 2 ? 1 : 0) | ((h->params.reserved_ >> 8) << 8);
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
         sa.mapt = h->d_mapt; sa.sigs = h->d_sigs; sa.cls_fast = h->d_cls_fast;

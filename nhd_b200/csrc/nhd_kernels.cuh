@@ -595,7 +595,7 @@ __global__ void unpack_slots_kernel(const uint4* __restrict__ xchg, int ws, int 
 #endif
 
 #ifdef NHD_CHECKS
-/* debugging aid: first violated invariant of the multi-warp sweep -> prof[56..63] */
+/* debugging aid: first directly committed decision the general path disagrees with -> prof[56..63] */
 #define CHK_FAIL(code, x0, x1, x2) do { if (lane == 0 && atomicCAS(&a.prof[56], 0ULL, (unsigned long long)(code)) == 0ULL) { \
     a.prof[57] = (unsigned long long)(x0); a.prof[58] = (unsigned long long)(x1); a.prof[59] = (unsigned long long)(x2); a.prof[60] = (unsigned long long)wid; a.prof[61] = (unsigned long long)i; __threadfence_system(); } } while (0)
 #define CHK_SANE(du_, node_, where_) do { const int k_ = ((du_).d.info >> 2) & 7; \
@@ -612,9 +612,6 @@ constexpr int SPMEMO_SLOTS = 256;                 /* NIC sub-problem memo (16 B 
 
 constexpr int DCACHE_SLOTS = 512;                 /* node-summary cache (32 B entries + tag)          */
 constexpr int SWEEP_TYPES_SMEM_MAX = 64;
-#ifndef NHD_DEFAULT_CPU_WARPS
-#define NHD_DEFAULT_CPU_WARPS 7              /* CPU-only pod class: the committing warp + 6 workers (standing decisions per type) */
-#endif
 
 struct SweepArgs {
     uint8_t* nodes;
@@ -624,7 +621,7 @@ struct SweepArgs {
     nhd_binding* out;
     int n_pods, n_types, n_nodes, words;
     int dual;                    /* 1: constant clock -> standing decisions per pod type (see sweep_kernel) */
-    int n_cpu_warps;             /* low byte 1: never sweep the two pod classes side by side; bits 8..: debug switches */
+    int sweep_flags;             /* bit 0: never sweep the two pod classes side by side; bits 8..: debug switches */
     int n_names;                 /* > 0: per-pod node-group masks, one bitmap per name after BUSY */
     uint64_t names_used;
     const uint64_t* pod_groups;  /* [n_pods] when n_names > 0 */
@@ -886,12 +883,8 @@ struct SweepCtx {
     bool types_in_smem;
     int lane;
     int smemo_mask, dmemo_mask, dcache_mask, spmemo_mask, clsnic_mask;   /* slice sizes - 1 */
-    int32_t* peer_dtag;      /* summary-cache tags of the other pod class (multi-warp mode), else null */
-    int peer_mask;
-    bool write_back;         /* several committing warps share the summary cache (see store_dyn) */
     const uint16_t* s_needb; /* [T][2][32] per-tuple socket demand for 2-NUMA nodes: need0 | need1 << 8 */
     struct ClsNic* clsnic;   /* CLSNIC_SLOTS x 48 B: static NIC layout per hardware class */
-    int* clsnic_lock;
     uint4* spmemo;           /* SPMEMO_SLOTS x 16 B: first surviving NIC assignment of (type, groups S, NUMA k, NICs in use there) */
     const FastTables* ft;    /* direct-path tables (null when the batch has too many pod types) */
 };
@@ -900,51 +893,14 @@ union DynU { NodeDyn d; uint4 q[2]; __device__ DynU() {} };
 
 /*
  * Node summaries: HBM (later batches and commit_kernel read them) behind a direct-mapped shared-memory
- * cache per pod class.  One warp per class commits at a time, in pod order; the other warps of the
- * CPU-only class only read (they work ahead and are validated later, see sweep_kernel), so:
- *   - a slot's tag is taken away before its data changes and put back after (shared-memory accesses of a
- *     warp are performed in order), so a reader that sees the tag before and after its reads never mixes
- *     two nodes;
- *   - store_dyn keeps HBM current for every node that is not in the cache.
+ * cache per sweeping warp, written through: HBM is current for every node at all times, the cache only
+ * shortens the chain.  One warp owns a cache (one CTA per pod class when the classes run side by side).
  */
-__device__ __forceinline__ int ld_vol(const volatile int* p)
-{
-    const int v = *p;
-    asm volatile("" ::: "memory");
-    return v;
-}
-
-/* committing warp: exact */
 __device__ __forceinline__ void load_dyn(const SweepArgs& a, const SweepCtx& cx, int node, DynU& du)
 {
     const int cs = node & cx.dcache_mask;
     if (cx.dtag[cs] == node) { du.q[0] = cx.dcache[2 * cs]; du.q[1] = cx.dcache[2 * cs + 1]; }
     else { du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]); }   /* L2: the sweep also updates summaries with atomics */
-}
-
-/* speculating warp: false when the slot changed hands under the read; a summary of the right node that is
- * stale or half-updated is fine (every field only moves one way inside a batch, and the result is compared
- * with the committed summary before it is used) */
-__device__ __forceinline__ bool spec_load_dyn(const SweepArgs& a, const SweepCtx& cx, int node, DynU& du)
-{
-    const int cs = node & cx.dcache_mask;
-    /* the committing warp changes these words while we read: the whole warp must read them in the same
-     * instructions (converged), or its lanes could see different values and part ways */
-    __syncwarp();
-    bool ok = true;
-    if (ld_vol(cx.dtag + cs) == node) {
-        du.q[0] = cx.dcache[2 * cs]; du.q[1] = cx.dcache[2 * cs + 1];
-        asm volatile("" ::: "memory");
-        ok = ld_vol(cx.dtag + cs) == node;
-    } else {
-        du.q[0] = __ldcg(&a.dyn[(size_t)node * 2]); du.q[1] = __ldcg(&a.dyn[(size_t)node * 2 + 1]);
-    }
-    /* belt and braces: lane 0's copy for everybody */
-    du.q[0].x = __shfl_sync(0xFFFFFFFFu, du.q[0].x, 0); du.q[0].y = __shfl_sync(0xFFFFFFFFu, du.q[0].y, 0);
-    du.q[0].z = __shfl_sync(0xFFFFFFFFu, du.q[0].z, 0); du.q[0].w = __shfl_sync(0xFFFFFFFFu, du.q[0].w, 0);
-    du.q[1].x = __shfl_sync(0xFFFFFFFFu, du.q[1].x, 0); du.q[1].y = __shfl_sync(0xFFFFFFFFu, du.q[1].y, 0);
-    du.q[1].z = __shfl_sync(0xFFFFFFFFu, du.q[1].z, 0); du.q[1].w = __shfl_sync(0xFFFFFFFFu, du.q[1].w, 0);
-    return __shfl_sync(0xFFFFFFFFu, (int)ok, 0) != 0;
 }
 
 __device__ __forceinline__ bool same_dyn(const DynU& x, const DynU& y)
@@ -953,46 +909,18 @@ __device__ __forceinline__ bool same_dyn(const DynU& x, const DynU& y)
            x.q[1].x == y.q[1].x && x.q[1].y == y.q[1].y && x.q[1].z == y.q[1].z && x.q[1].w == y.q[1].w;
 }
 
-/*
- * Committing warp.  Ordinarily write-through (HBM copy + shared-memory cache).  When several warps share the
- * cache (cx.write_back) the summary of a GPU-less node stays in the cache until its slot is needed — the
- * evicting warp then writes it to HBM, fenced, before the tag goes — or until the end of the sweep; nobody
- * else ever has a store to that node in flight, so a node that is not cached is always current in L2.
- * Summaries of GPU nodes (CPU-only pods that spilled) are written through and fenced at once: the GPU-pod
- * warp reads them from L2.
- */
+/* write-through: HBM copy + the warp's cache slot (tag last) */
 __device__ __forceinline__ void store_dyn(const SweepArgs& a, const SweepCtx& cx, int node, const DynU& du)
 {
     const int cs = node & cx.dcache_mask;
-    const bool through = !cx.write_back || du.d.n_gpus != 0;
     __syncwarp();                                        /* every lane has finished reading the cache */
-    if (cx.write_back) {
-        if (cx.lane == 0) {
-            const int old = ld_vol(cx.dtag + cs);
-            if (old != node) {
-                if (old >= 0) {
-                    DynU ev;
-                    ev.q[0] = cx.dcache[2 * cs]; ev.q[1] = cx.dcache[2 * cs + 1];
-                    if (ev.d.n_gpus == 0) {
-                        a.dyn[(size_t)old * 2] = ev.q[0]; a.dyn[(size_t)old * 2 + 1] = ev.q[1];
-                        __threadfence_block();
-                    }
-                }
-                cx.dtag[cs] = -1;
-            }
-        }
-        __syncwarp();
-    }
     const uint4 half = cx.lane == 0 ? du.q[0] : du.q[1];      /* a select, not an index: keeps the summary in registers */
     if (cx.lane < 2) {
-        if (through) a.dyn[(size_t)node * 2 + cx.lane] = half;
+        a.dyn[(size_t)node * 2 + cx.lane] = half;
         cx.dcache[2 * cs + cx.lane] = half;
     }
-    if (cx.write_back && through) __threadfence_block();
     __syncwarp();
     if (cx.lane == 2) cx.dtag[cs] = node;
-    /* the other pod class may hold an older copy of this node (spills, revisits) */
-    if (cx.lane == 3 && cx.peer_dtag && cx.peer_dtag[node & cx.peer_mask] == node) atomicCAS(&cx.peer_dtag[node & cx.peer_mask], node, -1);
 }
 
 /* claimed NIC order, list({x[0] for x in nic_list}) (NHDScheduler.py:302), registers only:
@@ -1129,17 +1057,14 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
     const uint32_t balA = 0x55555555u & (nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1));
 
     /* static NIC layout of the node's hardware class */
-    /* the table is shared by the warps of the CPU-only class: one writer at a time (lock), tag cleared before
-     * the data changes and set after; a reader keeps what it read only if the tag held before and after */
+    /* per-warp table: read by all lanes, refilled by lane 0 between two __syncwarp()s */
     ClsNic* ce = &cx.clsnic[du.d.hw_class & cx.clsnic_mask];
     uint32_t m0, m1, nk, spk0, spk1;
     unsigned long long sp0, sp1;
     __syncwarp();
     const uint32_t want = (uint32_t)du.d.hw_class + 1u;
-    bool hit = (uint32_t)ld_vol(reinterpret_cast<const volatile int*>(&ce->tag)) == want;
+    bool hit = ce->tag == want;
     m0 = ce->m0; m1 = ce->m1; nk = ce->nk; sp0 = ce->sp0; sp1 = ce->sp1; spk0 = ce->spk0; spk1 = ce->spk1;
-    asm volatile("" ::: "memory");
-    hit = hit && (uint32_t)ld_vol(reinterpret_cast<const volatile int*>(&ce->tag)) == want;
     hit = __all_sync(0xFFFFFFFFu, hit);
     if (!hit) {
         missed = true;
@@ -1156,12 +1081,9 @@ __device__ __forceinline__ int resolve_cpu2(const SweepArgs& a, const SweepCtx& 
         j = 0;
         for (uint32_t f = m1; f && j < 8; f &= f - 1, j++) { const int l = ctz32(f); spk1 |= (uint32_t)(((l < 16 ? sp0 : sp1) >> (4 * (l & 15))) & 0xF) << (4 * j); }
         __syncwarp();
-        if (lane == 0 && atomicCAS(cx.clsnic_lock, 0, 1) == 0) {
-            volatile ClsNic* vc = ce;
-            vc->tag = 0;
-            vc->m0 = m0; vc->m1 = m1; vc->nk = nk; vc->sp0 = sp0; vc->sp1 = sp1; vc->spk0 = spk0; vc->spk1 = spk1;
-            vc->tag = want;
-            *reinterpret_cast<volatile int*>(cx.clsnic_lock) = 0;
+        if (lane == 0) {
+            ce->m0 = m0; ce->m1 = m1; ce->nk = nk; ce->sp0 = sp0; ce->sp1 = sp1; ce->spk0 = spk0; ce->spk1 = spk1;
+            ce->tag = want;
         }
         __syncwarp();
     }
@@ -1785,7 +1707,7 @@ __device__ __noinline__ int ordinary_pod(const SweepArgs& a, const SweepCtx& cx,
         };
         for (int pass = t.needs_gpu ? 1 : 0; pass < 2 && chosen < 0; pass++) {
             /* (1) the cursor: first word with any candidate of this pass */
-            int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* warps working ahead advance it too: one read for all lanes */
+            int c = __shfl_sync(0xFFFFFFFFu, cursors[ti * 3 + pass], 0);     /* one read for all lanes */
             const int c_in = c;
             uint64_t raw = 0;
             while (c < W) {
@@ -1932,9 +1854,10 @@ __device__ __noinline__ int ordinary_pod(const SweepArgs& a, const SweepCtx& cx,
 }
 
 /*
- * Decision sweep.  One CTA; warp 0 walks the pods in order (all lanes execute the scalar parts
+ * Decision sweep.  One CTA — or two, one per pod class, when the classes provably cannot meet (see the
+ * certificate below); in each, warp 0 walks its pods in order (all lanes execute the scalar parts
  * redundantly, so there is no intra-warp hand-off), the other warps only help to stage tables
- * into shared memory.  Per pod:
+ * into shared memory.  Per pod on the general path (ordinary_pod):
  *   first fit   cursor word of the type's feasibility bitmap (minus busy nodes; GPU-less nodes
  *               first for CPU-only pods, Matcher.py:412-416), 32-wide ballot search when empty;
  *   untouched?  the snapshot bit of a node no pod of this batch was bound to is exact, so a GPU
@@ -1955,7 +1878,7 @@ sweep_kernel(const SweepArgs a)
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = a.words, T = a.n_types;
     const int wid = tid >> 5;
-    const int dbg = a.n_cpu_warps >> 8;       /* debug switch: 1 = no standing decisions (ordinary path for every pod) */
+    const int dbg = a.sweep_flags >> 8;       /* debug switch: 1 = no standing decisions (ordinary path for every pod) */
     SweepCtx cx;
     cx.lane = lane;
     cx.ft = nullptr;
@@ -1964,20 +1887,15 @@ sweep_kernel(const SweepArgs a)
     cx.spmemo_mask = SPMEMO_SLOTS - 1;
     cx.clsnic_mask = CLSNIC_SLOTS - 1;
     cx.dcache_mask = DCACHE_SLOTS - 1;
-    cx.peer_mask = cx.dcache_mask;
     cx.smemo = reinterpret_cast<uint4*>(smem);                                 /* SMEMO_SLOTS x 16 B */
     cx.dmemo = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16);              /* DMEMO_SLOTS x 48 B */
     cx.dcache = reinterpret_cast<uint4*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48);   /* DCACHE_SLOTS x 32 B */
     int32_t* dtag_all = reinterpret_cast<int32_t*>(smem + SMEMO_SLOTS * 16 + DMEMO_SLOTS * 48 + DCACHE_SLOTS * 32);
     cx.dtag = dtag_all;
-    cx.peer_dtag = nullptr;
-    int* misc = dtag_all + DCACHE_SLOTS;                                             /* [3] lock word of the class-layout table */
     ClsNic* clsnic_all = reinterpret_cast<ClsNic*>(dtag_all + DCACHE_SLOTS + 4);     /* CLSNIC_SLOTS x 48 B */
     uint4* spmemo_all = reinterpret_cast<uint4*>(clsnic_all + CLSNIC_SLOTS);         /* SPMEMO_SLOTS x 16 B */
     cx.clsnic = clsnic_all;
-    cx.clsnic_lock = &misc[3];
     cx.spmemo = spmemo_all;
-    cx.write_back = false;                                 /* one sweeping warp: summaries are written through */
     uint8_t* p0 = reinterpret_cast<uint8_t*>(spmemo_all + SPMEMO_SLOTS);
     PodType* s_types = reinterpret_cast<PodType*>(p0);
     cx.types_in_smem = T <= SWEEP_TYPES_SMEM_MAX;
@@ -2007,7 +1925,6 @@ sweep_kernel(const SweepArgs a)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < CLSNIC_SLOTS * 3 + SPMEMO_SLOTS; i += SWEEP_THREADS) reinterpret_cast<uint4*>(clsnic_all)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < DCACHE_SLOTS; i += SWEEP_THREADS) dtag_all[i] = -1;
-    if (tid < 4) misc[tid] = 0;
     for (int i = tid; i < W; i += SWEEP_THREADS) s_touched[i] = 0;
     const bool have_tables = fast_cap && a.ftab != nullptr && !(dbg & 4);
     const bool fast = have_tables && a.dual != 0 && a.n_names == 0 && !(dbg & 1);
@@ -2096,7 +2013,7 @@ sweep_kernel(const SweepArgs a)
      * compute it from the same inputs); with a busy window every GPU pod of the batch lands on a node no pod was
      * bound to, so CTA 1 only scans and stamps */
     bool split = false;
-    if (fast && a.min_busy > 0.0 && !(dbg & 2) && (a.n_cpu_warps & 0xFF) != 1) {
+    if (fast && a.min_busy > 0.0 && !(dbg & 2) && !(a.sweep_flags & 1)) {
         split = true;
         for (int tt = 0; tt < T; tt++) {
             const PodType& ty = a.types[tt];

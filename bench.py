@@ -51,54 +51,114 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    """SM clock / throttle-reason sampler running DURING the timed region.  The timed region is short (20 steps of
+    about 3 ms), so the samples come from NVML inside this process (a thread polling every 2 ms: dozens of samples
+    under load); nvidia-smi in a loop is the fallback where NVML cannot be loaded."""
     FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
               'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, uuid=None):
         self.index = index
+        self.uuid = uuid
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            for u in (self.uuid, 'GPU-' + self.uuid):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u.encode() if hasattr(u, 'encode') else u)
+                except Exception:
+                    pass
+        idx = self.index
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        if vis:
+            ids = [x.strip() for x in vis.split(',') if x.strip()]
+            if idx < len(ids) and ids[idx].isdigit():
+                idx = int(ids[idx])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self, nv, h):
+        bits = ((nv.nvmlClocksEventReasonHwSlowdown, 'hw_slowdown'),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 'sw_thermal_slowdown'),
+                (nv.nvmlClocksEventReasonSwPowerCap, 'sw_power_cap'))
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if mx is not None:
+                    self.mx.append(mx)
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for bit, nm in bits:
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)            # fails here, not in the thread
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.source = 'nvml, 2 ms period'
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            self.source = 'nvidia-smi -lms 100'
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        try:
-            for line in open(self.path):
-                parts = [x.strip() for x in line.split(',')]
-                if len(parts) < 6:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    mx.append(float(parts[1]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, parts[2:6]):
-                    if v.lower().startswith('active'):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'source': self.source}
+        sm, mx, reasons = self.sm, self.mx, self.reasons
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            try:
+                for line in open(self.path):
+                    parts = [x.strip() for x in line.split(',')]
+                    if len(parts) < 6:
+                        continue
+                    try:
+                        sm.append(float(parts[0]))
+                        mx.append(float(parts[1]))
+                    except ValueError:
+                        continue
+                    for nm, v in zip(self.NAMES, parts[2:6]):
+                        if v.lower().startswith('active'):
+                            reasons.add(nm)
+                os.unlink(self.path)
+            except Exception:
+                pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)) if mx else None,
+                       reasons=sorted(reasons), samples=len(sm))
         return out
 
 
@@ -143,7 +203,7 @@ def pick_threads(ob, recs, speed, pods, now, single_per_pod=None):
     return best
 
 
-def quick_value(Solver, recs, speed, pods, now, steps=3, **kw):
+def quick_value(Solver, recs, speed, pods, now, steps=3, pre_step=None, **kw):
     """decisions/s (device-timed total, batch resident) of a side workload: `steps` solves from the same snapshot."""
     s = Solver(speed, **kw)
     try:
@@ -153,6 +213,9 @@ def quick_value(Solver, recs, speed, pods, now, steps=3, **kw):
         best = None
         for _ in range(steps + 1):
             s.restore()
+            s.sync()
+            if pre_step is not None:
+                pre_step()                     # several ranks: enter the step together (else the collective times their skew)
             s.solve_staged()
             s.sync()
             t = s.timing()
@@ -267,7 +330,11 @@ def main():
     # ---------------- value: batch + cluster resident in HBM, kernels only -----------------
     solver.stage_batch(pods, now)
     phase = {'filter_ms': [], 'exchange_ms': [], 'sweep_ms': [], 'total_ms': []}
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     launches = 0
     barrier()
     t_wall0 = None
@@ -337,7 +404,7 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))     # a fresh id: one per handle
         dist.broadcast(idt, 0)
         r5, s5, p5, n5 = workload.make_workload(5)
-        cfg5_multi = quick_value(Solver, r5, s5, p5, n5, device=local_rank, rank=rank, world_size=world,
+        cfg5_multi = quick_value(Solver, r5, s5, p5, n5, pre_step=barrier, device=local_rank, rank=rank, world_size=world,
                                  nccl_id=bytes(idt.cpu().numpy().tobytes()))
         tt = torch.tensor([cfg5_multi['ms']], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

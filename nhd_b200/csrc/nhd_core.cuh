@@ -422,6 +422,106 @@ NHD_HD bool node_feasible(const nhd_node_rec& r, const PodType& t, const double*
     return false;
 }
 
+/*
+ * The same predicate for the common shape — a 2-NUMA node and a pod of one or two groups — written so that
+ * nothing is indexed dynamically: the record, the per-NUMA counts and the search state all stay in registers
+ * (node_feasible keeps its tuples, demand sums and NIC search stack in arrays, which the GPU puts in local
+ * memory).  Only EXISTENCE of a surviving entry matters here, so the order of enumeration is free; what must
+ * not change is the arithmetic of each test: fp64 subtraction in group order on a shared NIC
+ * (Matcher.py:261-268), the per-switch count of the PCI pruning (:312-322).  The part that does not depend on
+ * the pod type is computed once per node (Pre2).
+ */
+struct Pre2 {
+    int fc0, fc1;                /* Node.GetFreeCpuCores */
+    int fg0, fg1;                /* Node.GetFreeNumaGPUs */
+    uint64_t gsw;                /* Node.GetFreeGPUPCICount, 4 bits per local switch id */
+    bool smt;
+};
+
+NHD_HD void make_pre2(const nhd_node_rec& r, int fc0, int fc1, Pre2& q)
+{
+    const uint32_t fr = ~(uint32_t)r.gpu_used & ((1u << r.n_gpus) - 1);
+    q.fc0 = fc0; q.fc1 = fc1;
+    q.fg0 = popc32(fr & r.gpu_numa_mask[0]);
+    q.fg1 = popc32(fr & r.gpu_numa_mask[1]);
+    q.gsw = fr ? free_gpus_per_switch(r) : 0;
+    q.smt = rec_smt(r);
+}
+
+NHD_HD int nic_switch2(const nhd_node_rec& r, int l)
+{
+    return (int)(((l < 16 ? r.nic_sw[0] : r.nic_sw[1]) >> (4 * (l & 15))) & 0xF);
+}
+NHD_HD double nic_free_bw2(const nhd_node_rec& r, int l, const double* cap)
+{
+    const int sc = (int)(((l < 16 ? r.nic_speed[0] : r.nic_speed[1]) >> (4 * (l & 15))) & 0xF);
+    return ((r.nic_inuse >> l) & 1) ? 0.0 : cap[sc];
+}
+
+/* NIC stage of one NUMA tuple (p0, p1), G <= 2: does filts['nic'] keep an entry with this NUMA part? */
+NHD_HD bool nic_any_fit2(const nhd_node_rec& r, const PodType& t, int p0, int p1, const double* cap, uint64_t gsw)
+{
+    const uint32_t nm0 = p0 ? r.nic_numa_mask[1] : r.nic_numa_mask[0];
+    const double rx0 = t.pod.groups[0].rx_gbps, tx0 = t.pod.groups[0].tx_gbps;
+    if (t.G == 1) {
+        for (uint32_t m = nm0; m; m &= m - 1) {
+            const int l = ctz32(m);
+            const double c = nic_free_bw2(r, l, cap);
+            if ((c - rx0 < 0) || (c - tx0 < 0)) continue;
+            if (t.pci && ((gsw >> (4 * nic_switch2(r, l))) & 0xF) < 1) continue;
+            return true;
+        }
+        return false;
+    }
+    const uint32_t nm1 = p1 ? r.nic_numa_mask[1] : r.nic_numa_mask[0];
+    const double rx1 = t.pod.groups[1].rx_gbps, tx1 = t.pod.groups[1].tx_gbps;
+    if (nm1 == 0) return false;
+    for (uint32_t m = nm0; m; m &= m - 1) {
+        const int l0 = ctz32(m);
+        const double c0 = nic_free_bw2(r, l0, cap);
+        const double r0 = c0 - rx0, q0 = c0 - tx0;
+        if ((r0 < 0) || (q0 < 0)) continue;
+        const int s0 = nic_switch2(r, l0);
+        const int f0 = (int)((gsw >> (4 * s0)) & 0xF);
+        if (t.pci && f0 < 1) continue;
+        for (uint32_t n = nm1; n; n &= n - 1) {
+            const int l1 = ctz32(n);
+            double r1, q1;
+            if (l1 == l0) { r1 = r0 - rx1; q1 = q0 - tx1; }        /* what group 0 left of the NIC (:261-268) */
+            else { const double c1 = nic_free_bw2(r, l1, cap); r1 = c1 - rx1; q1 = c1 - tx1; }
+            if ((r1 < 0) || (q1 < 0)) continue;
+            if (t.pci) {
+                const int s1 = nic_switch2(r, l1);
+                if (s1 == s0 ? f0 < 2 : ((gsw >> (4 * s1)) & 0xF) < 1) continue;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+/* node_feasible for r.n_numa == 2 and t.G <= 2 (the caller checks both) */
+NHD_HD bool node_feasible_k2(const nhd_node_rec& r, const PodType& t, const double* cap, const Pre2& q)
+{
+    if (!t.valid_map) return false;
+    if (!node_gates(r, t)) return false;
+    const uint8_t* cl = q.smt ? t.cl_smt : t.cl_nosmt;
+    const bool two = t.G > 1;
+    const int c0 = cl[0], c1 = two ? cl[1] : 0, cm = two ? cl[2] : cl[1];
+    const int g0 = t.pod.groups[0].n_gpus, g1 = two ? t.pod.groups[1].n_gpus : 0;
+    if (g0 + g1 > q.fg0 + q.fg1 || c0 + c1 + cm > q.fc0 + q.fc1) return false;
+    const int np = two ? 4 : 2;
+    for (int pi = 0; pi < np; pi++) {
+        const int p0 = two ? (pi >> 1) : pi, p1 = pi & 1;           /* first element most significant */
+        const int a1 = (p0 ? g0 : 0) + ((two && p1) ? g1 : 0), a0 = g0 + g1 - a1;
+        if (a0 > q.fg0 || a1 > q.fg1) continue;                    /* Matcher.py:121-129 */
+        const int b1 = (p0 ? c0 : 0) + ((two && p1) ? c1 : 0), b0 = c0 + c1 - b1;
+        if (!((b0 + cm <= q.fc0 && b1 <= q.fc1) || (b0 <= q.fc0 && b1 + cm <= q.fc1))) continue;   /* :204-212 */
+        if (nic_any_fit2(r, t, p0, p1, cap, q.gsw)) return true;
+    }
+    return false;
+}
+
 /* ---------------------------------------------------------------- CPython set emulation */
 
 /*

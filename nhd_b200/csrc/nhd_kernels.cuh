@@ -418,6 +418,14 @@ struct FilterArgs {
     double cap[NHD_MAX_SPEED_CLASSES];
 };
 
+/* The general predicate, out of line and on its own copy of the record: its tuple / search arrays live in local
+ * memory, and inlined it would drag the caller's record there as well.  Only shapes outside the register-only form
+ * come here (other than 2 NUMA nodes, more than two groups). */
+__device__ __noinline__ bool node_feasible_general(const nhd_node_rec r, const PodType* t, const double* cap)
+{
+    return node_feasible(r, *t, cap);
+}
+
 __global__ void __launch_bounds__(FILTER_THREADS, 2)
 filter_kernel(const FilterArgs a)
 {
@@ -425,8 +433,10 @@ filter_kernel(const FilterArgs a)
     uint8_t* stage_buf = smem;                                          /* FILTER_STAGES x SUPER_BYTES */
     PodType* s_types = reinterpret_cast<PodType*>(smem + FILTER_STAGES * SUPER_BYTES);
     __shared__ __align__(8) uint64_t full_bar[FILTER_STAGES];
+    __shared__ double s_cap[NHD_MAX_SPEED_CLASSES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < NHD_MAX_SPEED_CLASSES) s_cap[tid] = a.cap[tid];       /* ordered by the barrier below */
     /* CTA = (position in the walk over the super-tiles, type chunk): with few super-tiles per GPU (small clusters,
      * node-sharded ranks) the pod types are dealt over several CTAs so that the whole machine still works */
     const int TS = a.type_split, tch = (int)blockIdx.x % TS, cta = (int)blockIdx.x / TS, ncta = (int)gridDim.x / TS;
@@ -509,6 +519,11 @@ filter_kernel(const FilterArgs a)
         const uint32_t* f_sub1 = reinterpret_cast<const uint32_t*>(a.ftab + ftab_off_sub1(T_));
         const TyFast* f_ty = reinterpret_cast<const TyFast*>(a.ftab + ftab_off_ty(T_));
 
+        /* every other (type, node) pair of the common shape: the register-only predicate, its node part once */
+        const bool k2 = valid && u.r.n_numa == 2;
+        Pre2 pre;
+        if (k2) make_pre2(u.r, du.d.fc[0], du.d.fc[1], pre);
+
         const size_t w32 = ((size_t)node >> 5) - (size_t)a.word_base * 2;
         for (int t = tch; t < a.n_types; t += TS) {
             bool f;
@@ -518,8 +533,10 @@ filter_kernel(const FilterArgs a)
                 const uint32_t mB = __ldg(&f_tb[((t * 2 + d_smt) * 2 + 0) * 64 + d_c0]) & __ldg(&f_tb[((t * 2 + d_smt) * 2 + 1) * 64 + d_c1]);
                 const uint32_t mi = f_ty[t].G == 2 ? ((mB << 4) | mC) : (4096 + (((mB & 15) << 2) | (mC & 3)));
                 f = node_gates(u.r, types[t]) && (__ldg(&a.mapt[mi]) & 0x80) != 0;
-            } else
-                f = valid && node_feasible(u.r, types[t], a.cap);
+            } else if (k2 && types[t].G >= 1 && types[t].G <= 2)
+                f = node_feasible_k2(u.r, types[t], s_cap, pre);
+            else
+                f = valid && node_feasible_general(u.r, &types[t], s_cap);
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, f);
             if (lane == 0) out32[(size_t)t * words32 + w32] = bal;
         }

@@ -54,6 +54,26 @@ int nhd_emu_feasible(double bw, const double* speed, int n_nodes, const nhd_node
     return 0;
 }
 
+/* the register-only form of the predicate the filter kernel uses on 2-NUMA nodes for pods of <= 2 groups;
+ * out[n] = 2 where that form does not apply */
+int nhd_emu_feasible_k2(double bw, const double* speed, int n_nodes, const nhd_node_rec* recs,
+                        const nhd_pod* pod, uint8_t* out)
+{
+    double cap[NHD_MAX_SPEED_CLASSES];
+    for (int i = 0; i < NHD_MAX_SPEED_CLASSES; i++) cap[i] = speed[i] * bw;
+    PodType t;
+    make_pod_type(*pod, t);
+    for (int n = 0; n < n_nodes; n++) {
+        if (recs[n].n_numa != 2 || t.G < 1 || t.G > 2) { out[n] = 2; continue; }
+        NodeDyn d;
+        make_dyn(recs[n], d);
+        Pre2 q;
+        make_pre2(recs[n], d.fc[0], d.fc[1], q);
+        out[n] = node_feasible_k2(recs[n], t, cap, q);
+    }
+    return 0;
+}
+
 int nhd_emu_choose(int K, int G, const uint64_t* a, const uint64_t* b, const uint64_t* c, int* p, int* m)
 {
     TMask ma, mb, mc;

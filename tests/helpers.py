@@ -21,14 +21,15 @@ def emu_solve(emu, recs, speed_table, pods, now, bw=0.9, min_busy=30.0, two_stag
     return out, recs
 
 
-def emu_feasible(emu, recs, speed_table, pod, bw=0.9):
+def emu_feasible(emu, recs, speed_table, pod, bw=0.9, k2=False):
+    """node_feasible per node; k2=True: the register-only 2-NUMA form (2 = form does not apply to that node / pod)."""
     recs = np.ascontiguousarray(recs, dtype=wire.NODE_DTYPE)
     pod = np.ascontiguousarray(pod, dtype=wire.POD_DTYPE).reshape(1)
     speed = np.ascontiguousarray(speed_table, dtype='<f8')
     out = np.zeros(len(recs), dtype=np.uint8)
-    emu.nhd_emu_feasible.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                     ctypes.c_void_p, ctypes.c_void_p]
-    emu.nhd_emu_feasible(bw, speed.ctypes.data, len(recs), recs.ctypes.data, pod.ctypes.data, out.ctypes.data)
+    fn = emu.nhd_emu_feasible_k2 if k2 else emu.nhd_emu_feasible
+    fn.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    fn(bw, speed.ctypes.data, len(recs), recs.ctypes.data, pod.ctypes.data, out.ctypes.data)
     return out
 
 

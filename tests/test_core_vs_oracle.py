@@ -39,6 +39,39 @@ def test_snapshot_predicate_matches_oracle_candidates(oracle_lib, emu):
     assert checked > 50
 
 
+def test_register_only_predicate_equals_the_general_one(oracle_lib, emu):
+    """node_feasible_k2 (2-NUMA nodes, pods of one or two groups: what the filter kernel runs for the types outside
+    its tables) == node_feasible, pair by pair, on partially filled clusters of every flavour — NUMA and PCI mode,
+    shared NICs, switches shared across NUMA nodes, SR-IOV VFs — and on the benchmark clusters."""
+    import workload
+    applied = yes = 0
+    cases = []
+    for seed in range(60):
+        flavor = ('mixed', 'wild', 'vf', 'big')[seed % 4]
+        scn = scenarios.random_scenario(4100 + seed * 7, n_nodes=16, n_pods=40, flavor=flavor, max_groups=3)
+        recs, pods, now, layout = ref_compare.pack_scenario(scn)
+        cases.append((recs, layout.speed_table(), pods, now, 20))
+    for config in (3, 5):
+        for wild in (False, True):
+            recs, speed, pods, now = workload.make_workload(config, n_nodes=256, n_pods=600, wild=wild)
+            cases.append((recs, speed, pods, now, 400))
+    for recs, speed, pods, now, n_fill in cases:
+        _, filled = oracle_lib.solve(recs, speed, pods[:n_fill], now[:n_fill])
+        seen = set()
+        for pod in pods[n_fill:]:
+            key = pod.tobytes()
+            if key in seen or pod['map_type'] not in (1, 2):
+                continue
+            seen.add(key)
+            gen = helpers.emu_feasible(emu, filled, speed, pod)
+            k2 = helpers.emu_feasible(emu, filled, speed, pod, k2=True)
+            on = k2 != 2
+            assert np.array_equal(gen[on], k2[on]), (np.flatnonzero(on & (gen != k2))[:5], pod)
+            applied += int(on.sum())
+            yes += int(k2[on].sum())
+    assert applied > 5000 and yes > 500 and applied - yes > 500, (applied, yes)
+
+
 @pytest.mark.parametrize('config', [2, 3, 5])
 def test_two_stage_core_on_baseline_shapes(oracle_lib, emu, config):
     """Summary-state decisions + deferred core ids (the CUDA sweep's structure) on the benchmark's

@@ -14,7 +14,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from nhd_b200 import wire
+from nhd_b200 import tracking, wire
 
 
 _log = logging.getLogger('nhd_b200')
@@ -249,6 +249,7 @@ def apply_binding(node, top, b):
     ``Node.SetPhysicalIdsFromMapping`` does (``Node.py:674-818``) and return ``used_nics``.
     Raises ``IndexError`` for a failed assignment (``Node.py:825-837``)."""
     status = int(b['status'])
+    tracking.bump(node)                                  # the node's sub-objects change below (Matcher's change counter)
     if status in (wire.ASSIGN_FAILED, wire.REF_WOULD_CRASH):
         raise IndexError('physical assignment failed on node %s' % node.name)
     if status != wire.PLACED:

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -105,6 +106,7 @@ struct nhd_handle {
     uint8_t* d_xchg = nullptr;  size_t xchg_cap = 0;     /* node-sharded ranks: one slot per rank (summaries + bitmap columns) */
     uint8_t* d_ftab = nullptr;            /* direct-path tables of the staged batch's pod types */
     uint8_t* d_mapt = nullptr;            /* GetNumaGroupIdx table of the direct path */
+    uint8_t* d_mapt2 = nullptr;           /* ... with the GPU stage (resolve_kernel); the device's shared copy, not owned */
     uint32_t* d_sigs = nullptr;           /* per-NUMA NIC signatures */
     ClsFast* d_cls_fast = nullptr;        /* per hardware class */
     double now0 = 0.0;
@@ -239,6 +241,28 @@ extern "C" int32_t nhd_nccl_unique_id(uint8_t out[128])
     return NHD_OK;
 }
 
+/* MAPT2 (mapt2_kernel) is a constant of the CPython set model, 64 KB: one copy per device for the life of the process,
+ * shared by every handle on that device and never freed.  Published only after the kernel that fills it has finished. */
+static std::mutex g_mapt2_mu;
+static uint8_t* g_mapt2[64];
+static cudaError_t shared_mapt2(int device, cudaStream_t st, uint8_t** out)
+{
+    std::lock_guard<std::mutex> lk(g_mapt2_mu);
+    if (device < 0 || device >= 64) return cudaErrorInvalidValue;
+    if (!g_mapt2[device]) {
+        uint8_t* t = nullptr;
+        cudaError_t e = cudaMalloc((void**)&t, (size_t)MAPT2_BYTES);
+        if (e != cudaSuccess) return e;
+        mapt2_kernel<<<(MAPT2_BYTES + 127) / 128, 128, 0, st>>>(t);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(t); return e; }
+        g_mapt2[device] = t;
+    }
+    *out = g_mapt2[device];
+    return cudaSuccess;
+}
+
 extern "C" int32_t nhd_destroy(nhd_handle* h)
 {
     if (!h) return NHD_OK;
@@ -309,6 +333,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
     CK(cudaMemsetAsync(h->d_cls_fast, 0, (size_t)CLASS_SLOTS * sizeof(ClsFast), h->stream));
     mapt_kernel<<<(MAPT_BYTES + 127) / 128, 128, 0, h->stream>>>(h->d_mapt);
     CK(cudaGetLastError());
+    CK(shared_mapt2(p->device, h->stream, &h->d_mapt2));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             FILTER_STAGES * SUPER_BYTES + TYPES_SMEM_MAX * (int)sizeof(PodType)));
     CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -725,7 +750,7 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
         sa.sweep_flags = ((h->params.reserved_ & 0xFF) == 2 ? 1 : 0) | ((h->params.reserved_ >> 8) << 8);
         sa.bitmaps = h->d_bitmaps; sa.dyn = h->d_dyn; sa.cursors = h->d_cursors; sa.busy_list = h->d_busy_list;
         sa.memo = h->d_memo; sa.prof = h->d_prof; sa.pend_pod = h->d_pend;
-        sa.mapt = h->d_mapt; sa.sigs = h->d_sigs; sa.cls_fast = h->d_cls_fast;
+        sa.mapt = h->d_mapt; sa.mapt2 = h->d_mapt2; sa.sigs = h->d_sigs; sa.cls_fast = h->d_cls_fast;
         sa.ftab = (T > 0 && T <= FAST_MAX_TYPES) ? h->d_ftab : nullptr;
         sa.min_busy = h->params.min_busy_secs;
         memcpy(sa.cap, h->cap, sizeof(sa.cap));

@@ -522,6 +522,76 @@ NHD_HD bool node_feasible_k2(const nhd_node_rec& r, const PodType& t, const doub
     return false;
 }
 
+/*
+ * The three stage masks of stage_masks_fc in the same register-only form (r.n_numa == 2, t.G <= 2): bit p of mA /
+ * mC = NUMA tuple p passes the GPU stage / keeps a NIC entry, bit 2p + m of mB = CPU tuple (p, m) passes.  With the
+ * GetNumaGroupIdx table over (mA, mB, mC) (mapt2_kernel) this is everything the mapping of a pod needs on such a node.
+ */
+NHD_HD bool stage_masks_k2(const nhd_node_rec& r, const PodType& t, const double* cap, const Pre2& q,
+                           uint32_t& mA, uint32_t& mB, uint32_t& mC)
+{
+    const uint8_t* cl = q.smt ? t.cl_smt : t.cl_nosmt;
+    const bool two = t.G > 1;
+    const int c0 = cl[0], c1 = two ? cl[1] : 0, cm = two ? cl[2] : cl[1];
+    const int g0 = t.pod.groups[0].n_gpus, g1 = two ? t.pod.groups[1].n_gpus : 0;
+    const int np = two ? 4 : 2;
+    mA = mB = mC = 0;
+    for (int pi = 0; pi < np; pi++) {
+        const int p0 = two ? (pi >> 1) : pi, p1 = pi & 1;
+        const int a1 = (p0 ? g0 : 0) + ((two && p1) ? g1 : 0), a0 = g0 + g1 - a1;
+        if (a0 <= q.fg0 && a1 <= q.fg1) mA |= 1u << pi;
+        const int b1 = (p0 ? c0 : 0) + ((two && p1) ? c1 : 0), b0 = c0 + c1 - b1;
+        if (b0 + cm <= q.fc0 && b1 <= q.fc1) mB |= 1u << (2 * pi);
+        if (b0 <= q.fc0 && b1 + cm <= q.fc1) mB |= 2u << (2 * pi);
+        if (nic_any_fit2(r, t, p0, p1, cap, t.pci ? q.gsw : 0)) mC |= 1u << pi;
+    }
+    return mA != 0 && mB != 0 && mC != 0;
+}
+
+/*
+ * nic_first_fit for the NUMA tuple (p0, p1), same shapes: the FIRST surviving entry in the reference's order — NUMA 0's
+ * groups vary slowest, inside a NUMA node the first group (Matcher.py:245-258).  Packed result: per group g the
+ * per-NUMA NodeNic.idx in bits 8g.. of *idx and the index in Node.nics in bits 8g.. of *li.
+ */
+NHD_HD bool nic_first_fit2(const nhd_node_rec& r, const PodType& t, int p0, int p1, const double* cap, uint64_t gsw,
+                           uint32_t* idx, uint32_t* li)
+{
+    const bool two = t.G > 1;
+    /* level order: a group on NUMA 0 before a group on NUMA 1, else group order */
+    const int ga = (two && p0 > p1) ? 1 : 0, gb = 1 - ga;
+    const uint32_t nma = (ga ? p1 : p0) ? r.nic_numa_mask[1] : r.nic_numa_mask[0];
+    const double rxa = t.pod.groups[ga].rx_gbps, txa = t.pod.groups[ga].tx_gbps;
+    for (uint32_t m = nma; m; m &= m - 1) {
+        const int la = ctz32(m);
+        const double ca = nic_free_bw2(r, la, cap);
+        const double ra = ca - rxa, qa = ca - txa;
+        if ((ra < 0) || (qa < 0)) continue;
+        const int sa = nic_switch2(r, la);
+        const int fa = (int)((gsw >> (4 * sa)) & 0xF);
+        if (t.pci && fa < 1) continue;
+        const uint32_t ia = (uint32_t)popc32(nma & ((1u << la) - 1));
+        if (!two) { *idx = ia; *li = (uint32_t)la; return true; }
+        const uint32_t nmb = (gb ? p1 : p0) ? r.nic_numa_mask[1] : r.nic_numa_mask[0];
+        const double rxb = t.pod.groups[gb].rx_gbps, txb = t.pod.groups[gb].tx_gbps;
+        for (uint32_t n = nmb; n; n &= n - 1) {
+            const int lb = ctz32(n);
+            double rb, qb;
+            if (lb == la) { rb = ra - rxb; qb = qa - txb; }
+            else { const double cb = nic_free_bw2(r, lb, cap); rb = cb - rxb; qb = cb - txb; }
+            if ((rb < 0) || (qb < 0)) continue;
+            if (t.pci) {
+                const int sb = nic_switch2(r, lb);
+                if (sb == sa ? fa < 2 : ((gsw >> (4 * sb)) & 0xF) < 1) continue;
+            }
+            const uint32_t ib = (uint32_t)popc32(nmb & ((1u << lb) - 1));
+            *idx = (ia << (8 * ga)) | (ib << (8 * gb));
+            *li = ((uint32_t)la << (8 * ga)) | ((uint32_t)lb << (8 * gb));
+            return true;
+        }
+    }
+    return false;
+}
+
 /* ---------------------------------------------------------------- CPython set emulation */
 
 /*

@@ -235,6 +235,24 @@ __global__ void mapt_kernel(uint8_t* mapt)
     mapt[i] = choose_mapping(2, G, ma, mb, mc, &ps, &ms) ? (uint8_t)(0x80 | ps | (ms << 2)) : (uint8_t)0;
 }
 
+/* The same function with the GPU stage as a third input (GPU pods; resolve_kernel): [0, 65536): G = 2, index =
+ * GPU mask (4 bits, p) << 12 | CPU mask (8 bits) << 4 | NIC mask (4 bits); [65536, 65792): G = 1, index =
+ * GPU mask (2 bits) << 6 | CPU mask (4 bits) << 2 | NIC mask (2 bits).  Same value format.  Once per handle. */
+constexpr int MAPT2_BYTES = 65536 + 256;
+__global__ void mapt2_kernel(uint8_t* mapt2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MAPT2_BYTES) return;
+    const int G = i < 65536 ? 2 : 1;
+    const int j = i < 65536 ? i : i - 65536;
+    TMask ma = tm_zero(), mb = tm_zero(), mc = tm_zero();
+    ma.w[0] = G == 2 ? (uint32_t)(j >> 12) : (uint32_t)(j >> 6);
+    mb.w[0] = G == 2 ? (uint32_t)((j >> 4) & 0xFF) : (uint32_t)((j >> 2) & 15);
+    mc.w[0] = G == 2 ? (uint32_t)(j & 15) : (uint32_t)(j & 3);
+    int ps = 0, ms = 0;
+    mapt2[i] = choose_mapping(2, G, ma, mb, mc, &ps, &ms) ? (uint8_t)(0x80 | ps | (ms << 2)) : (uint8_t)0;
+}
+
 /*
  * Per hardware class (ClassSlot key = the static description of its nodes): the NIC list indices of each NUMA
  * node in NodeNic.idx order and the signature ids (NIC count + speed classes in that order) of the two NUMA
@@ -649,6 +667,7 @@ struct SweepArgs {
     int32_t* pend_pod;           /* [n_nodes] pod whose resolution is pending on the node */
     uint64_t* memo;              /* MEMO_SLOTS x 2 words (global, persists across batches) */
     const uint8_t* mapt;         /* MAPT_BYTES: GetNumaGroupIdx table of the direct path (mapt_kernel, once per handle) */
+    const uint8_t* mapt2;        /* MAPT2_BYTES: the same with the GPU stage (mapt2_kernel); read by resolve_kernel */
     const uint32_t* sigs;        /* FAST_NSIG per-NUMA NIC signatures (cls_fast_kernel, at load / update time) */
     const uint8_t* ftab;         /* direct-path tables of the batch's pod types (fast_tables_kernel), null when T > FAST_MAX_TYPES */
     const struct ClsFast* cls_fast;   /* [CLASS_SLOTS] */
@@ -2360,13 +2379,38 @@ __global__ void resolve_kernel(const SweepArgs a)
     for (int c = 0; c < 8; c++) bu.q[c] = make_uint4(0, 0, 0, 0);
     bu.b.node = node;
     const uint64_t gsw = t.pci ? free_gpus_per_switch(u.r) : 0;
-    TMask ma, mb, mc;
-    int ps = 0, ms = 0;
     Mapping m;
-    if (stage_masks_fc(u.r, du.d.fc, t, a.cap, gsw, ma, mb, mc) && choose_mapping(u.r.n_numa, t.G, ma, mb, mc, &ps, &ms)) {
-        tuple_digits(ps, u.r.n_numa, t.G, m.gpu_numa);
-        m.misc_numa = (uint8_t)ms;
-        nic_first_fit(u.r, t, m.gpu_numa, u.r.n_numa, a.cap, gsw, m.nic_idx, m.nic_li);
+    bool mapped = false;
+    if (u.r.n_numa == 2 && t.G >= 1 && t.G <= 2 && a.mapt2) {
+        /* the common shape: stage masks without arrays, GetNumaGroupIdx from the table, then the first NIC entry of
+         * the chosen tuple — the same values as the general branch below */
+        Pre2 pre;
+        make_pre2(u.r, du.d.fc[0], du.d.fc[1], pre);
+        uint32_t mA, mB, mC;
+        if (stage_masks_k2(u.r, t, a.cap, pre, mA, mB, mC)) {
+            const uint32_t e = __ldg(&a.mapt2[t.G == 2 ? ((mA << 12) | (mB << 4) | mC) : (65536u + ((mA << 6) | (mB << 2) | mC))]);
+            if (e & 0x80) {
+                const int p0 = t.G == 2 ? (int)((e >> 1) & 1) : (int)(e & 1), p1 = (int)(e & 1);
+                uint32_t idx = 0, li = 0;
+                nic_first_fit2(u.r, t, p0, p1, a.cap, gsw, &idx, &li);
+                m.gpu_numa[0] = (uint8_t)p0; m.gpu_numa[1] = (uint8_t)(t.G == 2 ? p1 : 0); m.gpu_numa[2] = m.gpu_numa[3] = 0;
+                m.misc_numa = (uint8_t)((e >> 2) & 1);
+                m.nic_idx[0] = (uint8_t)(idx & 0xFF); m.nic_idx[1] = (uint8_t)((idx >> 8) & 0xFF); m.nic_idx[2] = m.nic_idx[3] = 0;
+                m.nic_li[0] = (uint8_t)(li & 0xFF); m.nic_li[1] = (uint8_t)((li >> 8) & 0xFF); m.nic_li[2] = m.nic_li[3] = 0;
+                mapped = true;
+            }
+        }
+    } else {
+        TMask ma, mb, mc;
+        int ps = 0, ms = 0;
+        if (stage_masks_fc(u.r, du.d.fc, t, a.cap, gsw, ma, mb, mc) && choose_mapping(u.r.n_numa, t.G, ma, mb, mc, &ps, &ms)) {
+            tuple_digits(ps, u.r.n_numa, t.G, m.gpu_numa);
+            m.misc_numa = (uint8_t)ms;
+            nic_first_fit(u.r, t, m.gpu_numa, u.r.n_numa, a.cap, gsw, m.nic_idx, m.nic_li);
+            mapped = true;
+        }
+    }
+    if (mapped) {
         assign_resources(u.r, du.d, t, m, du.d.busy_time, &bu.b);
     } else {
         bu.b.status = NHD_NO_CANDIDATE;        /* cannot happen: the snapshot bit said feasible */

@@ -74,6 +74,49 @@ int nhd_emu_feasible_k2(double bw, const double* speed, int n_nodes, const nhd_n
     return 0;
 }
 
+/* stage_masks_k2 / nic_first_fit2 (the register-only forms resolve_kernel uses) against stage_masks_fc /
+ * nic_first_fit on every applicable node: returns the number of differences, counts[0] = nodes compared,
+ * counts[1] = NIC entries compared */
+int nhd_emu_check_k2(double bw, const double* speed, int n_nodes, const nhd_node_rec* recs, const nhd_pod* pod, int* counts)
+{
+    double cap[NHD_MAX_SPEED_CLASSES];
+    for (int i = 0; i < NHD_MAX_SPEED_CLASSES; i++) cap[i] = speed[i] * bw;
+    PodType t;
+    make_pod_type(*pod, t);
+    int bad = 0;
+    counts[0] = counts[1] = 0;
+    if (t.G < 1 || t.G > 2) return 0;
+    for (int n = 0; n < n_nodes; n++) {
+        const nhd_node_rec& r = recs[n];
+        if (r.n_numa != 2) continue;
+        NodeDyn d;
+        make_dyn(r, d);
+        Pre2 q;
+        make_pre2(r, d.fc[0], d.fc[1], q);
+        const uint64_t gsw = t.pci ? free_gpus_per_switch(r) : 0;
+        TMask ma, mb, mc;
+        const bool ok = stage_masks_fc(r, d.fc, t, cap, gsw, ma, mb, mc);
+        uint32_t a, b, c;
+        const bool ok2 = stage_masks_k2(r, t, cap, q, a, b, c);
+        counts[0]++;
+        if (ok != ok2 || ma.w[0] != a || mb.w[0] != b || mc.w[0] != c) bad++;
+        const int np = 1 << t.G;
+        for (int pi = 0; pi < np; pi++) {
+            uint8_t p[NHD_MAX_GROUPS], idx[NHD_MAX_GROUPS] = {0, 0, 0, 0}, li[NHD_MAX_GROUPS] = {0, 0, 0, 0};
+            tuple_digits(pi, 2, t.G, p);
+            const bool f = nic_first_fit(r, t, p, 2, cap, gsw, idx, li);
+            uint32_t i2 = 0, l2 = 0;
+            const bool f2 = nic_first_fit2(r, t, p[0], t.G > 1 ? p[1] : 0, cap, gsw, &i2, &l2);
+            counts[1]++;
+            if (f != f2) { bad++; continue; }
+            if (!f) continue;
+            for (int g = 0; g < t.G; g++)
+                if (((i2 >> (8 * g)) & 0xFF) != idx[g] || ((l2 >> (8 * g)) & 0xFF) != li[g]) bad++;
+        }
+    }
+    return bad;
+}
+
 int nhd_emu_choose(int K, int G, const uint64_t* a, const uint64_t* b, const uint64_t* c, int* p, int* m)
 {
     TMask ma, mb, mc;

@@ -1,8 +1,11 @@
 """CPU-only: the product's scalar core (nhd_core.cuh compiled with g++, tests/emu) must agree
 with the oracle bit for bit — bindings and final node records — on randomized clusters."""
+import ctypes
+
 import numpy as np
 import pytest
 
+from nhd_b200 import wire
 from tests import helpers, ref_compare, scenarios
 
 
@@ -44,7 +47,7 @@ def test_register_only_predicate_equals_the_general_one(oracle_lib, emu):
     its tables) == node_feasible, pair by pair, on partially filled clusters of every flavour — NUMA and PCI mode,
     shared NICs, switches shared across NUMA nodes, SR-IOV VFs — and on the benchmark clusters."""
     import workload
-    applied = yes = 0
+    applied = yes = masks = entries = 0
     cases = []
     for seed in range(60):
         flavor = ('mixed', 'wild', 'vf', 'big')[seed % 4]
@@ -69,7 +72,18 @@ def test_register_only_predicate_equals_the_general_one(oracle_lib, emu):
             assert np.array_equal(gen[on], k2[on]), (np.flatnonzero(on & (gen != k2))[:5], pod)
             applied += int(on.sum())
             yes += int(k2[on].sum())
+            # and the forms resolve_kernel uses: the three stage masks, the first NIC entry of every NUMA tuple
+            cnt = (ctypes.c_int * 2)()
+            pr = np.ascontiguousarray(pod, dtype=wire.POD_DTYPE).reshape(1)
+            sp = np.ascontiguousarray(speed, dtype='<f8')
+            fr = np.ascontiguousarray(filled, dtype=wire.NODE_DTYPE)
+            emu.nhd_emu_check_k2.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]
+            assert emu.nhd_emu_check_k2(0.9, sp.ctypes.data, len(fr), fr.ctypes.data, pr.ctypes.data, cnt) == 0, pod
+            masks += cnt[0]
+            entries += cnt[1]
     assert applied > 5000 and yes > 500 and applied - yes > 500, (applied, yes)
+    assert masks > 5000 and entries > 10000, (masks, entries)
 
 
 @pytest.mark.parametrize('config', [2, 3, 5])

@@ -283,6 +283,7 @@ def main():
     ap.add_argument('--impl', default='nhd_b200', choices=['nhd_b200', 'reference'])
     ap.add_argument('--cpu-sample-pods', type=int, default=128)
     ap.add_argument('--no-extra', action='store_true', help='skip the side workloads (config 5, heterogeneous, moving clock)')
+    ap.add_argument('--stop-after-e2e', action='store_true', help='developer switch: print value / e2e / clocks only and stop')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
 
@@ -297,7 +298,7 @@ def main():
     import torch
     import torch.distributed as dist
     from nhd_b200 import wire
-    from nhd_b200.solver import Solver, nccl_unique_id, pinned_array
+    from nhd_b200.solver import Solver, nccl_unique_id, pinned_array, shard_min_pairs
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 solver has no CPU fallback')
@@ -393,24 +394,44 @@ def main():
             e2e_t.append(dt)
     e2e_value = P * len(e2e_t) / sum(e2e_t)
     same = all(np.array_equal(out[n], bindings[n]) for n in out.dtype.names if n != 'pad_')
+    if args.stop_after_e2e and world == 1:
+        print(json.dumps({'partial': True, 'value': value, 'e2e_value': e2e_value, 'e2e_ms': [round(1e3 * x, 3) for x in e2e_t],
+                          'clocks': clocks, 'bindings_equal_resident_run': bool(same)}), flush=True)
+        solver.close()
+        return
     h2d = N * wire.NODE_DTYPE.itemsize + n_types * 176 + P * 12
     d2h = P * wire.BINDING_DTYPE.itemsize
 
-    # BASELINE config 5 (262 144 x 8 192, SR-IOV VFs + node groups) on all ranks: a side number, a few solves
-    cfg5_multi = None
-    if world > 1 and not args.no_extra:
+    # side numbers on all ranks, a few solves each (every rank runs the same calls in the same order):
+    #  * BASELINE config 5 (262 144 x 8 192, SR-IOV VFs + node groups): above the sharding threshold
+    #  * config 4 forced onto the node-sharded path: what the exchange costs where the library chooses not to shard
+    def multi_quick(r_, s_, p_, n_, min_pairs=None):
         idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))     # a fresh id: one per handle
         dist.broadcast(idt, 0)
-        r5, s5, p5, n5 = workload.make_workload(5)
-        cfg5_multi = quick_value(Solver, r5, s5, p5, n5, pre_step=barrier, device=local_rank, rank=rank, world_size=world,
-                                 nccl_id=bytes(idt.cpu().numpy().tobytes()))
-        tt = torch.tensor([cfg5_multi['ms']], dtype=torch.float64, device='cuda')
+        old = os.environ.pop('NHD_SHARD_MIN_PAIRS', None)
+        if min_pairs is not None:
+            os.environ['NHD_SHARD_MIN_PAIRS'] = str(min_pairs)          # read when the handle is created
+        try:
+            q = quick_value(Solver, r_, s_, p_, n_, pre_step=barrier, device=local_rank, rank=rank, world_size=world,
+                            nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        finally:
+            os.environ.pop('NHD_SHARD_MIN_PAIRS', None)
+            if old is not None:
+                os.environ['NHD_SHARD_MIN_PAIRS'] = old
+        tt = torch.tensor([q['ms']], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cfg5_multi['ms'] = float(tt.item())
-        cfg5_multi['value'] = len(p5) / (cfg5_multi['ms'] / 1e3)
+        q['ms'] = float(tt.item())
+        q['value'] = len(p_) / (q['ms'] / 1e3)
+        return q
+
+    cfg5_multi = cfg4_forced = None
+    if world > 1 and not args.no_extra:
+        r5, s5, p5, n5 = workload.make_workload(5)
+        cfg5_multi = multi_quick(r5, s5, p5, n5)
         del r5, p5
+        cfg4_forced = multi_quick(recs, speed, pods, now, min_pairs=1)
 
     # every rank ran the identical replicated sweep: their bindings must be byte-identical (digest vs rank 0)
     ranks_agree = True
@@ -490,14 +511,18 @@ def main():
                'host_cores_available': os.cpu_count()}
 
     placed = int((bindings['status'] == 0).sum())
+    min_pairs = shard_min_pairs()
+    sharded = world > 1 and N * n_types >= min_pairs
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': step_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'u64', 'data': 'synthetic',
         'config': {'workload': f'BASELINE config {CONFIG}: {N} nodes x {P} pods, 16 pod types (50% GPU/PCI), '
                                f'30% nodes pre-occupied, constant clock',
-                   'parallelism': f'node-sharded filter x{world} + one NCCL all-gather + replicated sweep' if world > 1
-                   else 'single GPU',
+                   'parallelism': 'single GPU' if world == 1 else
+                   f'node-sharded filter x{world} + one NCCL all-gather + replicated sweep' if sharded else
+                   f'{world} replicas, no collective: {N} nodes x {n_types} pod types is below the sharding threshold '
+                   f'({min_pairs} pairs) — the exchange would cost more than the shards save (extra.config4_forced_sharding)',
                    'l2': 'flushed between steps (256 MiB memset)', 'pods_placed': placed, 'pod_types': n_types},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': 1e3 * sum(e2e_t) / len(e2e_t), 'steps': len(e2e_t),
@@ -536,10 +561,12 @@ def main():
             extra['error'] = str(e)[:200]
     if cfg5_multi is not None:
         extra[f'config5_262144x8192_{world}gpu'] = cfg5_multi
+    if cfg4_forced is not None:
+        extra['config4_forced_sharding'] = dict(cfg4_forced, note='the headline workload with NHD_SHARD_MIN_PAIRS=1: filter shards + all-gather + unpack')
     total_ms = float(np.mean(phase['total_ms']))
     line['amdahl'] = {'filter_share': filter_ms / total_ms,
                       'limit_if_filter_were_free': total_ms / max(total_ms - filter_ms, 1e-9),
-                      'note': 'only the filter shards over GPUs; the sweep (sequential first-fit) is replicated'}
+                      'note': 'only the filter shards over GPUs (and only above nhd_shard_min_pairs); the sweep (sequential first-fit) is replicated'}
     if extra:
         line['extra'] = extra
     if cpu is not None:

@@ -192,6 +192,11 @@ typedef struct nhd_handle nhd_handle;
 
 void    nhd_default_params(nhd_params* p);
 int32_t nhd_nccl_unique_id(uint8_t out[128]);
+/* (nodes x distinct pod types of a batch) from which world_size > 1 handles split the snapshot filter over the ranks
+ * and exchange the results with one all-gather; smaller batches are filtered whole by every rank with no collective
+ * (the reference has no counterpart: it is one process, NHDScheduler.py:43).  NHD_SHARD_MIN_PAIRS in the environment
+ * — the same on every rank — overrides the default (2^21) for handles created afterwards. */
+int64_t nhd_shard_min_pairs(void);
 int32_t nhd_create(const nhd_params* p, nhd_handle** out);
 int32_t nhd_destroy(nhd_handle* h);
 const char* nhd_last_error(const nhd_handle* h);

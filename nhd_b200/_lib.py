@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get('NHD_B200_LIB', 'libnhd_b200.so'))
 
 # every symbol include/nhd_b200.h declares
-EXPORTS = ('nhd_default_params', 'nhd_nccl_unique_id', 'nhd_create', 'nhd_destroy', 'nhd_last_error',
+EXPORTS = ('nhd_default_params', 'nhd_nccl_unique_id', 'nhd_shard_min_pairs', 'nhd_create', 'nhd_destroy', 'nhd_last_error',
            'nhd_validate_node', 'nhd_validate_pod', 'nhd_load_nodes', 'nhd_update_nodes', 'nhd_read_nodes',
            'nhd_snapshot', 'nhd_restore', 'nhd_solve_batch', 'nhd_stage_batch', 'nhd_solve_staged',
            'nhd_fetch_bindings', 'nhd_sync', 'nhd_run_filter_only', 'nhd_last_timing', 'nhd_read_filter',
@@ -51,6 +51,7 @@ def load():
     sig = {
         'nhd_default_params': (None, [ctypes.POINTER(Params)]),
         'nhd_nccl_unique_id': (i32, [vp]),
+        'nhd_shard_min_pairs': (i64, []),
         'nhd_create': (i32, [ctypes.POINTER(Params), ctypes.POINTER(vp)]),
         'nhd_destroy': (i32, [vp]),
         'nhd_last_error': (ctypes.c_char_p, [vp]),

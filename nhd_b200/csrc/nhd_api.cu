@@ -111,6 +111,7 @@ struct nhd_handle {
     ClsFast* d_cls_fast = nullptr;        /* per hardware class */
     double now0 = 0.0;
     bool const_clock = true;
+    long long shard_min_pairs = 1LL << 21;   /* nhd_shard_min_pairs() when the handle was created */
     int n_names = 0;
     uint64_t names_used = 0;
     uint64_t* d_pod_groups = nullptr; size_t pod_groups_cap = 0;
@@ -231,6 +232,26 @@ extern "C" void nhd_default_params(nhd_params* p)
     p->world_size = 1;
 }
 
+/*
+ * Node-sharding threshold: (nodes x distinct pod types) from which the snapshot filter is split over the ranks.
+ * Below it the exchange costs more than the shard saves — measured on B200s over NVSwitch: the whole filter of
+ * 65 536 nodes x 16 types takes 0.047 ms on one GPU, the all-gather + unpack of its bitmaps 0.026 / 0.029 / 0.070 ms
+ * on 2 / 4 / 8 ranks — so every rank filters the whole cluster and no collective runs.  Every rank must use the same
+ * value (it decides whether the collective is entered): NHD_SHARD_MIN_PAIRS in the environment of all ranks, read
+ * when a handle is created; default 2^21.
+ */
+static long long shard_min_pairs_now()
+{
+    const char* e = getenv("NHD_SHARD_MIN_PAIRS");
+    if (e && *e) {
+        char* end = nullptr;
+        const long long v = strtoll(e, &end, 10);
+        if (end && *end == 0 && v >= 0) return v;
+    }
+    return 1LL << 21;
+}
+extern "C" int64_t nhd_shard_min_pairs(void) { return (int64_t)shard_min_pairs_now(); }
+
 extern "C" int32_t nhd_nccl_unique_id(uint8_t out[128])
 {
     if (!out) return NHD_ERR_INVALID;
@@ -306,6 +327,7 @@ extern "C" int32_t nhd_create(const nhd_params* p, nhd_handle** out)
         return NHD_ERR_CUDA;                                    /* no CPU fallback */
     }
     *out = h;
+    h->shard_min_pairs = shard_min_pairs_now();
     CK(cudaSetDevice(p->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, p->device));
@@ -677,12 +699,12 @@ static int32_t solve_staged(nhd_handle* h, bool filter_only)
     /* 1. snapshot predicate kernel over this rank's node shard.  With several ranks every rank filters the nodes
      * of S consecutive super-tiles into its slot of an exchange buffer (their NodeDyn summaries, then their
      * columns of every bitmap row); one all-gather hands every rank all slots, and a small kernel lays them out
-     * as the arrays the (replicated) sweep reads.  Clusters too small for that to pay are filtered whole by
-     * every rank, without any exchange. */
+     * as the arrays the (replicated) sweep reads.  Clusters too small for that to pay (nhd_shard_min_pairs) are
+     * filtered whole by every rank, without any exchange. */
     const int ws = h->params.world_size, rk = h->params.rank;
     const int rows = T + 2 + h->n_names;
     const size_t bm_bytes = (size_t)rows * W * 8;
-    const bool sharded = ws > 1 && h->n_pods > 0 && (long)h->n_nodes * T >= 16384;
+    const bool sharded = ws > 1 && h->n_pods > 0 && (long long)h->n_nodes * T >= h->shard_min_pairs;
     const int S = sharded ? (h->n_super + ws - 1) / ws : h->n_super;
     const int super_lo = sharded ? std::min(rk * S, h->n_super) : 0;
     const int super_hi = sharded ? std::min(super_lo + S, h->n_super) : h->n_super;

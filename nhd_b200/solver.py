@@ -28,6 +28,12 @@ def nccl_unique_id() -> bytes:
     return bytes(buf)
 
 
+def shard_min_pairs() -> int:
+    """(nodes x distinct pod types) from which a world_size > 1 handle created now would node-shard its filter
+    (``nhd_shard_min_pairs``; ``NHD_SHARD_MIN_PAIRS`` in the environment of every rank overrides the default)."""
+    return int(_lib.load().nhd_shard_min_pairs())
+
+
 def pinned_array(n, dtype):
     """numpy array of n records in page-locked host memory (nhd_alloc_pinned): such buffers go to
     and from the device without a staging copy.  Keep the returned array alive while in use."""

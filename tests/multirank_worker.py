@@ -24,7 +24,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     failures = []
-    for cfg, n_nodes, n_pods in ((3, 4096, 384), (5, 8192, 512), (4, None, None)):
+    oracle_cache = {}
+    # (config, nodes, pods, NHD_SHARD_MIN_PAIRS): the small clusters and one run of the full config 4 are forced onto the
+    # node-sharded path (filter shards + all-gather); config 4 also runs at the default threshold, where every rank
+    # filters the whole cluster and no collective is entered
+    for cfg, n_nodes, n_pods, min_pairs in ((3, 4096, 384, '1'), (5, 8192, 512, '1'), (4, None, None, '1'), (4, None, None, None)):
+        os.environ.pop('NHD_SHARD_MIN_PAIRS', None)
+        if min_pairs is not None:
+            os.environ['NHD_SHARD_MIN_PAIRS'] = min_pairs          # read by nhd_create; the same on every rank
         # one communicator per solver handle: a fresh NCCL unique id each time (they are single-use)
         idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
         if rank == 0:
@@ -53,12 +60,14 @@ def main():
             failures.append(f'config {cfg}: rank {rank} differs from rank 0')
         if rank == 0:
             from oracle import binding
-            ob, orecs = binding.solve(recs, speed, pods, now, threads=max(1, os.cpu_count() or 1))
+            if cfg not in oracle_cache:
+                oracle_cache[cfg] = binding.solve(recs, speed, pods, now, threads=max(1, os.cpu_count() or 1))
+            ob, orecs = oracle_cache[cfg]
             if not helpers.binding_bytes_equal(ob, got):
                 failures.append(f'config {cfg}: bindings differ from the oracle: {helpers.first_binding_diff(ob, got)}')
             if orecs.tobytes() != final.tobytes():
                 failures.append(f'config {cfg}: final records differ from the oracle')
-            print(f'config {cfg}: {len(recs)} nodes x {len(pods)} pods on {world} ranks: '
+            print(f'config {cfg} ({"node-sharded" if min_pairs else "default threshold"}): {len(recs)} nodes x {len(pods)} pods on {world} ranks: '
                   f'{"equal to the oracle" if not failures else failures}', flush=True)
     bad = torch.tensor([len(failures)], device='cuda')
     dist.all_reduce(bad)

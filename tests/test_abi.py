@@ -26,7 +26,7 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     text = open(HEADER).read()
-    declared = set(re.findall(r'^\s*(?:int32_t|void|const char\*)\s+(nhd_\w+)\s*\(', text, flags=re.M))
+    declared = set(re.findall(r'^\s*(?:int32_t|int64_t|void|const char\*)\s+(nhd_\w+)\s*\(', text, flags=re.M))
     assert len(declared) >= 18
     assert declared == set(_lib.EXPORTS)
     for name in declared:

@@ -131,8 +131,8 @@ s.close()
 '''
 
 
-@pytest.mark.parametrize('world,config', [(2, 3), (4, 5)])
-def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path, world, config):
+@pytest.mark.parametrize('world,config,min_pairs', [(2, 3, '1'), (4, 5, '1'), (2, 3, None)], ids=['2-cfg3-sharded', '4-cfg5-sharded', '2-cfg3-whole'])
+def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path, world, config, min_pairs):
     """SURVEY 8e on the CPU: ``world`` processes, each with an emulated device and the full cluster, compute
     their shard of the bitmaps, exchange them with one all-gather (tests/emu/fake_nccl: shared memory instead
     of NVLink) and run the identical sweep — every rank must return the oracle's bindings and records."""
@@ -147,11 +147,16 @@ def test_node_sharded_ranks_match_the_oracle(emu_cuda_lib, oracle_lib, tmp_path,
     nodes, pods_n = 1800, 500                                       # 8 super-tiles of 256 nodes: uneven shards for 4 ranks
     code = RANK_CODE % dict(root=ROOT, nccl=nccl, config=config, nodes=nodes, pods=pods_n)
     env = dict(os.environ, NHD_B200_LIB=emu_cuda_lib, NHD_B200_ALLOW_EMULATED='1', EMU_LANE_ORDER='d')
+    env.pop('NHD_SHARD_MIN_PAIRS', None)
+    if min_pairs is not None:
+        env['NHD_SHARD_MIN_PAIRS'] = min_pairs         # clusters this small are filtered whole by every rank otherwise
     procs = [subprocess.Popen([sys.executable, '-c', code, str(r), str(world), str(tmp_path)], cwd=ROOT, env=env,
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
     outs = [p.communicate(timeout=600) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, (o + e)[-2000:]
+        # tables + filter + sweep + resolve + core ids + commit, and the all-gather + unpack only when sharded
+        assert int(o.split('launches')[-1].split()[0]) == (8 if min_pairs is not None else 6), o[-200:]
     recs, speed, pods, now = workload.make_workload(config, n_nodes=nodes, n_pods=pods_n)
     ob, orecs = oracle_lib.solve(recs, speed, pods, now)
     for r in range(world):

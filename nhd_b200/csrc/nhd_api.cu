@@ -204,7 +204,8 @@ static bool tuple_limits_ok(int K, int G)
 
 static inline uint8_t schedulable_numa(const nhd_node_rec& r)
 {
-    return ((r.flags & NHD_NODE_ACTIVE) && !(r.flags & NHD_NODE_MAINTENANCE)) ? (uint8_t)r.n_numa : (uint8_t)0;
+    /* (a record not validated yet may say anything: counts beyond the limit are not counted — the load is rejected) */
+    return ((r.flags & NHD_NODE_ACTIVE) && !(r.flags & NHD_NODE_MAINTENANCE) && r.n_numa <= NHD_MAX_NUMA) ? (uint8_t)r.n_numa : (uint8_t)0;
 }
 
 static void track_numa(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx)
@@ -396,7 +397,8 @@ static bool is_pinned_host(const void* p)
 
 /* host -> device, ingest into the tiled layout, validate on the device, classify.  Records that
  * already sit in pinned memory (nhd_alloc_pinned) are copied straight from the caller's buffer. */
-static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx, int* max_numa)
+static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, const int32_t* idx, int* max_numa,
+                              bool track_while_copying = false)
 {
     const size_t bytes = (size_t)n * sizeof(nhd_node_rec);
     CK(grow_dev(h->d_stage, h->d_stage_cap, bytes));
@@ -420,6 +422,9 @@ static int32_t upload_records(nhd_handle* h, int n, const nhd_node_rec* recs, co
     CK(cudaGetLastError());
     int vres[4];
     CK(cudaMemcpyAsync(vres, h->d_vresult, 16, cudaMemcpyDeviceToHost, h->stream));
+    /* full load: the host's own walk over the records (NUMA bookkeeping) runs while the copy and the validation are in
+     * flight; a rejected load leaves the handle unloaded, and the next load starts that bookkeeping afresh */
+    if (track_while_copying) track_numa(h, n, recs, idx);
     CK(cudaStreamSynchronize(h->stream));
     if (vres[0] != 0x7FFFFFFF) {
         const int32_t v = nhd_validate_node(&recs[vres[0]]);
@@ -472,9 +477,8 @@ extern "C" int32_t nhd_load_nodes(nhd_handle* h, int32_t n_nodes, const nhd_node
     h->numa_hist[0] = n_nodes;
     if (n_nodes == 0) { CK(cudaStreamSynchronize(h->stream)); return NHD_OK; }
     int mx = 1;
-    const int32_t rc = upload_records(h, n_nodes, recs, nullptr, &mx);
+    const int32_t rc = upload_records(h, n_nodes, recs, nullptr, &mx, true);
     if (rc != NHD_OK) { h->loaded = false; return rc; }
-    track_numa(h, n_nodes, recs, nullptr);
     return NHD_OK;
 }
 

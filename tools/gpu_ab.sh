@@ -3,7 +3,8 @@
 # the ncu launch list, the full-size parity tests
 mkdir -p gpurun_out
 : > gpurun_out/ab.txt
-for L in ab/lib_b48d048.so ab/lib_a6dda53.so libnhd_b200.so; do
+# builds of earlier revisions go under nhd_b200/ab/ (nvcc on `git show <rev>:nhd_b200/csrc/...`), named lib_<rev>.so
+for L in $(cd nhd_b200 && ls ab/lib_*.so 2>/dev/null) libnhd_b200.so; do
   NHD_B200_LIB=$L timeout 150 python tools/ab_bench.py 4 >> gpurun_out/ab.txt 2>> gpurun_out/ab_err.log
 done
 cat gpurun_out/ab.txt

@@ -176,11 +176,17 @@ class DeviceCluster:
             self._solver.update_nodes(idx, recs)
             self.delta_nodes += len(idx)
 
-    def solve(self, tops: Sequence, pod_groups: Sequence[Iterable[str]], now: float):
-        """Bindings of ``tops`` scheduled in order on the synced cluster (one GPU call)."""
+    def solve(self, tops: Sequence, pod_groups: Sequence[Iterable[str]], now: float, packed: Sequence = None):
+        """Bindings of ``tops`` scheduled in order on the synced cluster (one GPU call).  ``packed``: records
+        ``pack_pod`` already made of them; only the node-group mask is worked out again (``sync`` may have met new
+        group names since)."""
         pods = np.zeros(len(tops), dtype=wire.POD_DTYPE)
         for i, top in enumerate(tops):
-            packing.pack_pod(top, pod_groups[i], self._layout, out=pods[i])
+            if packed is not None and packed[i] is not None:
+                pods[i] = packed[i]
+                pods[i]['group_mask'] = self._layout.groups_mask(pod_groups[i], create=False)
+            else:
+                packing.pack_pod(top, pod_groups[i], self._layout, out=pods[i])
         self.batches += 1
         self._solver.snapshot()                       # so that rewind() can step back inside this batch
         self._last = (pods, np.full(len(tops), now, dtype='<f8'))
@@ -206,11 +212,11 @@ class DeviceCluster:
 
 class _Pending:
     """One pending pod between the Kubernetes reads and the Kubernetes writes."""
-    __slots__ = ('pos', 'key', 'pobj', 'tcfg', 'top', 'groups', 'ready', 'unsupported')
+    __slots__ = ('pos', 'key', 'pobj', 'tcfg', 'top', 'groups', 'ready', 'unsupported', 'rec')
 
     def __init__(self, pos, key):
         self.pos, self.key = pos, key
-        self.pobj = self.tcfg = self.top = self.groups = self.unsupported = None
+        self.pobj = self.tcfg = self.top = self.groups = self.unsupported = self.rec = None
         self.ready = False
 
 
@@ -373,7 +379,7 @@ class NHDScheduler:
             return
         e.groups = self.k8s.GetPodNodeGroups(podname, ns)
         try:                                         # a request beyond the packed layout (include/nhd_b200.h, NHD_MAX_*)
-            packing.pack_pod(e.top, e.groups, self.cluster.layout)
+            e.rec = packing.pack_pod(e.top, e.groups, self.cluster.layout)     # kept for the solve (group mask aside)
         except packing.UnsupportedError as err:      # cannot be solved here and is never approximated: the pod fails,
             e.unsupported = str(err)                 # loudly, instead of taking the scheduler thread down
 
@@ -477,7 +483,8 @@ class NHDScheduler:
                 out = []
                 while solvable:
                     try:
-                        out = self.cluster.solve([e.top for e in solvable], [e.groups for e in solvable], now)
+                        out = self.cluster.solve([e.top for e in solvable], [e.groups for e in solvable], now,
+                                                 packed=[e.rec for e in solvable])
                         break
                     except Exception as err:
                         # a limit that depends on the cluster as well (numa^(groups+1) tuples, include/nhd_b200.h):

@@ -70,7 +70,7 @@ class ClusterLayout:
 
 
 def _enum_value(x) -> int:
-    return int(getattr(x, 'value', x))
+    return x if type(x) is int else int(getattr(x, 'value', x))
 
 
 def pack_node(node, layout: ClusterLayout, out=None):
@@ -254,14 +254,15 @@ def apply_binding(node, top, b):
         raise IndexError('physical assignment failed on node %s' % node.name)
     if status != wire.PLACED:
         raise RuntimeError('binding has no placement (status %d)' % status)
-    cores = [int(x) for x in b['cores'][:int(b['n_cores'])]]
-    gpus = [int(x) for x in b['gpu_index'][:int(b['n_gpus'])]]
+    cores = b['cores'][:int(b['n_cores'])].tolist()
+    gpus = b['gpu_index'][:int(b['n_gpus'])].tolist()
+    nic_list_index = b['nic_list_index'].tolist()
     ci = gi = 0
     used_nics = []
     for pi, pv in enumerate(top.proc_groups):
         if pv.vlan is not None:
             pv.vlan.vlan = node.data_vlan
-        nic_index = int(b['nic_list_index'][pi])
+        nic_index = nic_list_index[pi]
         nic = node.nics[nic_index]
         for gv in pv.group_gpus:
             dev = node.gpus[gpus[gi]]

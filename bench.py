@@ -540,6 +540,14 @@ def main():
                              'record read once per decision, SURVEY 8d), not DRAM traffic: the sweep keeps its working '
                              'set in shared memory / L2 (traffic = ncu dram bytes per launch) and is bound by the '
                              'latency of the dependent chain on one SM, not by HBM'},
+        'roofline_filter': {
+            'kernel': 'filter_kernel (+ fast_tables_kernel in front of it, inside the same pair of events)', 'bound': 'hbm',
+            'bytes_per_launch': int(N * 128 + (n_types + 2) * N // 8 + N * 32),
+            'achieved': (N * 128 + (n_types + 2) * N // 8 + N * 32) / (filter_ms / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+            'frac': (N * 128 + (n_types + 2) * N // 8 + N * 32) / (filter_ms / 1e3) / 1e9 / peak,
+            'note': 'the one kernel that streams the node records: reads every 128-byte record once, writes the bitmaps and '
+                    'the 32-byte summaries (physical = algorithmic bytes); one wave of CTAs, compute- and launch-bound at '
+                    'this size, not bandwidth-bound'},
         'clocks': clocks,
     }
     # ---------------- side workloads (not the headline; a few solves each) -------------------

@@ -23,6 +23,7 @@ import inspect
 
 _GETTER_PREFIXES = ('Get', 'Is', 'Print')
 _GETTER_NAMES = frozenset(('SMTEnabled', 'PodPresent', 'FormatMac', 'ParseRangeList'))
+_UNPACKED = frozenset(('last_busy_time_seconds',))    # written by the getter IsBusy (Node.py:848); no record field comes from it
 _FLAG = '_nhd_tracked'
 VERSION = '_nhd_version'
 
@@ -61,8 +62,9 @@ def track_changes(cls) -> bool:
 
         def __setattr__(self, name, value, _set=plain_setattr):
             _set(self, name, value)
-            d = self.__dict__
-            d[VERSION] = d.get(VERSION, 0) + 1
+            if name not in _UNPACKED:
+                d = self.__dict__
+                d[VERSION] = d.get(VERSION, 0) + 1
 
         wrapped = {}
         for name, fn in inspect.getmembers(cls, inspect.isfunction):

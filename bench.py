@@ -162,6 +162,16 @@ class ClockSampler:
         return out
 
 
+def host_cpu_model():
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.lower().startswith('model name'):
+                return ln.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     """Threads for the CPU arm: the host cores this process may really use (affinity mask, cgroup CPU quota)."""
     try:
@@ -527,7 +537,9 @@ def main():
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': 1e3 * sum(e2e_t) / len(e2e_t), 'steps': len(e2e_t),
                 'includes': 'cluster records H2D + ingest, pod batch H2D, kernels, bindings D2H',
-                'bindings_equal_resident_run': bool(same)},
+                'bindings_equal_resident_run': bool(same),
+                'note': 'wall clock around host calls: moves with the host (CPU, NUMA placement of the pinned buffers, PCIe)',
+                'host_cpu': host_cpu_model()},
         'gpu_launches': int(launches),
         'kernel_ms': {'filter': filter_ms, 'exchange': float(np.mean(phase['exchange_ms'])), 'sweep': sweep_ms,
                       'wall_per_step_incl_restore_and_flush': 1e3 * wall_s / args.steps},

@@ -172,6 +172,28 @@ def host_cpu_model():
     return None
 
 
+def pin_near_gpu(torch, local_rank):
+    """One process per GPU, run on the CPUs next to that GPU (its PCIe root's NUMA node), as such a process is deployed:
+    the pinned host buffers of the end-to-end leg are then allocated on that node.  Returns (previous affinity, cpus
+    now allowed) or None when the topology cannot be read or nothing would change."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(f'/sys/bus/pci/devices/{bus}/local_cpulist').read().strip().split(','):
+            if part:
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        old = os.sched_getaffinity(0)
+        new = cpus & old
+        if len(new) >= 2 and new != old:
+            os.sched_setaffinity(0, new)
+            return old, len(new)
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     """Threads for the CPU arm: the host cores this process may really use (affinity mask, cgroup CPU quota)."""
     try:
@@ -313,6 +335,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 solver has no CPU fallback')
     torch.cuda.set_device(local_rank)
+    pinned = pin_near_gpu(torch, local_rank)          # before any host buffer is allocated; undone before the CPU legs
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -403,6 +426,11 @@ def main():
         if it >= args.warmup:
             e2e_t.append(dt)
     e2e_value = P * len(e2e_t) / sum(e2e_t)
+    if pinned is not None:
+        try:
+            os.sched_setaffinity(0, pinned[0])           # the CPU baseline legs use every host core again
+        except Exception:
+            pass
     same = all(np.array_equal(out[n], bindings[n]) for n in out.dtype.names if n != 'pad_')
     if args.stop_after_e2e and world == 1:
         print(json.dumps({'partial': True, 'value': value, 'e2e_value': e2e_value, 'e2e_ms': [round(1e3 * x, 3) for x in e2e_t],
@@ -539,7 +567,8 @@ def main():
                 'includes': 'cluster records H2D + ingest, pod batch H2D, kernels, bindings D2H',
                 'bindings_equal_resident_run': bool(same),
                 'note': 'wall clock around host calls: moves with the host (CPU, NUMA placement of the pinned buffers, PCIe)',
-                'host_cpu': host_cpu_model()},
+                'host_cpu': host_cpu_model(),
+                'cpu_affinity': f'the {pinned[1]} CPUs local to the GPU (sysfs local_cpulist)' if pinned else 'unchanged'},
         'gpu_launches': int(launches),
         'kernel_ms': {'filter': filter_ms, 'exchange': float(np.mean(phase['exchange_ms'])), 'sweep': sweep_ms,
                       'wall_per_step_incl_restore_and_flush': 1e3 * wall_s / args.steps},

@@ -121,3 +121,13 @@ def test_emulated_test_build_is_refused_by_the_loader():
     env.pop('NHD_B200_ALLOW_EMULATED', None)
     out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True).stdout
     assert out.strip() == 'REFUSED'
+
+
+def test_shard_threshold_default_and_environment(lib, monkeypatch):
+    """nhd_shard_min_pairs: 2^21 unless NHD_SHARD_MIN_PAIRS holds a non-negative integer (anything else is ignored)."""
+    monkeypatch.delenv('NHD_SHARD_MIN_PAIRS', raising=False)
+    assert lib.nhd_shard_min_pairs() == 1 << 21
+    for text, want in (('1', 1), ('0', 0), ('123456789012', 123456789012), ('abc', 1 << 21), ('-5', 1 << 21), ('', 1 << 21),
+                       ('12x', 1 << 21)):
+        monkeypatch.setenv('NHD_SHARD_MIN_PAIRS', text)
+        assert lib.nhd_shard_min_pairs() == want, text
